@@ -1,0 +1,226 @@
+// Specialised-kernel compilation: generated CUDA source -> sm_100a cubin.
+//
+// The cubin comes from the in-tree cache (gaast_b200/kernel_cache/<key>.cubin,
+// filled at build time for the plans of the shipped workloads and tests) or,
+// for a plan never seen before, from NVRTC found with dlopen.  The key is a hash
+// of the source and the compile options, so a stale entry can never be used.
+// Nothing here needs a device: cubins are built for a named architecture.
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+
+#include "../runtime.hpp"
+
+namespace gaast {
+
+namespace {
+
+using nvrtcProgram = struct _nvrtcProgram*;
+struct Nvrtc {
+    void* handle = nullptr;
+    std::string path, error;
+    int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    int (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*Version)(int*, int*) = nullptr;
+};
+
+Nvrtc& nvrtc() {
+    static Nvrtc n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        std::vector<std::string> names;
+        if (const char* e = std::getenv("GAAST_NVRTC")) names.push_back(e);
+        names.insert(names.end(), {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                                   "/usr/local/cuda/lib64/libnvrtc.so"});
+        for (const auto& nm : names) {
+            n.handle = dlopen(nm.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (n.handle) {
+                n.path = nm;
+                break;
+            }
+        }
+        if (!n.handle) {
+            n.error = "NVRTC not found (tried libnvrtc.so.12 and /usr/local/cuda/lib64; set GAAST_NVRTC)";
+            return;
+        }
+        auto sym = [&](const char* s) {
+            void* p = dlsym(n.handle, s);
+            if (!p && n.error.empty()) n.error = std::string("NVRTC lacks symbol ") + s;
+            return p;
+        };
+        n.CreateProgram = reinterpret_cast<decltype(n.CreateProgram)>(sym("nvrtcCreateProgram"));
+        n.CompileProgram = reinterpret_cast<decltype(n.CompileProgram)>(sym("nvrtcCompileProgram"));
+        n.GetCUBINSize = reinterpret_cast<decltype(n.GetCUBINSize)>(sym("nvrtcGetCUBINSize"));
+        n.GetCUBIN = reinterpret_cast<decltype(n.GetCUBIN)>(sym("nvrtcGetCUBIN"));
+        n.GetProgramLogSize = reinterpret_cast<decltype(n.GetProgramLogSize)>(sym("nvrtcGetProgramLogSize"));
+        n.GetProgramLog = reinterpret_cast<decltype(n.GetProgramLog)>(sym("nvrtcGetProgramLog"));
+        n.DestroyProgram = reinterpret_cast<decltype(n.DestroyProgram)>(sym("nvrtcDestroyProgram"));
+        n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(sym("nvrtcGetErrorString"));
+        n.Version = reinterpret_cast<decltype(n.Version)>(sym("nvrtcVersion"));
+    });
+    return n;
+}
+
+const char* kOptions[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true",
+                          "--extra-device-vectorization"};
+constexpr int kNumOptions = int(sizeof kOptions / sizeof kOptions[0]);
+
+std::string hash_key(const std::string& src) {
+    uint64_t h1 = 1469598103934665603ull, h2 = 0x9E3779B97F4A7C15ull;
+    auto mix = [&](const char* p, size_t n) {
+        for (size_t i = 0; i < n; ++i) {
+            h1 = (h1 ^ uint8_t(p[i])) * 1099511628211ull;
+            h2 = (h2 + uint8_t(p[i])) * 0xD6E8FEB86659FD93ull;
+            h2 ^= h2 >> 32;
+        }
+    };
+    mix(src.data(), src.size());
+    for (const char* o : kOptions) mix(o, std::strlen(o));
+    char buf[40];
+    std::snprintf(buf, sizeof buf, "%016llx%016llx", (unsigned long long)h1, (unsigned long long)h2);
+    return buf;
+}
+
+bool read_file(const std::string& path, std::vector<char>& out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    f.seekg(0, std::ios::end);
+    const std::streamoff n = f.tellg();
+    if (n <= 0) return false;
+    out.resize(size_t(n));
+    f.seekg(0);
+    f.read(out.data(), n);
+    return bool(f);
+}
+
+void write_file_atomic(const std::string& path, const char* data, size_t n) {
+    const std::string tmp = path + ".tmp" + std::to_string(getpid());
+    {
+        std::ofstream f(tmp, std::ios::binary);
+        if (!f) return;
+        f.write(data, std::streamsize(n));
+        if (!f) return;
+    }
+    if (std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
+}
+
+}  // namespace
+
+std::string jit_cache_dir() {
+    if (const char* e = std::getenv("GAAST_KERNEL_CACHE")) return e;
+    Dl_info info;
+    if (dladdr(reinterpret_cast<void*>(&jit_cache_dir), &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        const size_t slash = p.rfind('/');
+        p = slash == std::string::npos ? std::string(".") : p.substr(0, slash);
+        return p + "/kernel_cache";
+    }
+    return "kernel_cache";
+}
+
+bool jit_available(std::string* why) {
+    Nvrtc& n = nvrtc();
+    if (!n.error.empty() || !n.handle) {
+        if (why) *why = n.error;
+        return false;
+    }
+    return true;
+}
+
+std::vector<char> jit_cubin(const CodegenResult& cg, std::string* key_out, std::string* origin, std::string* log_out) {
+    const std::string key = hash_key(cg.source);
+    if (key_out) *key_out = key;
+    const std::string dir = jit_cache_dir();
+    const std::string base = dir + "/" + key;
+    std::vector<char> cubin;
+    if (!std::getenv("GAAST_NO_KERNEL_CACHE") && read_file(base + ".cubin", cubin)) {
+        if (origin) *origin = "cache";
+        return cubin;
+    }
+    Nvrtc& n = nvrtc();
+    if (!n.error.empty() || !n.handle)
+        throw Error(GAAST_ERR_JIT, "no cached cubin for this plan (" + key + ") and " + n.error);
+    mkdir(dir.c_str(), 0755);
+    const std::string src_path = base + ".cu";
+    write_file_atomic(src_path, cg.source.data(), cg.source.size());
+    nvrtcProgram prog = nullptr;
+    int rc = n.CreateProgram(&prog, cg.source.c_str(), src_path.c_str(), 0, nullptr, nullptr);
+    if (rc != 0) throw Error(GAAST_ERR_JIT, std::string("nvrtcCreateProgram: ") + n.GetErrorString(rc));
+    rc = n.CompileProgram(prog, kNumOptions, kOptions);
+    std::string log;
+    size_t log_size = 0;
+    if (n.GetProgramLogSize(prog, &log_size) == 0 && log_size > 1) {
+        log.resize(log_size);
+        n.GetProgramLog(prog, &log[0]);
+    }
+    if (log_out) *log_out = log;
+    if (rc != 0) {
+        n.DestroyProgram(&prog);
+        if (log.size() > 4000) log.resize(4000);
+        throw Error(GAAST_ERR_JIT, std::string("NVRTC compilation failed: ") + n.GetErrorString(rc) + "\n" + log);
+    }
+    size_t size = 0;
+    rc = n.GetCUBINSize(prog, &size);
+    if (rc == 0 && size) {
+        cubin.resize(size);
+        rc = n.GetCUBIN(prog, cubin.data());
+    }
+    n.DestroyProgram(&prog);
+    if (rc != 0 || cubin.empty()) throw Error(GAAST_ERR_JIT, "NVRTC produced no cubin");
+    write_file_atomic(base + ".cubin", cubin.data(), cubin.size());
+    if (origin) *origin = "nvrtc";
+    return cubin;
+}
+
+std::shared_ptr<JitKernel> jit_load(const CodegenResult& cg, const std::vector<char>& cubin) {
+    auto k = std::make_shared<JitKernel>();
+    cudaError_t e = cudaLibraryLoadData(&k->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) throw Error(GAAST_ERR_JIT, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e));
+    e = cudaLibraryGetKernel(&k->kernel, k->lib, cg.kernel_name.c_str());
+    if (e != cudaSuccess) throw Error(GAAST_ERR_JIT, "kernel " + cg.kernel_name + " not found in its cubin");
+    if (!cg.uniform_kernel_name.empty()) {
+        e = cudaLibraryGetKernel(&k->uniform_kernel, k->lib, cg.uniform_kernel_name.c_str());
+        if (e != cudaSuccess) throw Error(GAAST_ERR_JIT, "kernel " + cg.uniform_kernel_name + " not found in its cubin");
+    }
+    k->name = cg.kernel_name;
+    k->threads = cg.threads;
+    k->elems_per_thread = cg.elems_per_thread;
+    k->min_blocks = cg.min_blocks;
+    k->n_uniform = cg.n_uniform;
+    k->smem_bytes = cg.smem_bytes;
+    if (k->smem_bytes > 48 * 1024) {
+        e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k->kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(k->smem_bytes));
+        if (e != cudaSuccess) throw Error(GAAST_ERR_JIT, std::string("cannot reserve shared memory for the batch-sum: ") + cudaGetErrorString(e));
+    }
+    cudaFuncAttributes attr;
+    if (cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(k->kernel)) == cudaSuccess) {
+        k->regs = attr.numRegs;
+        k->local_bytes = attr.localSizeBytes;
+    } else {
+        cudaGetLastError();
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(k->kernel), k->threads, k->smem_bytes) ==
+            cudaSuccess &&
+        per_sm > 0)
+        k->blocks_per_sm = per_sm;
+    else
+        cudaGetLastError();
+    return k;
+}
+
+}  // namespace gaast

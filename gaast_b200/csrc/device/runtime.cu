@@ -1,0 +1,553 @@
+// C ABI of the device side (include/gaast_b200.h): ctx, batch, plan, eval.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "../runtime.hpp"
+
+using gaast::Error;
+
+namespace {
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return;
+    gaast_status st = GAAST_ERR_CUDA;
+    if (e == cudaErrorMemoryAllocation) st = GAAST_ERR_OOM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) st = GAAST_ERR_NO_DEVICE;
+    throw Error(st, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+
+template <class F>
+gaast_status guard(F&& f) {
+    try {
+        f();
+        return GAAST_OK;
+    } catch (const Error& e) {
+        gaast::set_last_error(e.what());
+        return e.status;
+    } catch (const std::bad_alloc&) {
+        gaast::set_last_error("out of host memory");
+        return GAAST_ERR_OOM;
+    } catch (const std::exception& e) {
+        gaast::set_last_error(e.what());
+        return GAAST_ERR_INVALID;
+    }
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cuda_check(cudaSetDevice(dev), "cudaSetDevice");
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+uint32_t rows_of(uint32_t n, uint32_t mask) {
+    uint32_t r = 0;
+    for (uint32_t k = 0; k <= n; ++k)
+        if (mask >> k & 1) r += uint32_t(gaast::binomial(n, k));
+    return r;
+}
+
+template <class T>
+void upload(T*& dst, const std::vector<T>& src, cudaStream_t s) {
+    dst = nullptr;
+    if (src.empty()) return;
+    cuda_check(cudaMalloc(&dst, src.size() * sizeof(T)), "cudaMalloc(plan table)");
+    cuda_check(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s), "upload plan table");
+}
+
+void ensure(double*& p, size_t& cap, size_t want) {
+    if (want <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cuda_check(cudaMalloc(&p, want * sizeof(double)), "cudaMalloc(scratch)");
+    cap = want;
+}
+
+// Fills the stream table of EvalArgs and validates the bound batches.
+void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out, bool need_out,
+                  gaast::EvalArgs& a, uint64_t* broadcast_slots, long long* n_out) {
+    const gaast::DevicePlanHost& h = plan->h;
+    if (n_inputs != h.n_slots) throw Error(GAAST_ERR_SHAPE, "eval: the plan expects " + std::to_string(h.n_slots) + " input batches");
+    if (h.n_slots && !inputs) throw Error(GAAST_ERR_INVALID, "eval: null inputs array");
+    long long n = -1;
+    if (out) {
+        if (out->n != h.n) throw Error(GAAST_ERR_SHAPE, "eval: output batch has another dimension");
+        if (out->mask != h.buffer_masks[0])
+            throw Error(GAAST_ERR_SHAPE, "eval: output batch must carry exactly the root grade set");
+        if (out->broadcast) throw Error(GAAST_ERR_SHAPE, "eval: output batch cannot be a broadcast operand");
+        n = (long long)out->len;
+    } else if (need_out) {
+        throw Error(GAAST_ERR_INVALID, "eval: null output batch");
+    }
+    *broadcast_slots = 0;
+    for (uint32_t s = 0; s < h.n_slots; ++s) {
+        const gaast_batch* b = inputs[s];
+        if (!b) throw Error(GAAST_ERR_INVALID, "eval: null input batch");
+        if (b->n != h.n) throw Error(GAAST_ERR_SHAPE, "eval: input batch has another dimension");
+        if (h.slot_masks[s] & ~b->mask)
+            throw Error(GAAST_ERR_SHAPE, "eval: input batch " + std::to_string(s) + " lacks a grade the plan reads");
+        if (b->broadcast) {
+            *broadcast_slots |= uint64_t(1) << s;
+        } else {
+            if (n < 0) n = (long long)b->len;
+            if ((long long)b->len != n) throw Error(GAAST_ERR_SHAPE, "eval: batch lengths differ");
+        }
+    }
+    if (n < 0) n = 1;  // everything is broadcast: one element
+    *n_out = n;
+    std::memset(&a, 0, sizeof a);
+    for (size_t i = 0; i < h.streams.size(); ++i) {
+        const gaast::Stream& st = h.streams[i];
+        if (st.slot == 0xFFFFFFFFu) {
+            a.sptr[i] = out ? out->grade_ptr[st.grade] : nullptr;
+            a.srow[i] = out ? (long long)out->stride : 0;
+        } else {
+            const gaast_batch* b = inputs[st.slot];
+            a.sptr[i] = b->grade_ptr[st.grade];
+            a.srow[i] = (long long)b->stride;
+            if (b->broadcast) a.bcast[i >> 6] |= 1ull << (i & 63);
+        }
+    }
+    a.n = n;
+    a.consts = plan->d_consts;
+    a.total_cols = int(h.total_cols);
+    a.root_col = int(h.buf_col[0]);
+    a.store_out = out ? 1 : 0;
+}
+
+const char* engine_name(int e) { return e == GAAST_ENGINE_TABLE ? "table" : "specialized"; }
+
+}  // namespace
+
+gaast::JitKernel::~JitKernel() {
+    if (lib) cudaLibraryUnload(lib);
+}
+
+extern "C" {
+
+const char* gaast_version(void) { return "gaast_b200 0.1 (sm_100a)"; }
+
+gaast_status gaast_ctx_create(int device, void* stream, gaast_ctx** out) {
+    return guard([&] {
+        if (!out) throw Error(GAAST_ERR_INVALID, "null output pointer");
+        *out = nullptr;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw Error(GAAST_ERR_NO_DEVICE, std::string("no CUDA device: gaast_b200 has no CPU path (") +
+                                                 (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + ")");
+        if (device < 0 || device >= count) throw Error(GAAST_ERR_NO_DEVICE, "device ordinal out of range");
+        cuda_check(cudaSetDevice(device), "cudaSetDevice");
+        auto ctx = std::make_unique<gaast_ctx>();
+        ctx->device = device;
+        cudaDeviceProp prop;
+        cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->smem_optin = int(prop.sharedMemPerBlockOptin);
+        ctx->cc_major = prop.major;
+        ctx->cc_minor = prop.minor;
+        if (prop.major != 10)
+            throw Error(GAAST_ERR_NO_DEVICE, "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                                                 ": this library carries sm_100a code only");
+        if (stream) {
+            ctx->stream = static_cast<cudaStream_t>(stream);
+        } else {
+            cuda_check(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            ctx->own_stream = true;
+        }
+        *out = ctx.release();
+    });
+}
+
+gaast_status gaast_ctx_destroy(gaast_ctx* ctx) {
+    return guard([&] {
+        if (!ctx) return;
+        if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+        if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
+        if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+    });
+}
+
+gaast_status gaast_ctx_sync(gaast_ctx* ctx) {
+    return guard([&] {
+        if (!ctx) throw Error(GAAST_ERR_INVALID, "null ctx");
+        cuda_check(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    });
+}
+
+void* gaast_ctx_stream(gaast_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+uint64_t gaast_ctx_launch_count(gaast_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------- plan ----
+gaast_status gaast_plan_create(gaast_ctx* ctx, const gaast_plan_desc* desc, gaast_plan** out) {
+    return guard([&] {
+        if (!out) throw Error(GAAST_ERR_INVALID, "null output pointer");
+        *out = nullptr;
+        if (!desc) throw Error(GAAST_ERR_INVALID, "null plan description");
+        auto plan = std::make_unique<gaast_plan>();
+        plan->ctx = ctx;
+        plan->h.build(*desc);
+        if (ctx) {
+            DeviceGuard dg(ctx->device);
+            upload(plan->d_micro, plan->h.micro, ctx->stream);
+            upload(plan->d_chunks, plan->h.chunks, ctx->stream);
+            upload(plan->d_consts, plan->h.const_values, ctx->stream);
+            cuda_check(cudaStreamSynchronize(ctx->stream), "plan upload");
+        }
+        *out = plan.release();
+    });
+}
+
+gaast_status gaast_plan_destroy(gaast_plan* plan) {
+    return guard([&] {
+        if (!plan) return;
+        if (plan->ctx) {
+            DeviceGuard dg(plan->ctx->device);
+            plan->jit.clear();
+            if (plan->pipe) gaast::host_pipe_destroy(plan->pipe);
+            cudaFree(plan->d_micro);
+            cudaFree(plan->d_chunks);
+            cudaFree(plan->d_consts);
+            cudaFree(plan->d_partials);
+            cudaFree(plan->d_ws);
+            cudaFree(plan->d_uniform);
+        }
+        delete plan;
+    });
+}
+
+gaast_status gaast_plan_cost(const gaast_plan* plan, uint64_t broadcast_slots, uint64_t* bytes_per_elem,
+                             uint64_t* flops_per_elem) {
+    return guard([&] {
+        if (!plan) throw Error(GAAST_ERR_INVALID, "null plan");
+        const auto& h = plan->h;
+        uint64_t doubles = 0;
+        for (const auto& st : h.streams) {
+            if (st.slot != 0xFFFFFFFFu && (broadcast_slots >> st.slot & 1)) continue;
+            doubles += st.rows;
+        }
+        if (bytes_per_elem) *bytes_per_elem = 8 * doubles;
+        if (flops_per_elem) *flops_per_elem = 2 * h.total_terms;
+    });
+}
+
+uint32_t gaast_plan_root_mask(const gaast_plan* plan) { return plan ? plan->h.buffer_masks[0] : 0; }
+uint32_t gaast_plan_dim(const gaast_plan* plan) { return plan ? plan->h.n : 0; }
+uint32_t gaast_plan_slot_mask(const gaast_plan* plan, uint32_t slot) {
+    return (plan && slot < plan->h.n_slots) ? plan->h.slot_masks[slot] : 0;
+}
+uint32_t gaast_plan_num_slots(const gaast_plan* plan) { return plan ? plan->h.n_slots : 0; }
+const char* gaast_plan_last_kernel(const gaast_plan* plan) { return plan ? plan->last_kernel.c_str() : ""; }
+
+gaast_status gaast_plan_set_tuning(gaast_plan* plan, int elems_per_thread, int variant) {
+    return guard([&] {
+        if (!plan) throw Error(GAAST_ERR_INVALID, "null plan");
+        plan->force_ept = elems_per_thread;
+        plan->variant = variant;
+    });
+}
+
+size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, char* buf,
+                                size_t cap) {
+    size_t len = 0;
+    gaast_status st = guard([&] {
+        if (!plan) throw Error(GAAST_ERR_INVALID, "null plan");
+        gaast::CodegenOptions opt;
+        opt.broadcast_slots = broadcast_slots;
+        opt.arith = arith;
+        opt.with_sum = with_sum != 0;
+        opt.elems_per_thread = plan->force_ept;
+        opt.variant = plan->variant;
+        gaast::CodegenResult cg = gaast::generate_kernel(plan->h, opt);
+        len = cg.source.size();
+        if (buf && cap) {
+            const size_t ncopy = std::min(cap - 1, len);
+            std::memcpy(buf, cg.source.data(), ncopy);
+            buf[ncopy] = 0;
+        }
+    });
+    return st == GAAST_OK ? len : 0;
+}
+
+gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, int store_out) {
+    return guard([&] {
+        if (!plan) throw Error(GAAST_ERR_INVALID, "null plan");
+        gaast::CodegenOptions opt;
+        opt.broadcast_slots = broadcast_slots;
+        opt.arith = arith;
+        opt.with_sum = with_sum != 0;
+        opt.store_out = store_out != 0;
+        opt.elems_per_thread = plan->force_ept;
+        opt.variant = plan->variant;
+        gaast::CodegenResult cg = gaast::generate_kernel(plan->h, opt);
+        std::string key, origin, log;
+        gaast::jit_cubin(cg, &key, &origin, &log);
+        plan->last_kernel = cg.kernel_name + " key=" + key + " origin=" + origin;
+    });
+}
+
+// --------------------------------------------------------------- batch ----
+static gaast_status batch_make(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
+                               int broadcast, void* const* grade_ptrs, gaast_batch** out) {
+    return guard([&] {
+        if (!out) throw Error(GAAST_ERR_INVALID, "null output pointer");
+        *out = nullptr;
+        if (!ctx) throw Error(GAAST_ERR_INVALID, "null ctx");
+        if (n > GAAST_MAX_DIM) throw Error(GAAST_ERR_INVALID, "dimension above GAAST_MAX_DIM");
+        if (grade_mask & ~((2u << n) - 1)) throw Error(GAAST_ERR_INVALID, "grade mask has grades above n");
+        if (broadcast && len != 1) throw Error(GAAST_ERR_INVALID, "a broadcast batch holds exactly one element");
+        auto b = std::make_unique<gaast_batch>();
+        b->ctx = ctx;
+        b->n = n;
+        b->mask = grade_mask;
+        b->len = len;
+        b->broadcast = broadcast != 0;
+        b->rows = rows_of(n, grade_mask);
+        DeviceGuard dg(ctx->device);
+        if (grade_ptrs) {
+            if (stride < len) throw Error(GAAST_ERR_INVALID, "stride smaller than the batch length");
+            b->stride = stride;
+            uint32_t i = 0;
+            for (uint32_t k = 0; k <= n; ++k)
+                if (grade_mask >> k & 1) {
+                    if (!grade_ptrs[i] && len) throw Error(GAAST_ERR_INVALID, "null grade pointer");
+                    b->grade_ptr[k] = static_cast<double*>(grade_ptrs[i++]);
+                }
+        } else {
+            b->stride = (len + 15) / 16 * 16;  // rows start on 128-byte boundaries
+            if (b->stride == 0) b->stride = 16;
+            const size_t total = size_t(b->rows) * b->stride;
+            if (total) {
+                cuda_check(cudaMalloc(&b->base, total * sizeof(double)), "cudaMalloc(batch)");
+                b->owned = true;
+            }
+            size_t row = 0;
+            for (uint32_t k = 0; k <= n; ++k)
+                if (grade_mask >> k & 1) {
+                    b->grade_ptr[k] = b->base + row * b->stride;
+                    row += gaast::binomial(n, k);
+                }
+        }
+        *out = b.release();
+    });
+}
+
+gaast_status gaast_batch_alloc(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, int broadcast,
+                               gaast_batch** out) {
+    return batch_make(ctx, n, grade_mask, len, 0, broadcast, nullptr, out);
+}
+
+gaast_status gaast_batch_wrap(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
+                              int broadcast, void* const* grade_ptrs, gaast_batch** out) {
+    if (!grade_ptrs) {
+        gaast::set_last_error("null grade pointer array");
+        return GAAST_ERR_INVALID;
+    }
+    return batch_make(ctx, n, grade_mask, len, stride, broadcast, grade_ptrs, out);
+}
+
+gaast_status gaast_batch_free(gaast_batch* b) {
+    return guard([&] {
+        if (!b) return;
+        if (b->owned && b->base) {
+            DeviceGuard dg(b->ctx->device);
+            cudaFree(b->base);
+        }
+        delete b;
+    });
+}
+
+uint64_t gaast_batch_len(const gaast_batch* b) { return b ? b->len : 0; }
+uint64_t gaast_batch_stride(const gaast_batch* b) { return b ? b->stride : 0; }
+uint32_t gaast_batch_grade_mask(const gaast_batch* b) { return b ? b->mask : 0; }
+void* gaast_batch_grade_ptr(const gaast_batch* b, uint32_t grade) {
+    if (!b || grade > b->n || !(b->mask >> grade & 1)) return nullptr;
+    return b->grade_ptr[grade];
+}
+
+static void batch_copy(const gaast_batch* b, uint32_t grade, double* host, uint64_t host_stride, bool to_device) {
+    if (!b) throw Error(GAAST_ERR_INVALID, "null batch");
+    if (grade > b->n || !(b->mask >> grade & 1)) throw Error(GAAST_ERR_SHAPE, "the batch does not hold this grade");
+    if (!host) throw Error(GAAST_ERR_INVALID, "null host pointer");
+    if (host_stride < b->len) throw Error(GAAST_ERR_INVALID, "host stride smaller than the batch length");
+    const size_t rows = gaast::binomial(b->n, grade);
+    if (!rows || !b->len) return;
+    DeviceGuard dg(b->ctx->device);
+    double* dev = b->grade_ptr[grade];
+    if (to_device)
+        cuda_check(cudaMemcpy2DAsync(dev, b->stride * 8, host, host_stride * 8, b->len * 8, rows, cudaMemcpyHostToDevice,
+                                     b->ctx->stream),
+                   "batch upload");
+    else
+        cuda_check(cudaMemcpy2DAsync(host, host_stride * 8, dev, b->stride * 8, b->len * 8, rows, cudaMemcpyDeviceToHost,
+                                     b->ctx->stream),
+                   "batch download");
+}
+
+gaast_status gaast_batch_upload(gaast_batch* b, uint32_t grade, const double* host, uint64_t host_stride) {
+    return guard([&] { batch_copy(b, grade, const_cast<double*>(host), host_stride, true); });
+}
+gaast_status gaast_batch_download(const gaast_batch* b, uint32_t grade, double* host, uint64_t host_stride) {
+    return guard([&] { batch_copy(b, grade, host, host_stride, false); });
+}
+gaast_status gaast_batch_zero(gaast_batch* b) {
+    return guard([&] {
+        if (!b) throw Error(GAAST_ERR_INVALID, "null batch");
+        DeviceGuard dg(b->ctx->device);
+        for (uint32_t k = 0; k <= b->n; ++k)
+            if (b->mask >> k & 1)
+                cuda_check(cudaMemsetAsync(b->grade_ptr[k], 0, gaast::binomial(b->n, k) * b->stride * 8, b->ctx->stream),
+                           "batch zero");
+    });
+}
+
+// ---------------------------------------------------------------- eval ----
+static std::shared_ptr<gaast::JitKernel> get_specialized(gaast_plan* plan, const gaast::CodegenOptions& opt) {
+    auto key = std::make_tuple(opt.broadcast_slots, opt.arith, int(opt.with_sum), int(opt.store_out),
+                               opt.elems_per_thread, opt.variant);
+    auto it = plan->jit.find(key);
+    if (it != plan->jit.end()) return it->second;
+    gaast::CodegenResult cg = gaast::generate_kernel(plan->h, opt);
+    std::string ckey, origin, log;
+    std::vector<char> cubin = gaast::jit_cubin(cg, &ckey, &origin, &log);
+    auto k = gaast::jit_load(cg, cubin);
+    k->key = ckey;
+    k->origin = origin;
+    plan->jit.emplace(key, k);
+    return k;
+}
+
+static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out, double* dev_sum,
+                      bool with_sum, int engine, int arith) {
+    if (!plan) throw Error(GAAST_ERR_INVALID, "null plan");
+    gaast_ctx* ctx = plan->ctx;
+    if (!ctx) throw Error(GAAST_ERR_NO_DEVICE, "this plan was created without a ctx (offline): it cannot be evaluated");
+    if (arith != GAAST_ARITH_FMA && arith != GAAST_ARITH_STRICT) throw Error(GAAST_ERR_INVALID, "unknown arith mode");
+    if (with_sum && !dev_sum) throw Error(GAAST_ERR_INVALID, "eval_sum: null sum pointer");
+    DeviceGuard dg(ctx->device);
+    gaast::EvalArgs a;
+    uint64_t bslots = 0;
+    long long n = 0;
+    bind_streams(plan, inputs, n_inputs, out, !with_sum, a, &bslots, &n);
+    const gaast::DevicePlanHost& h = plan->h;
+    const int sum_cols = int(h.buf_cols[0]);
+    a.n_sum_cols = with_sum ? sum_cols : 0;
+    if (n == 0) {
+        if (with_sum) cuda_check(cudaMemsetAsync(dev_sum, 0, sum_cols * sizeof(double), ctx->stream), "zero sum");
+        return;
+    }
+
+    std::shared_ptr<gaast::JitKernel> jk;
+    if (engine == GAAST_ENGINE_AUTO || engine == GAAST_ENGINE_SPECIALIZED) {
+        if (plan->jit_error.empty() || engine == GAAST_ENGINE_SPECIALIZED) {
+            try {
+                gaast::CodegenOptions opt;
+                opt.broadcast_slots = bslots;
+                opt.arith = arith;
+                opt.with_sum = with_sum;
+                opt.store_out = out != nullptr;
+                opt.elems_per_thread = plan->force_ept;
+                opt.variant = plan->variant;
+                // 128-bit accesses need even strides and 16-byte aligned rows
+                bool aligned = (n % 2 == 0);
+                for (size_t i = 0; i < h.streams.size(); ++i) {
+                    const bool bc = (a.bcast[i >> 6] >> (i & 63)) & 1;
+                    if (bc || !a.sptr[i]) continue;
+                    if ((a.srow[i] & 1) || (reinterpret_cast<uintptr_t>(a.sptr[i]) & 15)) aligned = false;
+                }
+                if (!aligned) opt.elems_per_thread = 1;
+                jk = get_specialized(plan, opt);
+            } catch (const Error& e) {
+                if (engine == GAAST_ENGINE_SPECIALIZED) throw;
+                plan->jit_error = e.what();
+            }
+        }
+        if (!jk && engine == GAAST_ENGINE_SPECIALIZED) throw Error(GAAST_ERR_JIT, plan->jit_error);
+    } else if (engine != GAAST_ENGINE_TABLE) {
+        throw Error(GAAST_ERR_INVALID, "unknown engine");
+    }
+
+    int grid = 0;
+    if (jk) {
+        const long long per_block = (long long)jk->threads * jk->elems_per_thread;
+        const long long blocks = (n + per_block - 1) / per_block;
+        if (blocks > 0x7fffffffLL) throw Error(GAAST_ERR_SHAPE, "batch too long for one launch");
+        grid = int(blocks);
+        if (with_sum) {
+            // the batch-sum epilogue keeps per-block partials: bound the grid, blocks stride over the batch
+            const long long cap = (long long)ctx->sm_count * jk->blocks_per_sm;
+            if (grid > cap) grid = int(cap);
+            ensure(plan->d_partials, plan->partials_cap, size_t(grid) * sum_cols);
+            a.partials = plan->d_partials;
+        }
+        if (jk->n_uniform > 0) {
+            ensure(plan->d_uniform, plan->uniform_cap, size_t(jk->n_uniform));
+            a.uniform = plan->d_uniform;
+            void* params[] = {&a};
+            cuda_check(cudaLaunchKernel(reinterpret_cast<const void*>(jk->uniform_kernel), dim3(1), dim3(32), params, 0,
+                                        ctx->stream),
+                       "launch uniform prologue");
+            ctx->launches++;
+        }
+        void* params[] = {&a};
+        cuda_check(cudaLaunchKernel(reinterpret_cast<const void*>(jk->kernel), dim3(grid), dim3(jk->threads), params, jk->smem_bytes,
+                                    ctx->stream),
+                   "launch specialised kernel");
+        ctx->launches++;
+        char desc[512];
+        std::snprintf(desc, sizeof desc, "%s engine=specialized origin=%s grid=%d block=%d elems/thread=%d regs=%d spill=%zuB key=%s",
+                      jk->name.c_str(), jk->origin.c_str(), grid, jk->threads, jk->elems_per_thread, jk->regs,
+                      jk->local_bytes, jk->key.c_str());
+        plan->last_kernel = desc;
+    } else {
+        gaast::TableLaunch shape = gaast::table_engine_shape(*ctx, h, n, with_sum);
+        grid = shape.grid;
+        const size_t cols = h.total_cols + (with_sum ? sum_cols : 0);
+        if (shape.global_ws) {
+            ensure(plan->d_ws, plan->ws_cap, size_t(grid) * cols * shape.threads);
+            a.ws_global = plan->d_ws;
+        }
+        if (with_sum) {
+            ensure(plan->d_partials, plan->partials_cap, size_t(grid) * sum_cols);
+            a.partials = plan->d_partials;
+        }
+        a.micro = plan->d_micro;
+        a.chunks = plan->d_chunks;
+        a.n_micro = int(h.micro.size());
+        a.n_chunks = int(h.chunks.size());
+        cuda_check(gaast::table_engine_launch(a, shape, arith == GAAST_ARITH_STRICT, with_sum, ctx->stream),
+                   "launch table engine");
+        ctx->launches++;
+        char desc[256];
+        std::snprintf(desc, sizeof desc, "table_engine_kernel engine=table grid=%d block=%d smem=%zu ws=%s", grid,
+                      shape.threads, shape.smem, shape.global_ws ? "global" : "shared");
+        plan->last_kernel = desc;
+    }
+    if (with_sum) {
+        cuda_check(gaast::reduce_partials_launch(plan->d_partials, grid, sum_cols, dev_sum, ctx->stream),
+                   "launch partial-sum reduction");
+        ctx->launches++;
+    }
+    (void)engine_name;
+}
+
+gaast_status gaast_eval(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out, int engine,
+                        int arith) {
+    return guard([&] { eval_impl(plan, inputs, n_inputs, out, nullptr, false, engine, arith); });
+}
+
+gaast_status gaast_eval_sum(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out,
+                            double* dev_sum, int engine, int arith) {
+    return guard([&] { eval_impl(plan, inputs, n_inputs, out, dev_sum, true, engine, arith); });
+}
+
+}  // extern "C"

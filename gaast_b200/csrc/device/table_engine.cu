@@ -1,0 +1,257 @@
+// Table engine: the generic, plan-interpreting evaluator (sm_100a).
+//
+// One thread evaluates one batch element.  The element's buffers -- the
+// reference's cache entries (eval.rs:21-33) -- live in a per-block workspace
+// [total_cols][threads] in shared memory (column-major over threads, so every
+// access is bank-conflict free), or in global memory when the plan is too wide.
+// The block walks the plan's micro-ops in reference execution order.  For a
+// product (eval.rs:77-83) the term table is streamed chunk by chunk into shared
+// memory by the TMA unit (cp.async.bulk + mbarrier, double buffered) while the
+// threads consume the previous chunk; terms are pre-sorted by output slot, so
+// each run accumulates one output in a register, in the reference's term order.
+//
+// This engine is the always-available path: any valid plan runs here.  The
+// specialised engine (codegen.cpp) is the fast path.
+#include <cstdint>
+
+#include "../runtime.hpp"
+
+namespace gaast {
+
+namespace {
+
+constexpr int kStageBytes = int(sizeof(TermChunk));
+constexpr int kBarOffset = 2 * kStageBytes;
+constexpr int kWsOffset = ((kBarOffset + 16) + 127) / 128 * 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on `bar`.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GAAST_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GAAST_DONE;\n"
+        "bra GAAST_WAIT;\n"
+        "GAAST_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <bool kStrict>
+__device__ __forceinline__ double term_acc(double acc, double l, double r, double c) {
+    if (kStrict) return __dadd_rn(acc, __dmul_rn(__dmul_rn(l, r), c));  // eval.rs:82, no contraction
+    return fma(l * c, r, acc);
+}
+
+template <bool kStrict, bool kSum>
+__global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant__ EvalArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TermChunk* stage = reinterpret_cast<TermChunk*>(smem_raw);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + kBarOffset);
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int cols = a.total_cols + (kSum ? a.n_sum_cols : 0);
+    double* ws = a.ws_global ? a.ws_global + size_t(blockIdx.x) * cols * T
+                             : reinterpret_cast<double*>(smem_raw + kWsOffset);
+    double* w = ws + tid;  // column c of this thread's element: w[c * T]
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (kSum)
+        for (int c = 0; c < a.n_sum_cols; ++c) w[size_t(a.total_cols + c) * T] = 0.0;
+    __syncthreads();
+
+    const long long tile_step = (long long)gridDim.x * T;
+    const long long first = (long long)blockIdx.x * T;
+    long long n_tiles = first < a.n ? (a.n - first + tile_step - 1) / tile_step : 0;
+    const long long total_chunks = n_tiles * a.n_chunks;  // chunk loads this block will consume
+    long long q = 0;                                       // running chunk sequence number
+
+    auto issue = [&](long long seq) {  // thread 0 only
+        const int s = int(seq & 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&mbar[s], kStageBytes);
+        tma_bulk_g2s(&stage[s], a.chunks + (seq % a.n_chunks), kStageBytes, &mbar[s]);
+    };
+    if (tid == 0 && total_chunks > 0) issue(0);
+
+    for (long long base = first; base < a.n; base += tile_step) {
+        const long long e = base + tid;
+        const bool active = e < a.n;
+        for (int c = 0; c < a.total_cols; ++c) w[size_t(c) * T] = 0.0;  // init_null_mv, eval.rs:27-30
+
+        for (int m = 0; m < a.n_micro; ++m) {
+            const MicroOp op = a.micro[m];
+            switch (op.kind) {
+                case MK_LOAD_ADD: {  // eval.rs:45-50
+                    const bool bc = (a.bcast[op.a >> 6] >> (op.a & 63)) & 1;
+                    const double* src = a.sptr[op.a] + (long long)op.b * a.srow[op.a] + (bc ? 0 : e);
+                    const long long rs = a.srow[op.a];
+                    for (uint32_t r = 0; r < op.count; ++r) {
+                        double* d = &w[size_t(op.dst_col + r) * T];
+                        const double v = active ? __ldg(src + r * rs) : 0.0;
+                        *d = kStrict ? __dadd_rn(*d, v) : (*d + v);
+                    }
+                    break;
+                }
+                case MK_CONST_ADD:
+                    for (uint32_t r = 0; r < op.count; ++r) {
+                        double* d = &w[size_t(op.dst_col + r) * T];
+                        *d = *d + a.consts[op.a + r];
+                    }
+                    break;
+                case MK_MUL: {  // eval.rs:61-86
+                    const double* wl = w + size_t(op.a) * T;
+                    const double* wr = w + size_t(op.b) * T;
+                    double* wd = w + size_t(op.dst_col) * T;
+                    for (uint32_t ci = 0; ci < op.count; ++ci) {
+                        if (tid == 0 && q + 1 < total_chunks) issue(q + 1);
+                        mbar_wait(&mbar[q & 1], unsigned(q >> 1) & 1);
+                        const TermChunk& ch = stage[q & 1];
+                        const uint32_t n_runs = ch.n_runs;
+                        uint32_t s = ch.run_start[0];
+                        for (uint32_t r = 0; r < n_runs; ++r) {
+                            const uint32_t end = ch.run_start[r + 1];
+                            double* o = wd + size_t(ch.terms[s].out) * T;
+                            double acc = *o;
+                            for (; s < end; ++s) {
+                                const gaast_term t = ch.terms[s];
+                                acc = term_acc<kStrict>(acc, wl[size_t(t.a) * T], wr[size_t(t.b) * T], t.coeff);
+                            }
+                            *o = acc;
+                        }
+                        __syncthreads();  // stage q&1 may be refilled by the load issued next iteration
+                        ++q;
+                    }
+                    break;
+                }
+                case MK_NEG:  // graded.rs:61-65
+                    for (uint32_t r = 0; r < op.count; ++r) {
+                        double* d = &w[size_t(op.dst_col + r) * T];
+                        *d = -*d;
+                    }
+                    break;
+                case MK_INV: {  // eval.rs:107
+                    double* d = &w[size_t(op.dst_col) * T];
+                    *d = __ddiv_rn(1.0, *d);
+                    break;
+                }
+                case MK_SQRT: {  // eval.rs:108
+                    double* d = &w[size_t(op.dst_col) * T];
+                    *d = __dsqrt_rn(*d);
+                    break;
+                }
+                case MK_STORE: {
+                    double* dst = a.sptr[op.a] + (long long)op.b * a.srow[op.a] + e;
+                    const long long rs = a.srow[op.a];
+                    for (uint32_t r = 0; r < op.count; ++r) {
+                        const double v = w[size_t(op.dst_col + r) * T];
+                        if (active && a.store_out) dst[r * rs] = v;
+                        if (kSum && active) {
+                            double* sc = &w[size_t(a.total_cols + (op.dst_col - a.root_col) + r) * T];
+                            *sc = *sc + v;
+                        }
+                    }
+                    break;
+                }
+            }
+        }
+    }
+
+    if (kSum) {
+        // Fixed-order block reduction of the per-thread column sums.
+        __syncthreads();
+        for (int c = tid; c < a.n_sum_cols; c += T) {
+            const double* col = ws + size_t(a.total_cols + c) * T;
+            double s = 0.0;
+            for (int t = 0; t < T; ++t) s += col[t];
+            a.partials[size_t(blockIdx.x) * a.n_sum_cols + c] = s;
+        }
+    }
+}
+
+// out[c] = sum over blocks of partials[b][c], in block order (deterministic).
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int n_blocks, int n_cols,
+                                       double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += partials[size_t(b) * n_cols + c];
+    out[c] = s;
+}
+
+template <bool kStrict, bool kSum>
+cudaError_t launch_t(const EvalArgs& args, const TableLaunch& shape, cudaStream_t stream) {
+    auto k = table_engine_kernel<kStrict, kSum>;
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shape.smem));
+    if (err != cudaSuccess) return err;
+    k<<<shape.grid, shape.threads, shape.smem, stream>>>(args);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+TableLaunch table_engine_shape(const gaast_ctx& ctx, const DevicePlanHost& h, long long n, bool with_sum) {
+    TableLaunch s;
+    const size_t cols = h.total_cols + (with_sum ? h.buf_cols[0] : 0);
+    const size_t avail = ctx.smem_optin > kWsOffset ? size_t(ctx.smem_optin - kWsOffset) : 0;
+    int t = int(avail / (cols * sizeof(double))) / 32 * 32;
+    if (t >= 32) {
+        s.threads = t > 256 ? 256 : t;
+        s.smem = kWsOffset + cols * sizeof(double) * s.threads;
+        s.global_ws = false;
+    } else {
+        s.threads = 128;
+        s.smem = kWsOffset;
+        s.global_ws = true;
+    }
+    long long tiles = (n + s.threads - 1) / s.threads;
+    int per_sm = 1;
+    if (!s.global_ws) {
+        per_sm = int(size_t(ctx.smem_optin) / (s.smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm * s.threads > 2048) per_sm = 2048 / s.threads;
+    } else {
+        per_sm = 4;
+    }
+    long long g = (long long)ctx.sm_count * per_sm;
+    s.grid = int(tiles < g ? (tiles > 0 ? tiles : 1) : g);
+    return s;
+}
+
+cudaError_t table_engine_launch(const EvalArgs& args, const TableLaunch& shape, bool strict, bool with_sum,
+                                cudaStream_t stream) {
+    if (strict) return with_sum ? launch_t<true, true>(args, shape, stream) : launch_t<true, false>(args, shape, stream);
+    return with_sum ? launch_t<false, true>(args, shape, stream) : launch_t<false, false>(args, shape, stream);
+}
+
+cudaError_t reduce_partials_launch(const double* partials, int n_blocks, int n_cols, double* out,
+                                   cudaStream_t stream) {
+    if (n_cols <= 0) return cudaSuccess;
+    reduce_partials_kernel<<<(n_cols + 127) / 128, 128, 0, stream>>>(partials, n_blocks, n_cols, out);
+    return cudaGetLastError();
+}
+
+const char* table_engine_arch() { return "sm_100a"; }
+
+}  // namespace gaast

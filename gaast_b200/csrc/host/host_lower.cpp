@@ -1,0 +1,184 @@
+// Lowering: SpecializedAst -> flat plan (buffers, ordered ops, slot-resolved
+// term tables).  The walk below IS the reference's evaluator control flow
+// (eval.rs:21-115) with every arithmetic action recorded instead of executed,
+// so that replaying the ops in order on zeroed buffers reproduces eval.rs,
+// including in-place quirks and its panics.
+#include "host.hpp"
+
+namespace gaast {
+
+void PlanStorage::seal() {
+    desc.n_buffers = uint32_t(buffer_masks.size());
+    desc.buffer_masks = buffer_masks.data();
+    desc.n_inputs = uint32_t(inputs.size());
+    desc.inputs = inputs.data();
+    desc.n_const_values = uint32_t(const_values.size());
+    desc.const_values = const_values.data();
+    desc.n_ops = uint32_t(ops.size());
+    desc.ops = ops.data();
+    desc.n_terms = uint32_t(terms.size());
+    desc.terms = terms.data();
+    uint32_t slots = 0;
+    for (const auto& in : inputs)
+        if (in.kind == GAAST_INPUT_BATCH) slots = std::max(slots, in.slot + 1);
+    desc.n_slots = slots;
+}
+
+namespace {
+
+struct Lowerer {
+    const SpecializedAst& ast;
+    PlanStorage& out;
+    std::unordered_map<NodeId, uint32_t> buffer_of;     // the reference's cache keys
+    std::unordered_map<uint32_t, uint32_t> plan_input;  // ast input index -> plan input index
+
+    uint32_t input_for(const GradedNode& nd) {
+        auto it = plan_input.find(nd.input_index);
+        if (it != plan_input.end()) return it->second;
+        const ExprNode& leaf = *nd.leaf;
+        gaast_input_desc d{};
+        d.grade_mask = uint32_t(leaf.leaf_grades);
+        if (leaf.op == Op::Input) {
+            d.kind = GAAST_INPUT_BATCH;
+            d.slot = leaf.slot;
+        } else {
+            // Literal: re-sized to C(n,k) per grade.  `add_grades_from` zips the
+            // two slices (graded.rs:73), so a literal built for another
+            // dimension contributes its first min(C(n,k), C(dim,k)) values.
+            d.kind = GAAST_INPUT_CONST;
+            d.const_offset = uint32_t(out.const_values.size());
+            size_t src = 0;
+            for (unsigned k = 0; k < 32; ++k) {
+                if (!(leaf.leaf_grades >> k & 1)) continue;
+                const size_t have = binomial(leaf.leaf_dim, k), want = binomial(ast.n, k);
+                for (size_t i = 0; i < want; ++i) out.const_values.push_back(i < have ? leaf.values[src + i] : 0.0);
+                src += have;
+            }
+        }
+        const uint32_t idx = uint32_t(out.inputs.size());
+        out.inputs.push_back(d);
+        plan_input.emplace(nd.input_index, idx);
+        return idx;
+    }
+
+    void require_grades(uint32_t buf, GradeMask touched, const char* what) {
+        // grade_slice_mut on a grade the result lacks is `unwrap()` on None in
+        // GradeMapMV (graded.rs:191-193): the reference panics.
+        if (touched & ~GradeMask(out.buffer_masks[buf]))
+            throw Error(GAAST_ERR_PANIC, std::string("the reference panics here: ") + what +
+                                             " touches a grade absent from the result buffer");
+    }
+
+    uint32_t store_in_cache(NodeId id) {  // eval.rs:21-33
+        auto it = buffer_of.find(id);
+        if (it != buffer_of.end()) return it->second;
+        const uint32_t buf = uint32_t(out.buffer_masks.size());
+        out.buffer_masks.push_back(uint32_t(ast.arena[id].minimal));
+        buffer_of.emplace(id, buf);
+        add_to_res(buf, id);
+        return buf;
+    }
+
+    void neg(uint32_t buf, GradeMask mask) {
+        if (!mask) return;
+        require_grades(buf, mask, "negate_grade");
+        gaast_op op{};
+        op.kind = GAAST_OP_NEG_GRADES;
+        op.dst = buf;
+        op.mask = uint32_t(mask);
+        out.ops.push_back(op);
+    }
+
+    void add_to_res(uint32_t buf, NodeId id) {  // eval.rs:35-115
+        const GradedNode& nd = ast.arena[id];
+        if (nd.minimal == 0) return;  // :40-43
+        switch (nd.kind) {
+            case GAAST_NODE_GRADED_OBJ: {  // :45-50, graded.rs:67-78
+                const GradeMask add = nd.minimal & nd.leaf->leaf_grades;
+                if (!add) return;
+                require_grades(buf, add, "add_grades_from");
+                gaast_op op{};
+                op.kind = GAAST_OP_ADD_INPUT;
+                op.dst = buf;
+                op.a = input_for(nd);
+                op.mask = uint32_t(add);
+                out.ops.push_back(op);
+                return;
+            }
+            case GAAST_NODE_ADDITION:  // :51-54
+                add_to_res(buf, nd.c0);
+                add_to_res(buf, nd.c1);
+                return;
+            case GAAST_NODE_NEGATION:  // :55-60
+                add_to_res(buf, nd.c0);
+                neg(buf, nd.minimal);
+                return;
+            case GAAST_NODE_PRODUCT: {  // :61-86
+                const uint32_t lb = store_in_cache(nd.c0);
+                const uint32_t rb = store_in_cache(nd.c1);
+                gaast_op op{};
+                op.kind = GAAST_OP_MUL_TERMS;
+                op.dst = buf;
+                op.a = lb;
+                op.b = rb;
+                op.term_begin = uint32_t(out.terms.size());
+                op.term_count = uint32_t(nd.terms.size());
+                const GradeMask lm = out.buffer_masks[lb], rm = out.buffer_masks[rb], dm = out.buffer_masks[buf];
+                GradeMask touched = 0;
+                for (const CompMul& m : nd.terms) {
+                    touched |= GradeMask(1) << m.og;
+                    if (!(dm >> m.og & 1)) break;
+                    gaast_term t{};
+                    t.out = uint16_t(slot_of(ast.n, dm, m.og, m.oi));
+                    t.a = uint16_t(slot_of(ast.n, lm, m.lg, m.li));
+                    t.b = uint16_t(slot_of(ast.n, rm, m.rg, m.ri));
+                    t.coeff = m.coeff;
+                    out.terms.push_back(t);
+                }
+                require_grades(buf, touched, "a product term");
+                out.ops.push_back(op);
+                return;
+            }
+            case GAAST_NODE_REVERSE: {  // :87-94; k == 0 wraps in release builds: no flip (Q2)
+                add_to_res(buf, nd.c0);
+                GradeMask m = 0;
+                for (unsigned k = 1; k < 63; ++k)
+                    if ((nd.minimal >> k & 1) && (k * (k - 1) / 2) % 2 == 1) m |= GradeMask(1) << k;
+                neg(buf, m);
+                return;
+            }
+            case GAAST_NODE_GRADE_INVOLUTION: {  // :95-102
+                add_to_res(buf, nd.c0);
+                neg(buf, nd.minimal & 0xAAAAAAAAAAAAAAAAull);
+                return;
+            }
+            case GAAST_NODE_SCALAR_UNARY_OP: {  // :103-110
+                add_to_res(buf, nd.c0);
+                require_grades(buf, 1, "a scalar unary op");
+                gaast_op op{};
+                op.kind = nd.scalar_op == 0 ? GAAST_OP_SCALAR_INV : GAAST_OP_SCALAR_SQRT;
+                op.dst = buf;
+                out.ops.push_back(op);
+                return;
+            }
+            case GAAST_NODE_GRADE_PROJECTION: add_to_res(buf, nd.c0); return;  // :111
+            case GAAST_NODE_EXPONENTIAL:
+            case GAAST_NODE_LOGARITHM:  // :112-113 todo!()
+                throw Error(GAAST_ERR_UNSUPPORTED, "Exponential / Logarithm evaluation is todo!() in gaast (eval.rs:112-113)");
+        }
+    }
+};
+
+}  // namespace
+
+std::shared_ptr<PlanStorage> lower(const SpecializedAst& ast) {
+    if (ast.n > GAAST_MAX_DIM) throw Error(GAAST_ERR_INVALID, "dimension above GAAST_MAX_DIM");
+    auto ps = std::make_shared<PlanStorage>();
+    ps->desc.n = ast.n;
+    Lowerer lw{ast, *ps, {}, {}};
+    lw.store_in_cache(ast.root);  // buffer 0 == root
+    ps->seal();
+    return ps;
+}
+
+}  // namespace gaast

@@ -1,0 +1,130 @@
+// Internal structures of the device runtime (ctx / batch / plan handles) and
+// the interfaces between its translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "device_plan.hpp"
+#include "eval_args.h"
+
+namespace gaast {
+
+// A kernel specialised for one plan (codegen.cpp), compiled by NVRTC or loaded
+// from the in-tree cubin cache (jit.cpp).
+struct JitKernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;      // per-element kernel
+    cudaKernel_t uniform_kernel = nullptr;  // optional: hoisted broadcast-only prologue (1 thread)
+    std::string name;
+    std::string key;        // cache key (hash of the source + flags)
+    std::string origin;     // "cache" | "nvrtc"
+    int threads = 0;        // block size
+    int elems_per_thread = 1;
+    int min_blocks = 1;
+    int n_uniform = 0;      // doubles the uniform prologue writes
+    size_t smem_bytes = 0;  // dynamic shared memory (batch-sum accumulators)
+    int regs = 0;
+    size_t local_bytes = 0; // spills
+    int blocks_per_sm = 1;
+    ~JitKernel();
+};
+
+struct CodegenOptions {
+    uint64_t broadcast_slots = 0;
+    int arith = GAAST_ARITH_FMA;
+    bool with_sum = false;
+    bool store_out = true;
+    int elems_per_thread = 0;  // 0 = choose
+    int variant = 0;           // GAAST_CODEGEN_* bit flags (tuning knobs; 0 = defaults)
+};
+
+struct CodegenResult {
+    std::string source;
+    std::string kernel_name;
+    std::string uniform_kernel_name;  // empty when nothing was hoisted
+    int threads = 128;
+    int elems_per_thread = 1;
+    int min_blocks = 1;
+    int n_uniform = 0;
+    int n_sum_cols = 0;
+    size_t smem_bytes = 0;
+    std::string notes;  // human-readable summary of the decisions taken
+};
+
+// codegen.cpp: CUDA source of the specialised kernel for a plan.
+CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt);
+
+// jit.cpp: source -> cubin (NVRTC, found with dlopen) with an on-disk cache.
+bool jit_available(std::string* why);
+// Compiles (or finds in the cache) without touching a device.  Returns the cubin.
+std::vector<char> jit_cubin(const CodegenResult& cg, std::string* key, std::string* origin, std::string* log);
+// Loads a cubin on the current device.
+std::shared_ptr<JitKernel> jit_load(const CodegenResult& cg, const std::vector<char>& cubin);
+std::string jit_cache_dir();
+
+// table_engine.cu
+struct TableLaunch {
+    int threads = 0;
+    int grid = 0;
+    size_t smem = 0;
+    bool global_ws = false;
+};
+TableLaunch table_engine_shape(const gaast_ctx& ctx, const DevicePlanHost& h, long long n, bool with_sum);
+cudaError_t table_engine_launch(const EvalArgs& args, const TableLaunch& shape, bool strict, bool with_sum,
+                                cudaStream_t stream);
+cudaError_t reduce_partials_launch(const double* partials, int n_blocks, int n_cols, double* out,
+                                   cudaStream_t stream);
+const char* table_engine_arch();
+
+// host_pipeline.cu
+struct HostPipe;
+void host_pipe_destroy(HostPipe* p);
+
+}  // namespace gaast
+
+struct gaast_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t h2d = nullptr, d2h = nullptr;  // lazily created for gaast_eval_host
+    uint64_t launches = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    int cc_major = 0, cc_minor = 0;
+};
+
+struct gaast_batch {
+    gaast_ctx* ctx = nullptr;
+    uint32_t n = 0, mask = 0;
+    uint64_t len = 0, stride = 0;
+    bool broadcast = false, owned = false;
+    double* base = nullptr;
+    double* grade_ptr[GAAST_MAX_DIM + 1] = {};
+    uint32_t rows = 0;
+};
+
+struct gaast_plan {
+    gaast_ctx* ctx = nullptr;  // null: offline plan (source generation / precompilation only)
+    gaast::DevicePlanHost h;
+    gaast::MicroOp* d_micro = nullptr;
+    gaast::TermChunk* d_chunks = nullptr;
+    double* d_consts = nullptr;
+    double* d_partials = nullptr;
+    size_t partials_cap = 0;
+    double* d_ws = nullptr;  // table engine: global workspace when shared memory is too small
+    size_t ws_cap = 0;
+    double* d_uniform = nullptr;
+    size_t uniform_cap = 0;
+    std::string last_kernel;
+    // specialised kernels, keyed by (broadcast slots, arith, with_sum, store_out, elems/thread, variant)
+    std::map<std::tuple<uint64_t, int, int, int, int, int>, std::shared_ptr<gaast::JitKernel>> jit;
+    std::string jit_error;  // sticky: why the specialised engine is unavailable
+    int variant = 0;
+    int force_ept = 0;
+    gaast::HostPipe* pipe = nullptr;  // device buffer sets of gaast_eval_host
+};

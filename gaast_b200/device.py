@@ -1,0 +1,265 @@
+"""Device side of the host mirror: Ctx, DeviceBatch, Plan.
+
+`DeviceBatch` is the device-resident counterpart of the reference's
+`GradedData` / `GradedDataMut` (src/graded.rs:43-79): one f64 array per grade,
+C(n,k) rows x batch columns, batch innermost.  `Plan.eval` replaces
+`SpecializedAst::eval` (src/eval.rs:12-19) for whole batches.
+
+Everything here calls the C ABI of include/gaast_b200.h.  PyTorch is used only
+as plumbing (device memory for wrapped tensors, the current stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from math import comb
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .expr import SpecializedAst, grade_mask, grades_of
+
+
+class Ctx:
+    """One device + one stream (gaast_ctx)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        out = L.vp()
+        L.check(L.lib.gaast_ctx_create(int(device), L.vp(stream) if stream else None, C.byref(out)))
+        self._h = out
+        self.device = int(device)
+
+    @staticmethod
+    def on_torch_stream(device: int = 0) -> "Ctx":
+        """A ctx launching on a torch stream that is made current, so that
+        torch.cuda.Event timing and torch tensors are stream-ordered with it."""
+        return _torch_stream_ctx(device)
+
+    def sync(self):
+        L.check(L.lib.gaast_ctx_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return L.lib.gaast_ctx_stream(self._h) or 0
+
+    @property
+    def launch_count(self) -> int:
+        return L.lib.gaast_ctx_launch_count(self._h)
+
+    def close(self):
+        h, self._h = self._h, None
+        if h:
+            L.lib.gaast_ctx_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _torch_stream_ctx(device: int) -> Ctx:
+    # torch's default stream is the legacy NULL stream (handle 0), for which
+    # the library would create a private stream: use a real torch stream.
+    import torch
+    torch.cuda.set_device(device)
+    s = torch.cuda.Stream(device)
+    torch.cuda.set_stream(s)
+    ctx = Ctx(device, s.cuda_stream)
+    ctx.torch_stream = s  # keep alive
+    return ctx
+
+
+class DeviceBatch:
+    """gaast_batch: per grade k a [C(n,k)][stride] f64 device array."""
+
+    def __init__(self, handle, ctx: Ctx, n: int, keep=()):
+        self._h = handle
+        self.ctx = ctx
+        self.n = n
+        self._keep = keep
+
+    @staticmethod
+    def alloc(ctx: Ctx, n: int, grades: Iterable[int], length: int, broadcast: bool = False) -> "DeviceBatch":
+        out = L.vp()
+        L.check(L.lib.gaast_batch_alloc(ctx._h, n, grade_mask(grades), int(length), int(broadcast), C.byref(out)))
+        return DeviceBatch(out, ctx, n)
+
+    @staticmethod
+    def wrap_torch(ctx: Ctx, n: int, tensors: Dict[int, "object"], broadcast: bool = False) -> "DeviceBatch":
+        """Wrap caller-owned CUDA float64 tensors {grade: [C(n,k), len]} (row-major)."""
+        grades = sorted(tensors)
+        length, stride = None, None
+        ptrs = []
+        for k in grades:
+            t = tensors[k]
+            assert t.is_cuda and str(t.dtype) == "torch.float64" and t.dim() == 2 and t.shape[0] == comb(n, k)
+            assert t.stride(1) == 1 or t.shape[1] == 1
+            if length is None:
+                length, stride = t.shape[1], (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+            assert t.shape[1] == length
+            if t.shape[0] > 1:
+                assert t.stride(0) == stride, "all grades must share one row stride"
+            ptrs.append(t.data_ptr())
+        arr = (L.vp * len(ptrs))(*ptrs)
+        out = L.vp()
+        L.check(L.lib.gaast_batch_wrap(ctx._h, n, grade_mask(grades), int(length), int(stride), int(broadcast), arr,
+                                       C.byref(out)))
+        return DeviceBatch(out, ctx, n, keep=tuple(tensors.values()))
+
+    @staticmethod
+    def from_host(ctx: Ctx, n: int, data: Dict[int, np.ndarray], broadcast: bool = False) -> "DeviceBatch":
+        """Upload {grade: [C(n,k), len] float64} (a 1-D array is one broadcast element)."""
+        grades = sorted(data)
+        arrs = {k: np.ascontiguousarray(np.asarray(data[k], dtype=np.float64)) for k in grades}
+        for k in grades:
+            if arrs[k].ndim == 1:
+                arrs[k] = arrs[k].reshape(-1, 1)
+        length = arrs[grades[0]].shape[1] if grades else 0
+        b = DeviceBatch.alloc(ctx, n, grades, length, broadcast)
+        for k in grades:
+            b.upload(k, arrs[k])
+        ctx.sync()
+        return b
+
+    @property
+    def length(self) -> int:
+        return L.lib.gaast_batch_len(self._h)
+
+    @property
+    def stride(self) -> int:
+        return L.lib.gaast_batch_stride(self._h)
+
+    def grade_set(self) -> List[int]:  # Graded::grade_set, graded.rs:20-30
+        return grades_of(L.lib.gaast_batch_grade_mask(self._h))
+
+    def grade_ptr(self, k: int) -> int:  # GradedData::grade_slice, graded.rs:46
+        return L.lib.gaast_batch_grade_ptr(self._h, k) or 0
+
+    def upload(self, k: int, host: np.ndarray):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        assert host.ndim == 2 and host.shape[0] == comb(self.n, k)
+        L.check(L.lib.gaast_batch_upload(self._h, k, host.ctypes.data_as(L.vp), host.shape[1]))
+        self.ctx.sync()  # `host` may be a temporary
+
+    def download(self, k: int) -> np.ndarray:
+        out = np.empty((comb(self.n, k), self.length), dtype=np.float64)
+        L.check(L.lib.gaast_batch_download(self._h, k, out.ctypes.data_as(L.vp), out.shape[1]))
+        self.ctx.sync()
+        return out
+
+    def to_host(self) -> Dict[int, np.ndarray]:
+        return {k: self.download(k) for k in self.grade_set()}
+
+    def zero(self):  # GradedDataMut::init_null_mv, graded.rs:55
+        L.check(L.lib.gaast_batch_zero(self._h))
+
+    def free(self):
+        h, self._h = self._h, None
+        if h:
+            L.lib.gaast_batch_free(h)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Plan:
+    """gaast_plan: a lowered SpecializedAst, reusable with new inputs."""
+
+    def __init__(self, ctx: Optional[Ctx], ast: SpecializedAst):
+        self.ctx = ctx
+        self.ast = ast  # owns the plan description
+        out = L.vp()
+        L.check(L.lib.gaast_plan_create(ctx._h if ctx else None, ast.lower(), C.byref(out)))
+        self._h = out
+        self.n = L.lib.gaast_plan_dim(out)
+
+    def root_grades(self) -> List[int]:
+        return grades_of(L.lib.gaast_plan_root_mask(self._h))
+
+    def num_slots(self) -> int:
+        return L.lib.gaast_plan_num_slots(self._h)
+
+    def slot_grades(self, slot: int) -> List[int]:
+        return grades_of(L.lib.gaast_plan_slot_mask(self._h, slot))
+
+    def cost(self, broadcast_slots: int = 0):
+        b, f = L.u64(), L.u64()
+        L.check(L.lib.gaast_plan_cost(self._h, broadcast_slots, C.byref(b), C.byref(f)))
+        return b.value, f.value
+
+    def set_tuning(self, elems_per_thread: int = 0, variant: int = 0):
+        L.check(L.lib.gaast_plan_set_tuning(self._h, elems_per_thread, variant))
+
+    def kernel_source(self, broadcast_slots: int = 0, arith: int = L.ARITH_FMA, with_sum: bool = False) -> str:
+        n = L.lib.gaast_plan_kernel_source(self._h, broadcast_slots, arith, int(with_sum), None, 0)
+        if n == 0:
+            raise L.GaastError(L.ERR_JIT, L.last_error())
+        buf = C.create_string_buffer(n + 1)
+        L.lib.gaast_plan_kernel_source(self._h, broadcast_slots, arith, int(with_sum), buf, n + 1)
+        return buf.value.decode()
+
+    def precompile(self, broadcast_slots: int = 0, arith: int = L.ARITH_FMA, with_sum: bool = False,
+                   store_out: bool = True) -> str:
+        L.check(L.lib.gaast_plan_precompile(self._h, broadcast_slots, arith, int(with_sum), int(store_out)))
+        return self.last_kernel()
+
+    def last_kernel(self) -> str:
+        return (L.lib.gaast_plan_last_kernel(self._h) or b"").decode()
+
+    def alloc_output(self, length: int) -> DeviceBatch:
+        return DeviceBatch.alloc(self.ctx, self.n, self.root_grades(), length)
+
+    def eval(self, inputs: Sequence[DeviceBatch], out: Optional[DeviceBatch] = None, engine: int = L.ENGINE_AUTO,
+             arith: int = L.ARITH_FMA) -> DeviceBatch:
+        """out[i] = expr(inputs[0][i], inputs[1][i], ...); stream-ordered."""
+        if out is None:
+            length = next((b.length for b in inputs if not _is_broadcast(b)), 1)
+            out = self.alloc_output(length)
+        arr = (L.vp * max(1, len(inputs)))(*[b._h for b in inputs])
+        L.check(L.lib.gaast_eval(self._h, arr, len(inputs), out._h, engine, arith))
+        return out
+
+    def eval_sum(self, inputs: Sequence[DeviceBatch], dev_sum_ptr: int, out: Optional[DeviceBatch] = None,
+                 engine: int = L.ENGINE_AUTO, arith: int = L.ARITH_FMA):
+        arr = (L.vp * max(1, len(inputs)))(*[b._h for b in inputs])
+        L.check(L.lib.gaast_eval_sum(self._h, arr, len(inputs), out._h if out else None, L.vp(dev_sum_ptr), engine,
+                                     arith))
+
+    def eval_host(self, host_in: Sequence[np.ndarray], in_grades: Sequence[Iterable[int]],
+                  in_broadcast: Sequence[bool], length: int, host_out: np.ndarray, host_stride: Optional[int] = None,
+                  engine: int = L.ENGINE_AUTO, arith: int = L.ARITH_FMA):
+        """Host arrays in / out (see gaast_eval_host).  Arrays are [rows][host_stride] float64."""
+        n_in = len(host_in)
+        ptrs = (L.vp * max(1, n_in))(*[_host_ptr(a) for a in host_in])
+        masks = (L.u32 * max(1, n_in))(*[grade_mask(g) for g in in_grades])
+        bc = (C.c_int * max(1, n_in))(*[int(bool(x)) for x in in_broadcast])
+        stride = int(host_stride if host_stride is not None else length)
+        L.check(L.lib.gaast_eval_host(self._h, ptrs, masks, bc, n_in, int(length), stride, L.vp(_host_ptr(host_out)),
+                                      engine, arith))
+
+    def free(self):
+        h, self._h = self._h, None
+        if h:
+            L.lib.gaast_plan_destroy(h)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _is_broadcast(b: DeviceBatch) -> bool:
+    return False if b.length != 1 else True
+
+
+def _host_ptr(a) -> int:
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return int(a)

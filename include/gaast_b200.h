@@ -1,0 +1,223 @@
+/* gaast_b200.h -- C ABI of the B200-native batched evaluator for gaast's phase 4.
+ *
+ * This is the drop-in boundary: what a `gaast-b200-sys` Rust FFI crate binds
+ * (INTEGRATION.md shows the `extern "C"` block).  It replaces, for BATCHES of
+ * multivectors resident on the device, the reference's
+ *
+ *     SpecializedAst<T>::eval::<R>() -> R                 src/eval.rs:12-19
+ *       store_in_cache / add_to_res                        src/eval.rs:21-115
+ *       the term loop  res += l * r * coeff                src/eval.rs:77-83
+ *     GradedData::grade_slice / GradedDataMut::*           src/graded.rs:43-79
+ *
+ * Everything here is plain C: opaque handles, pointers and sizes.  No call
+ * unwinds; every call returns a gaast_status and records a message readable
+ * with gaast_last_error().  There is NO CPU fallback: without a CUDA device
+ * gaast_ctx_create() fails with GAAST_ERR_NO_DEVICE.
+ *
+ * Threading: handles are thread-compatible (no internal locking on the hot
+ * path); use one ctx per host thread / device.  A plan is immutable after
+ * creation and may be evaluated any number of times with new inputs -- the
+ * "precompiled AST reused with new inputs" the reference's README:80-83 asks for.
+ */
+#ifndef GAAST_B200_H
+#define GAAST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAAST_MAX_DIM 16u /* vector-space dimension n; 2^n <= 65536 blade slots */
+
+typedef enum gaast_status {
+    GAAST_OK = 0,
+    GAAST_ERR_INVALID = 1,     /* malformed argument / plan */
+    GAAST_ERR_UNSUPPORTED = 2, /* Exponential / Logarithm: todo!() in eval.rs:112-113 */
+    GAAST_ERR_PANIC = 3,       /* the reference would panic on this AST (unwrap/assert) */
+    GAAST_ERR_NO_DEVICE = 4,   /* no CUDA device: the product path refuses to run */
+    GAAST_ERR_CUDA = 5,
+    GAAST_ERR_OOM = 6,
+    GAAST_ERR_JIT = 7,         /* NVRTC unavailable or compilation failed */
+    GAAST_ERR_SHAPE = 8        /* batch does not match what the plan expects */
+} gaast_status;
+
+/* ------------------------------------------------------------------ plan --
+ * The flat, grade-blocked lowering of a SpecializedAst that gaast's
+ * specialize.rs emits on the host (in this repo: gaast_b200_host.h does it).
+ *
+ * Buffers  = the reference's cache entries: the root and every product operand
+ *            (eval.rs:21-33, 67-68), each with its minimal grade set.  A buffer
+ *            stores, for the grades of its mask in ascending order, C(n,k)
+ *            components each; a component's position in that concatenation is
+ *            its SLOT.  Buffer 0 is the root.
+ * Ops      = the reference's execution trace of add_to_res, in order.  Running
+ *            them in order on zero-initialised buffers reproduces eval.rs
+ *            exactly, including its in-place quirks.
+ * Terms    = IndividualCompMul (ast/base_types.rs:46-55) with (grade, index)
+ *            already resolved to slots, in the reference's emission order
+ *            (specialize.rs:162-183).
+ */
+typedef struct gaast_term {
+    uint16_t out;   /* slot in the op's dst buffer   */
+    uint16_t a;     /* slot in the op's left buffer  */
+    uint16_t b;     /* slot in the op's right buffer */
+    uint16_t flags; /* reserved, 0 */
+    double coeff;   /* signed metric coefficient (algebra.rs:73-83) */
+} gaast_term;       /* 16 bytes */
+
+typedef enum gaast_op_kind {
+    GAAST_OP_ADD_INPUT = 0,  /* dst += input[a] on grades `mask`      eval.rs:45-50 */
+    GAAST_OP_MUL_TERMS = 1,  /* dst += sum terms(left=a, right=b)     eval.rs:61-86 */
+    GAAST_OP_NEG_GRADES = 2, /* dst = -dst on grades `mask`           eval.rs:55-60,87-102 */
+    GAAST_OP_SCALAR_INV = 3, /* dst[grade 0] = 1/dst[grade 0]         eval.rs:103-110 */
+    GAAST_OP_SCALAR_SQRT = 4 /* dst[grade 0] = sqrt(dst[grade 0])     eval.rs:103-110 */
+} gaast_op_kind;
+
+typedef struct gaast_op {
+    uint32_t kind;       /* gaast_op_kind */
+    uint32_t dst;        /* destination buffer */
+    uint32_t a;          /* ADD_INPUT: input index; MUL_TERMS: left buffer */
+    uint32_t b;          /* MUL_TERMS: right buffer */
+    uint32_t mask;       /* ADD_INPUT / NEG_GRADES: grade mask */
+    uint32_t term_begin; /* MUL_TERMS: range in `terms` */
+    uint32_t term_count;
+    uint32_t reserved;
+} gaast_op;              /* 32 bytes */
+
+typedef enum gaast_input_kind {
+    GAAST_INPUT_BATCH = 0, /* bound at eval time: inputs[slot] */
+    GAAST_INPUT_CONST = 1  /* literal carried by the plan (basis vectors, scalars) */
+} gaast_input_kind;
+
+typedef struct gaast_input_desc {
+    uint32_t kind;         /* gaast_input_kind */
+    uint32_t grade_mask;   /* grades the GradedObj holds (its Graded::grade_set) */
+    uint32_t slot;         /* BATCH: index into the `inputs` array given to eval */
+    uint32_t const_offset; /* CONST: first value in `const_values` (grades ascending) */
+} gaast_input_desc;
+
+typedef struct gaast_plan_desc {
+    uint32_t n;                       /* vector-space dimension */
+    uint32_t n_buffers;
+    const uint32_t* buffer_masks;     /* [n_buffers] minimal grade sets; [0] = root */
+    uint32_t n_inputs;
+    const gaast_input_desc* inputs;   /* [n_inputs] */
+    uint32_t n_const_values;
+    const double* const_values;
+    uint32_t n_ops;
+    const gaast_op* ops;              /* [n_ops] in reference execution order */
+    uint32_t n_terms;
+    const gaast_term* terms;          /* [n_terms] */
+    uint32_t n_slots;                 /* number of distinct BATCH slots eval expects */
+    uint32_t reserved;
+} gaast_plan_desc;
+
+/* ------------------------------------------------------------- handles ---- */
+typedef struct gaast_ctx gaast_ctx;     /* one device + one stream */
+typedef struct gaast_plan gaast_plan;   /* validated plan + its device tables + compiled kernels */
+typedef struct gaast_batch gaast_batch; /* device-resident SoA batch: one f64 array per grade */
+
+/* Evaluation engines (all run on the GPU; there is no host engine). */
+typedef enum gaast_engine {
+    GAAST_ENGINE_AUTO = 0,        /* specialised if NVRTC is usable, else table */
+    GAAST_ENGINE_TABLE = 1,       /* generic table-driven kernels compiled into this library */
+    GAAST_ENGINE_SPECIALIZED = 2  /* straight-line sm_100a kernel generated from the plan */
+} gaast_engine;
+
+typedef enum gaast_arith {
+    GAAST_ARITH_FMA = 0,   /* one DFMA per term (default; within 1e-12 of eval.rs) */
+    GAAST_ARITH_STRICT = 1 /* (l*r)*coeff then add, reference order: bit-identical to eval.rs */
+} gaast_arith;
+
+/* Last error message of the calling thread (never NULL). */
+const char* gaast_last_error(void);
+/* Library version string, and the CUDA arch the embedded kernels were built for. */
+const char* gaast_version(void);
+
+/* ctx: `stream` is a cudaStream_t (or NULL for a private non-blocking stream). */
+gaast_status gaast_ctx_create(int device, void* stream, gaast_ctx** out);
+gaast_status gaast_ctx_destroy(gaast_ctx* ctx);
+gaast_status gaast_ctx_sync(gaast_ctx* ctx);
+void* gaast_ctx_stream(gaast_ctx* ctx);
+/* Counts kernel launches issued by this library on `ctx` since creation. */
+uint64_t gaast_ctx_launch_count(gaast_ctx* ctx);
+
+/* plan: validates `desc` (copying everything it needs) and uploads its tables.
+ * ctx may be NULL for an offline plan (kernel_source / precompile only). */
+gaast_status gaast_plan_create(gaast_ctx* ctx, const gaast_plan_desc* desc, gaast_plan** out);
+gaast_status gaast_plan_destroy(gaast_plan* plan);
+/* Algorithmic bytes and flops per batch element: 8 x (f64 read
+ * from non-broadcast inputs in the grades the plan reads + f64 written in the
+ * root grades) and 2 x terms.  `broadcast_slots` bit s = slot s is broadcast. */
+gaast_status gaast_plan_cost(const gaast_plan* plan, uint64_t broadcast_slots, uint64_t* bytes_per_elem,
+                             uint64_t* flops_per_elem);
+uint32_t gaast_plan_root_mask(const gaast_plan* plan);
+uint32_t gaast_plan_dim(const gaast_plan* plan);
+uint32_t gaast_plan_num_slots(const gaast_plan* plan);
+/* Grades of batch slot `slot` that the plan actually reads. */
+uint32_t gaast_plan_slot_mask(const gaast_plan* plan, uint32_t slot);
+/* CUDA source of the specialised kernel for this plan (for inspection / offline
+ * nvcc -Xptxas -v); returns the length, copies at most `cap` bytes (NUL-terminated). */
+size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, char* buf,
+                                size_t cap);
+/* Generates and compiles the specialised kernel into the in-tree cubin cache
+ * without a device (the plan may have been created with ctx == NULL).  Used
+ * by the build step so that the shipped workloads never compile at run time. */
+gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, int store_out);
+/* Tuning knobs of the specialised engine: elements per thread (0 = choose,
+ * 1, or 2 = 128-bit accesses) and emission-policy bits (0 = choose). */
+gaast_status gaast_plan_set_tuning(gaast_plan* plan, int elems_per_thread, int variant);
+
+/* batch: the device-resident counterpart of GradedData (graded.rs:43-47): for
+ * every grade k of `grade_mask` one f64 array of C(n,k) rows x `len` columns,
+ * batch-innermost (element i of component c at rows[c * stride + i]).
+ * len == 1 with broadcast != 0 makes a shared operand (batch stride 0). */
+gaast_status gaast_batch_alloc(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, int broadcast,
+                               gaast_batch** out);
+/* Wrap caller-owned device arrays (e.g. another library's allocation): one
+ * pointer per grade of the mask, ascending, each [C(n,k)][stride] f64. */
+gaast_status gaast_batch_wrap(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
+                              int broadcast, void* const* grade_ptrs, gaast_batch** out);
+gaast_status gaast_batch_free(gaast_batch* b);
+uint64_t gaast_batch_len(const gaast_batch* b);
+uint64_t gaast_batch_stride(const gaast_batch* b);
+uint32_t gaast_batch_grade_mask(const gaast_batch* b);
+/* Device pointer of grade k's [C(n,k)][stride] array (GradedData::grade_slice). */
+void* gaast_batch_grade_ptr(const gaast_batch* b, uint32_t grade);
+/* Stream-ordered copies of one grade: host array is [C(n,k)][host_stride]. */
+gaast_status gaast_batch_upload(gaast_batch* b, uint32_t grade, const double* host, uint64_t host_stride);
+gaast_status gaast_batch_download(const gaast_batch* b, uint32_t grade, double* host, uint64_t host_stride);
+/* GradedDataMut::init_null_mv: zero every grade. */
+gaast_status gaast_batch_zero(gaast_batch* b);
+
+/* eval: out[i] = expr(inputs[0][i], inputs[1][i], ...) for i in [0, len).
+ * `inputs` has plan.n_slots entries; `out` must carry exactly the plan's root
+ * grade set.  Stream-ordered, asynchronous. */
+gaast_status gaast_eval(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out,
+                        int engine, int arith);
+
+/* Batch-sum node (no reference definition: gaast has no batches): evaluates the
+ * plan and reduces the root over the batch on the device, writing
+ * sum_i out[i] as [root comps] f64 to `dev_sum` (device memory).  The
+ * reduction is fused in the kernel epilogue; per-CTA partials are then added
+ * in a fixed order, so the result is deterministic for a given launch shape.
+ * `out` may be NULL to skip materialising the per-element result. */
+gaast_status gaast_eval_sum(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out,
+                            double* dev_sum, int engine, int arith);
+
+/* End-to-end convenience used for the `e2e` measurement: host arrays in, host
+ * arrays out, chunked so that H2D, kernels and D2H overlap.  host_in[s] points
+ * to [comps of slot s][host_stride] (grades ascending), host_out likewise. */
+gaast_status gaast_eval_host(gaast_plan* plan, const double* const* host_in, const uint32_t* in_masks,
+                             const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
+                             double* host_out, int engine, int arith);
+
+/* Name and launch shape of the kernel the last gaast_eval on this plan used. */
+const char* gaast_plan_last_kernel(const gaast_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAAST_B200_H */

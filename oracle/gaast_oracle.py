@@ -121,7 +121,13 @@ class GradeSet:
         return k >= 0 and bool((self.bits >> k) & 1)
 
     def includes(self, other: "GradeSet") -> bool:  # :149-151
-        return (self.bits | other.bits) == self.bits
+        # `(self.bv.clone() | other.bv) == self.bv`: BitVec `|` keeps the LEFT
+        # operand's length and drops the right operand's excess bits (which is
+        # why `Add` sorts by length and `AddAssign` says "Using |= won't work,
+        # as self may be smaller than rhs", :287-300).  So grades of `other` at
+        # or above self's length are NOT checked.
+        low = other.bits & ((1 << self.length) - 1)
+        return (self.bits | low) == self.bits
 
     def is_just(self, k: int) -> bool:  # :154-156
         return self.contains(k) and self.is_single()

@@ -1,0 +1,135 @@
+"""Shared test helpers (TEST INFRASTRUCTURE).
+
+* `oracle_eval`   evaluate a workload-style expression with the CPU oracle
+                  (oracle/gaast_oracle.py) on numpy batches.
+* `run_plan_numpy` a literal numpy executor of a LOWERED plan (buffers, ops,
+                  slot-resolved terms), used to check the host mirror + lowering
+                  against the oracle on the CPU, without any CUDA.
+* tolerance helpers for the f64 parity bar of BASELINE.json (1e-12 relative).
+"""
+from __future__ import annotations
+
+from math import comb
+from typing import Callable, Dict, List, Sequence
+
+import numpy as np
+
+from oracle import gaast_oracle as go
+
+REL_TOL = 1e-12  # north_star: "within 1e-12 relative error in f64"
+
+
+def oracle_expr(build: Callable, inputs: Sequence[Dict[int, np.ndarray]], broadcast: Sequence[bool]):
+    """Build the oracle's expression for `build(*leaves)`; batch leaves are
+    (C, B) arrays, broadcast leaves (C,) arrays."""
+    leaves = []
+    for data, bc in zip(inputs, broadcast):
+        m = {k: (np.asarray(v)[:, 0] if bc else np.asarray(v)) for k, v in data.items()}
+        leaves.append(go.mv(go.GradeMapMV(m)))
+    return build(*leaves)
+
+
+def oracle_eval(build: Callable, metric: Sequence[float], inputs, broadcast, batch: int) -> Dict[int, np.ndarray]:
+    ast = oracle_expr(build, inputs, broadcast).specialize(go.Algebra(metric))
+    res = ast.eval(batch)
+    out = {}
+    for k, v in res.m.items():
+        out[k] = v if v.ndim == 2 else np.repeat(v[:, None], batch, 1)
+    return out
+
+
+def oracle_abs_scale(build: Callable, metric, inputs, broadcast, batch: int) -> Dict[int, np.ndarray]:
+    """Sum of |terms| per output component: the oracle evaluated with every
+    input replaced by its absolute value and every coefficient by |coeff|
+    (tolerance is relative to max(|result|, sum |l*r*coeff|))."""
+    abs_in = [{k: np.abs(v) for k, v in d.items()} for d in inputs]
+    ast = oracle_expr(build, abs_in, broadcast).specialize(go.Algebra(metric))
+    for node in ast.arena.values():
+        for m in node.ast_node.individual_comp_muls:
+            m.coeff = abs(m.coeff)
+    # sign flips and 1/x keep magnitudes; evaluate as is
+    res = _eval_abs(ast, batch)
+    return {k: (v if v.ndim == 2 else np.repeat(v[:, None], batch, 1)) for k, v in res.m.items()}
+
+
+def _eval_abs(ast, batch):
+    saved = go.GradeMapMV.negate_grade
+    go.GradeMapMV.negate_grade = lambda self, k: None  # magnitudes only: sign flips are no-ops
+    try:
+        res = go.eval_specialized(ast, batch)
+    finally:
+        go.GradeMapMV.negate_grade = saved
+    return go.GradeMapMV({k: np.abs(v) for k, v in res.m.items()})
+
+
+def assert_close(got: Dict[int, np.ndarray], want: Dict[int, np.ndarray], scale: Dict[int, np.ndarray] = None,
+                 rel: float = REL_TOL, what: str = ""):
+    assert sorted(got) == sorted(want), f"{what}: grade sets differ: {sorted(got)} vs {sorted(want)}"
+    for k in want:
+        g, w = np.asarray(got[k]), np.asarray(want[k])
+        assert g.shape == w.shape, f"{what}: grade {k}: shape {g.shape} vs {w.shape}"
+        ref = np.abs(w)
+        if scale is not None:
+            ref = np.maximum(ref, np.abs(scale[k]))
+        err = np.abs(g - w)
+        bad = err > rel * ref + 1e-300
+        assert not bad.any(), (f"{what}: grade {k}: {int(bad.sum())} components off; worst abs err "
+                               f"{err.max():.3e} at scale {ref.flat[err.argmax()]:.3e}")
+
+
+def assert_bit_exact(got: Dict[int, np.ndarray], want: Dict[int, np.ndarray], what: str = ""):
+    assert sorted(got) == sorted(want), f"{what}: grade sets differ"
+    for k in want:
+        g = np.ascontiguousarray(got[k], dtype=np.float64).view(np.uint64)
+        w = np.ascontiguousarray(want[k], dtype=np.float64).view(np.uint64)
+        # +0.0 and -0.0 compare equal in the reference's assert_eq! on f64
+        same = (g == w) | ((np.asarray(got[k]) == 0.0) & (np.asarray(want[k]) == 0.0))
+        assert same.all(), f"{what}: grade {k}: {int((~same).sum())} components differ bitwise"
+
+
+# ---- numpy executor of a lowered plan ---------------------------------------------
+def run_plan_numpy(plan: Dict, inputs: Sequence[Dict[int, np.ndarray]], batch: int) -> Dict[int, np.ndarray]:
+    """Executes plan_dict() literally: zeroed buffers, ops in order, (l*r)*coeff
+    then + per term.  inputs[slot] = {grade: (C, B) or (C, 1)}."""
+    n = plan["n"]
+    gd = [comb(n, k) for k in range(n + 1)]
+
+    def grades(mask):
+        return [k for k in range(n + 1) if mask >> k & 1]
+
+    def col0(mask, k):
+        return sum(gd[j] for j in grades(mask) if j < k)
+
+    bufs = [np.zeros((sum(gd[k] for k in grades(m)), batch)) for m in plan["buffer_masks"]]
+    consts = plan["const_values"]
+    for kind, dst, a, b, mask, tb, tc in plan["ops"]:
+        if kind == 0:  # ADD_INPUT
+            ikind, imask, slot, coff = plan["inputs"][a]
+            off = coff
+            for k in grades(imask):
+                if mask >> k & 1:
+                    c0 = col0(plan["buffer_masks"][dst], k)
+                    if ikind == 0:
+                        src = np.asarray(inputs[slot][k])
+                        if src.ndim == 1:
+                            src = src[:, None]
+                    else:
+                        src = np.array(consts[off:off + gd[k]])[:, None]
+                    bufs[dst][c0:c0 + gd[k]] = bufs[dst][c0:c0 + gd[k]] + src
+                off += gd[k]
+        elif kind == 1:  # MUL_TERMS
+            for out, ta, tbb, coeff in plan["terms"][tb:tb + tc]:
+                bufs[dst][out] = bufs[dst][out] + bufs[a][ta] * bufs[b][tbb] * coeff
+        elif kind == 2:  # NEG_GRADES
+            for k in grades(mask):
+                c0 = col0(plan["buffer_masks"][dst], k)
+                bufs[dst][c0:c0 + gd[k]] = -bufs[dst][c0:c0 + gd[k]]
+        elif kind in (3, 4):
+            c0 = col0(plan["buffer_masks"][dst], 0)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                bufs[dst][c0] = 1.0 / bufs[dst][c0] if kind == 3 else np.sqrt(bufs[dst][c0])
+    out, c = {}, 0
+    for k in grades(plan["buffer_masks"][0]):
+        out[k] = bufs[0][c:c + gd[k]]
+        c += gd[k]
+    return out
