@@ -130,8 +130,8 @@ extern "C" gaast_status gaast_eval_host(gaast_plan* plan, const double* const* h
                 gaast_batch* b = p->in[set][s];
                 const uint32_t rows = rows_of(h.n, in_masks[s]);
                 if (p->bcast[s]) {
-                    // one value per component: the host array is [rows][1] with the same row stride
-                    copy_rows(b->base, b->stride, host_in[s], host_stride, 1, rows, true, ctx->h2d);
+                    // a shared operand: the host array is [rows] contiguous, one value per component
+                    copy_rows(b->base, b->stride, host_in[s], 1, 1, rows, true, ctx->h2d);
                 } else {
                     copy_rows(b->base, b->stride, host_in[s] + off, host_stride, w, rows, true, ctx->h2d);
                 }

@@ -216,6 +216,8 @@ class Plan:
     def eval(self, inputs: Sequence[DeviceBatch], out: Optional[DeviceBatch] = None, engine: int = L.ENGINE_AUTO,
              arith: int = L.ARITH_FMA) -> DeviceBatch:
         """out[i] = expr(inputs[0][i], inputs[1][i], ...); stream-ordered."""
+        if self.ctx is None:
+            raise L.GaastError(L.ERR_NO_DEVICE, "offline plan (created without a ctx): there is no CPU evaluation path")
         if out is None:
             length = next((b.length for b in inputs if not _is_broadcast(b)), 1)
             out = self.alloc_output(length)

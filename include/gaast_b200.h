@@ -209,7 +209,10 @@ gaast_status gaast_eval_sum(gaast_plan* plan, gaast_batch* const* inputs, uint32
 
 /* End-to-end convenience used for the `e2e` measurement: host arrays in, host
  * arrays out, chunked so that H2D, kernels and D2H overlap.  host_in[s] points
- * to [comps of slot s][host_stride] (grades ascending), host_out likewise. */
+ * to [comps of slot s][host_stride] (grades of in_masks[s] ascending), or, for a
+ * broadcast slot, to [comps of slot s] contiguous values; host_out is
+ * [root comps][host_stride].  Pinned host memory is needed for the copies to
+ * overlap.  Synchronous: returns when host_out is complete. */
 gaast_status gaast_eval_host(gaast_plan* plan, const double* const* host_in, const uint32_t* in_masks,
                              const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
                              double* host_out, int engine, int arith);

@@ -83,7 +83,8 @@ def assert_bit_exact(got: Dict[int, np.ndarray], want: Dict[int, np.ndarray], wh
         g = np.ascontiguousarray(got[k], dtype=np.float64).view(np.uint64)
         w = np.ascontiguousarray(want[k], dtype=np.float64).view(np.uint64)
         # +0.0 and -0.0 compare equal in the reference's assert_eq! on f64
-        same = (g == w) | ((np.asarray(got[k]) == 0.0) & (np.asarray(want[k]) == 0.0))
+        same = (g == w) | ((np.asarray(got[k]) == 0.0) & (np.asarray(want[k]) == 0.0)) | \
+            (np.isnan(got[k]) & np.isnan(want[k]))  # NaN payloads are not part of the contract
         assert same.all(), f"{what}: grade {k}: {int((~same).sum())} components differ bitwise"
 
 

@@ -1,0 +1,79 @@
+"""The C-ABI library loads without a GPU, exports every symbol the two headers
+declare, and refuses to compute without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import gaast_b200 as g
+from gaast_b200 import _lib as L
+from gaast_b200 import workloads as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b(gaast_[a-z0-9_]+)\s*\(", text))
+    # function-pointer typedefs are not exports
+    names -= set(re.findall(r"\(\*\s*(gaast_[a-z0-9_]+)\s*\)", text))
+    return names
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    declared = _declared("gaast_b200.h") | _declared("gaast_b200_host.h")
+    assert len(declared) > 60
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/ but not exported"
+        assert name in L.PROTOTYPES, f"{name} has no ctypes prototype in gaast_b200/_lib.py"
+    for name in L.PROTOTYPES:
+        assert name in declared, f"{name} is bound but not declared in include/"
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(L.Term) == 16 and ctypes.sizeof(L.Op) == 32 and ctypes.sizeof(L.InputDesc) == 16
+    assert L.lib.gaast_version().startswith(b"gaast_b200")
+
+
+def test_offline_plan_and_kernel_source():
+    """A plan can be created, costed and turned into CUDA source with no device."""
+    w = W.WORKLOADS["cfg1"]
+    plan = g.Plan(None, W.specialize(w))
+    assert plan.cost() == (176, 48)  # 176 B and 24 terms per element
+    src = plan.kernel_source()
+    assert "gaast_eval" in src and "d_fma" in src
+    assert plan.root_grades() == [2]
+    with pytest.raises(g.GaastError) as ei:
+        plan.eval([])
+    assert ei.value.status in (L.ERR_NO_DEVICE, L.ERR_SHAPE)
+
+
+@pytest.mark.parametrize("name,cost", [("cfg2", (80, 320)), ("cfg2_full", (168, 672)), ("cfg3", (1536, 8192)),
+                                       ("cfg4", (2200, 3210)), ("cfg5", (1152, 3216))])
+def test_algorithmic_cost_of_the_workloads(name, cost):
+    w = W.WORKLOADS[name]
+    assert g.Plan(None, W.specialize(w)).cost(w.broadcast_mask()) == cost
+
+
+def test_generated_kernels_compile_for_sm100a(tmp_path, monkeypatch):
+    """NVRTC cross-compiles the specialised kernel without a GPU (fresh cache dir)."""
+    monkeypatch.setenv("GAAST_KERNEL_CACHE", str(tmp_path))
+    w = W.WORKLOADS["cfg2"]
+    plan = g.Plan(None, W.specialize(w))
+    info = plan.precompile(w.broadcast_mask())
+    assert "origin=nvrtc" in info
+    assert any(f.endswith(".cubin") for f in os.listdir(tmp_path))
+    info2 = plan.precompile(w.broadcast_mask())
+    assert "origin=cache" in info2
+
+
+def test_no_device_means_no_compute():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(g.GaastError) as ei:
+        g.Ctx(0)
+    assert ei.value.status == L.ERR_NO_DEVICE

@@ -1,0 +1,184 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on
+the same seeded inputs.
+
+Bars (BASELINE.json north_star): f64 within 1e-12 relative -- here relative to
+max(|oracle|, sum of |terms|) per component -- for the default
+FMA arithmetic; BIT-EXACT for GAAST_ARITH_STRICT, which performs the reference's
+`(l*r)*coeff` then `+` in the reference's order (eval.rs:82)."""
+from math import comb
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import gaast_b200 as g  # noqa: E402
+from gaast_b200 import _lib as L  # noqa: E402
+from gaast_b200 import workloads as W  # noqa: E402
+from gaast_b200.expr import Input, mv as pmv  # noqa: E402
+from tests.helpers import (assert_bit_exact, assert_close, oracle_abs_scale, oracle_eval)  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = g.Ctx(0)
+    yield c
+    c.close()
+
+
+def _device_inputs(ctx, w, host):
+    return [g.DeviceBatch.from_host(ctx, w.n, host[s], broadcast=bc) for s, (_, bc) in enumerate(w.inputs)]
+
+
+ENGINES = [("table", L.ENGINE_TABLE), ("specialized", L.ENGINE_SPECIALIZED)]
+
+
+@pytest.mark.parametrize("name", sorted(W.WORKLOADS))
+@pytest.mark.parametrize("engine", ENGINES, ids=[e[0] for e in ENGINES])
+@pytest.mark.parametrize("batch", [1, 2, 255, 4096 + 6])
+def test_workload_parity(ctx, name, engine, batch):
+    w = W.WORKLOADS[name]
+    host = W.host_inputs(w, batch)
+    bcs = [bc for _, bc in w.inputs]
+    want = oracle_eval(w.build, w.metric, host, bcs, batch)
+    scale = oracle_abs_scale(w.build, w.metric, host, bcs, batch)
+    plan = g.Plan(ctx, W.specialize(w))
+    dev = _device_inputs(ctx, w, host)
+    # strict arithmetic: bit-identical to the oracle
+    out = plan.eval(dev, engine=engine[1], arith=L.ARITH_STRICT)
+    ctx.sync()
+    assert engine[0] in plan.last_kernel()
+    assert_bit_exact(out.to_host(), want, f"{name} {engine[0]} strict")
+    # default arithmetic (one FMA per term): 1e-12
+    out2 = plan.eval(dev, engine=engine[1], arith=L.ARITH_FMA)
+    ctx.sync()
+    assert_close(out2.to_host(), want, scale, what=f"{name} {engine[0]} fma")
+    assert sorted(out2.to_host()) == plan.root_grades()  # Q3: the root grade set is part of the result
+
+
+SLOTS3 = [((0, 1, 2, 3), False)] * 3
+ZOO = [
+    lambda a, b, c: (a - b) * c,
+    lambda a, b, c: a.rev() * b.ginvol() * c.conj(),
+    lambda a, b, c: (a * b).g(2) + c.g(2),
+    lambda a, b, c: a.norm_sq().sqrt() * b,
+    lambda a, b, c: a * 2.5 + b / 4.0,
+    lambda a, b, c: (a.g(1) ^ b.g(1)).vinv() * c,
+    lambda a, b, c: a + b.g(0).sinv(),
+    lambda a, b, c: (a << b) + (b >> c),
+    lambda a, b, c: (a * b.clone()) + (b * c),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(ZOO)))
+@pytest.mark.parametrize("engine", ENGINES, ids=[e[0] for e in ENGINES])
+def test_operator_zoo(ctx, idx, engine):
+    build = ZOO[idx]
+    metric = [1.0, 1.0, -1.0] if idx % 2 else [1.0, 1.0, 1.0]
+    batch = 1000
+    rng = np.random.default_rng(100 + idx)
+    host = [{k: rng.uniform(-1, 1, (comb(3, k), batch)) for k in grades} for grades, _ in SLOTS3]
+    want = oracle_eval(build, metric, host, [False] * 3, batch)
+    ast = build(*[pmv(Input(s, gr)) for s, (gr, _) in enumerate(SLOTS3)]).specialize(metric)
+    plan = g.Plan(ctx, ast)
+    dev = [g.DeviceBatch.from_host(ctx, 3, h) for h in host]
+    out = plan.eval(dev, engine=engine[1], arith=L.ARITH_STRICT)
+    assert_bit_exact(out.to_host(), want, f"zoo {idx} {engine[0]}")
+
+
+@pytest.mark.parametrize("engine", ENGINES, ids=[e[0] for e in ENGINES])
+def test_degenerate_metric_and_constants(ctx, engine):
+    """vec_norm of the reference (eval.rs:146-150) batched: zero metric coefficient kept (Q4)."""
+    metric = [0.0, 1.0, 1.0]
+    batch = 513
+    rng = np.random.default_rng(7)
+    host = [{1: rng.uniform(-1, 1, (3, batch))}]
+    build = lambda v: (v * 2.0).norm_sq()  # noqa: E731
+    want = oracle_eval(build, metric, host, [False], batch)
+    plan = g.Plan(ctx, build(pmv(Input(0, (1,)))).specialize(metric))
+    out = plan.eval([g.DeviceBatch.from_host(ctx, 3, host[0])], engine=engine[1], arith=L.ARITH_STRICT)
+    assert_bit_exact(out.to_host(), want)
+
+
+def test_empty_batch_and_shape_errors(ctx):
+    w = W.WORKLOADS["cfg1"]
+    plan = g.Plan(ctx, W.specialize(w))
+    ins = [g.DeviceBatch.alloc(ctx, 3, (0, 1, 2, 3), 0) for _ in range(3)]
+    out = plan.eval(ins)  # zero elements: nothing to do, no error
+    assert out.length == 0
+    a = g.DeviceBatch.alloc(ctx, 3, (0, 1, 2, 3), 8)
+    b = g.DeviceBatch.alloc(ctx, 3, (0, 1, 2, 3), 9)
+    with pytest.raises(g.GaastError) as ei:
+        plan.eval([a, a, b])
+    assert ei.value.status == L.ERR_SHAPE
+    c = g.DeviceBatch.alloc(ctx, 3, (0, 1), 8)  # lacks grade 2, which the plan reads from slot 0
+    with pytest.raises(g.GaastError):
+        plan.eval([c, a, a])
+    wrong_out = g.DeviceBatch.alloc(ctx, 3, (1, 2), 8)  # root grade set is exactly {2}
+    with pytest.raises(g.GaastError):
+        plan.eval([a, a, a], out=wrong_out)
+
+
+@pytest.mark.parametrize("engine", ENGINES, ids=[e[0] for e in ENGINES])
+def test_batch_sum(ctx, engine):
+    import torch
+    w = W.WORKLOADS["cfg5"]
+    batch = 20000
+    host = W.host_inputs(w, batch)
+    want = oracle_eval(w.build, w.metric, host, [False, False], batch)
+    plan = g.Plan(ctx, W.specialize(w))
+    dev = _device_inputs(ctx, w, host)
+    sums = torch.zeros(66, dtype=torch.float64, device="cuda:0")
+    out = plan.alloc_output(batch)
+    plan.eval_sum(dev, sums.data_ptr(), out=out, engine=engine[1])
+    ctx.sync()
+    torch.cuda.synchronize()
+    ref = want[2].sum(axis=1)
+    mag = np.abs(want[2]).sum(axis=1)
+    assert np.all(np.abs(sums.cpu().numpy() - ref) <= 1e-12 * mag)
+    # without materialising the per-element result
+    sums2 = torch.zeros(66, dtype=torch.float64, device="cuda:0")
+    plan.eval_sum(dev, sums2.data_ptr(), out=None, engine=engine[1])
+    ctx.sync()
+    torch.cuda.synchronize()
+    assert np.all(np.abs(sums2.cpu().numpy() - ref) <= 1e-12 * mag)
+    # deterministic for a given launch shape
+    sums3 = torch.zeros(66, dtype=torch.float64, device="cuda:0")
+    plan.eval_sum(dev, sums3.data_ptr(), out=None, engine=engine[1])
+    torch.cuda.synchronize()
+    ctx.sync()
+    assert torch.equal(sums2, sums3)
+
+
+def test_eval_host_pipeline(ctx):
+    """gaast_eval_host: chunked H2D / kernel / D2H pipeline equals the resident path."""
+    w = W.WORKLOADS["cfg2"]
+    batch = 3 * 4096 * 100 + 17  # several chunks and a ragged tail
+    host = W.host_inputs(w, batch)
+    plan = g.Plan(ctx, W.specialize(w))
+    dev = _device_inputs(ctx, w, host)
+    want = plan.eval(dev).to_host()
+    R = np.concatenate([host[0][k] for k in (0, 2, 4)], axis=0)  # [16][1]
+    Rh = np.ascontiguousarray(R[:, 0])  # a broadcast slot is passed as [comps] contiguous values
+    X = np.ascontiguousarray(host[1][1])
+    out = np.zeros((5, batch))
+    plan.eval_host([Rh, X], [(0, 2, 4), (1,)], [True, False], batch, out)
+    assert np.array_equal(out, want[1])
+
+
+def test_wrap_torch_tensors(ctx):
+    import torch
+    w = W.WORKLOADS["cfg1"]
+    batch = 5000
+    tin = W.torch_inputs(w, batch, "cuda:0")
+    torch.cuda.synchronize()
+    plan = g.Plan(ctx, W.specialize(w))
+    dev = [g.DeviceBatch.wrap_torch(ctx, 3, t) for t in tin]
+    out_t = torch.empty((3, batch), dtype=torch.float64, device="cuda:0")
+    out = g.DeviceBatch.wrap_torch(ctx, 3, {2: out_t})
+    plan.eval(dev, out=out)
+    ctx.sync()
+    host = [{k: v.cpu().numpy() for k, v in t.items()} for t in tin]
+    want = oracle_eval(w.build, w.metric, host, [False] * 3, batch)
+    scale = oracle_abs_scale(w.build, w.metric, host, [False] * 3, batch)
+    assert_close({2: out_t.cpu().numpy()}, want, scale)
