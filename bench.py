@@ -157,7 +157,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------ GPU arm ----
-def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=None, with_sum=None):
+def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=None, with_sum=None, tuning=None):
     """Device-resident timing of one workload: returns dict with ms_per_step etc."""
     import gaast_b200 as g
     from gaast_b200 import _lib as L
@@ -165,6 +165,8 @@ def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=
     dev = torch.device("cuda", ctx.device)
     n = batch or w.batch
     plan = g.Plan(ctx, W.specialize(w))
+    if tuning:
+        plan.set_tuning(*tuning)
     tin = W.torch_inputs(w, n, dev)
     ins = [g.DeviceBatch.wrap_torch(ctx, w.n, t, broadcast=bc) for t, (_, bc) in zip(tin, w.inputs)]
     out = plan.alloc_output(n)
@@ -266,7 +268,10 @@ def run_gpu(args):
     peak_gbs, peak_src = _peaks()
 
     sampler = ClockSampler(local) if rank == 0 else None
-    res = time_workload(ctx, w, args.steps, args.warmup, torch, dist, world, batch=args.batch)
+    res = time_workload(ctx, w, args.steps, args.warmup, torch, dist, world, batch=args.batch,
+                        engine={'auto': 0, 'table': 1, 'specialized': 2}[args.engine],
+                        tuning=(args.ept, args.variant) if (args.ept or args.variant) else None,
+                        with_sum=False if args.no_sum else None)
     clocks = sampler.stop() if sampler else None
 
     n = res["elements"]
@@ -354,6 +359,10 @@ def main():
     ap.add_argument("--workload", default="cfg2", help="cfg1..cfg5 (default cfg2 = BASELINE configs[1])")
     ap.add_argument("--batch", type=int, default=None, help="override the batch length (default: the BASELINE size)")
     ap.add_argument("--impl", default="gaast_b200", choices=["gaast_b200", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "table", "specialized"])
+    ap.add_argument("--ept", type=int, default=0, help="tuning: elements per thread of the specialised kernel")
+    ap.add_argument("--variant", type=int, default=0, help="tuning: code generator policy bits")
+    ap.add_argument("--no-sum", action="store_true", help="skip the batch-sum node of cfg5")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--all", action="store_true", default=True, help="also time the other BASELINE workloads (N=1)")

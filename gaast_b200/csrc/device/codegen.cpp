@@ -56,7 +56,10 @@ struct Node {
     int stream = -1;    // LOAD
     uint32_t row = 0;   // LOAD
     int op = -1;        // ACC: index of the MUL_TERMS op it belongs to
+    uint32_t out_slot = 0, l_slot = 0, r_slot = 0;  // ACC: the term's slots in its op's buffers
     bool uniform = false;
+    bool reload = false;  // LOAD: parked in the thread's shared-memory column, re-read at every use
+    int smem_row = -1;    // reload: its row in the per-block staging area
     bool live = false;
     int export_idx = -1;  // uniform boundary node: index in EvalArgs::uniform
 };
@@ -181,7 +184,13 @@ struct Gen {
                     for (uint32_t t = op.term_begin; t < op.term_begin + op.term_count; ++t) {
                         const gaast_term& tm = h.terms[t];
                         Ref& d = buf[op.dst][tm.out];
+                        const size_t before = nodes.size();
                         d = make_acc(d, buf[op.a][tm.a], buf[op.b][tm.b], tm.coeff, int(oi));
+                        if (nodes.size() != before) {
+                            nodes.back().out_slot = tm.out;
+                            nodes.back().l_slot = tm.a;
+                            nodes.back().r_slot = tm.b;
+                        }
                     }
                     break;
                 case GAAST_OP_NEG_GRADES:
@@ -272,7 +281,7 @@ struct Gen {
     void line(const std::string& s) { body << std::string(size_t(indent) * 2, ' ') << s << "\n"; }
 
     // Operand text for a consumer of type `wide` (per-element) or scalar.
-    std::string opnd(Ref r, bool wide, bool flip = false) const {
+    std::string opnd(Ref r, bool wide, bool flip = false, const std::string& name = std::string()) const {
         const Node& n = nodes[r.id];
         const bool neg = r.neg ^ flip;
         std::string s;
@@ -281,7 +290,7 @@ struct Gen {
         else if (n.k == N_CONST)
             s = lit(n.cval);
         else
-            s = var(r.id);
+            s = name.empty() ? var(r.id) : name;
         const bool scalar = n.uniform;
         if (neg) s = (n.k == N_ZERO || n.k == N_CONST) ? "(-" + s + ")" : (scalar ? "(-" + s + ")" : "d_neg(" + s + ")");
         if (wide && scalar) s = "U(" + s + ")";
@@ -314,37 +323,72 @@ struct Gen {
             case N_INV: line(ty + v + " = d_inv(" + opnd(n.a, wide) + ");"); return;
             case N_SQRT: line(ty + v + " = d_sqrt(" + opnd(n.a, wide) + ");"); return;
             case N_ACC: {
-                const double c = n.cval;
-                const bool unit = std::fabs(c) == 1.0;
-                if (strict) {
-                    // (l * r) * coeff, then +  (eval.rs:82); multiplying by +-1 is exact
-                    std::string prod = "d_muls(" + opnd(n.b, wide) + ", " + opnd(n.c, wide) + ")";
-                    if (unit) {
-                        if (c < 0) prod = wide ? "d_neg(" + prod + ")" : "(-" + prod + ")";
-                    } else {
-                        prod = "d_muls(" + prod + ", " + (wide ? "U(" + lit(c) + ")" : lit(c)) + ")";
-                    }
-                    line(ty + v + " = d_adds(" + opnd(n.a, wide) + ", " + prod + ");");
-                    return;
-                }
-                const bool flip = unit && c < 0;
-                if (unit) {
-                    if (is_zero(n.a))
-                        line(ty + v + " = d_mul(" + opnd(n.b, wide, flip) + ", " + opnd(n.c, wide) + ");");
-                    else
-                        line(ty + v + " = d_fma(" + opnd(n.b, wide, flip) + ", " + opnd(n.c, wide) + ", " +
-                             opnd(n.a, wide) + ");");
-                } else {
-                    const std::string cl = wide ? "U(" + lit(c) + ")" : lit(c);
-                    const std::string prod = "d_mul(" + opnd(n.b, wide) + ", " + opnd(n.c, wide) + ")";
-                    if (is_zero(n.a))
-                        line(ty + v + " = d_mul(" + prod + ", " + cl + ");");
-                    else
-                        line(ty + v + " = d_fma(" + prod + ", " + cl + ", " + opnd(n.a, wide) + ");");
-                }
+                const std::string ln = use_name(n.b), rn = use_name(n.c);
+                line(ty + v + " = " +
+                     acc_rhs(n, wide, opnd(n.b, wide, acc_flip(n), ln), opnd(n.c, wide, false, rn), opnd(n.a, wide),
+                             is_zero(n.a)) + ";");
                 return;
             }
         }
+    }
+
+    // A RELOAD input row is not kept in a register.  It is parked once per
+    // element in the thread's private column of a shared-memory staging area
+    // ([row][thread], bank-conflict free, no barrier needed: a thread only reads
+    // what it wrote) and every use re-reads it with a volatile LDS into a
+    // temporary that dies at once.  (Re-reading global memory through L1 does not
+    // work: ptxas merges identical ld.global.nc and keeps the value live.)
+    int reload_counter = 0;
+    std::string load_addr(const Node& n) const {
+        const std::string s = std::to_string(n.stream);
+        return "s" + s + " + " + std::to_string(n.row) + " * r" + s + " + e";
+    }
+    std::string smem_read(const Node& n) const {
+        return "xs_ld<" + std::to_string(size_t(n.smem_row) * 8) + " * GAAST_THREADS>(xb)";
+    }
+    std::string use_name(Ref r) {
+        const Node& n = nodes[r.id];
+        if (n.k != N_LOAD || n.uniform || !n.reload || in_prologue) return std::string();
+        const std::string nm = "x" + std::to_string(r.id) + "_" + std::to_string(reload_counter++);
+        line("const D " + nm + " = " + smem_read(n) + ";");
+        return nm;
+    }
+    // All parked rows are fetched at the top of the element body (one burst of
+    // independent loads), then stored to shared memory.
+    void emit_staging() {
+        std::vector<int> ids;
+        for (size_t id = 0; id < nodes.size(); ++id)
+            if (nodes[id].live && nodes[id].k == N_LOAD && nodes[id].reload && !nodes[id].uniform) ids.push_back(int(id));
+        for (size_t i = 0; i < ids.size(); i += 16) {
+            const size_t end = std::min(ids.size(), i + 16);
+            for (size_t j = i; j < end; ++j)
+                line("const D g" + std::to_string(ids[j]) + " = d_load(" + load_addr(nodes[ids[j]]) + ");");
+            for (size_t j = i; j < end; ++j)
+                line("xs_st<" + std::to_string(size_t(nodes[ids[j]].smem_row) * 8) + " * GAAST_THREADS>(xb, g" +
+                     std::to_string(ids[j]) + ");");
+        }
+    }
+
+    // `acc + l*r*coeff` (eval.rs:82) as an expression over already formatted operands.
+    bool acc_flip(const Node& n) const { return !strict && std::fabs(n.cval) == 1.0 && n.cval < 0; }
+    std::string acc_rhs(const Node& n, bool wide, const std::string& L, const std::string& R, const std::string& P,
+                        bool p_zero) const {
+        const double c = n.cval;
+        const bool unit = std::fabs(c) == 1.0;
+        if (strict) {
+            // (l * r) * coeff, then +; multiplying by +-1 is exact
+            std::string prod = "d_muls(" + L + ", " + R + ")";
+            if (unit) {
+                if (c < 0) prod = wide ? "d_neg(" + prod + ")" : "(-" + prod + ")";
+            } else {
+                prod = "d_muls(" + prod + ", " + (wide ? "U(" + lit(c) + ")" : lit(c)) + ")";
+            }
+            return "d_adds(" + P + ", " + prod + ")";
+        }
+        if (unit) return p_zero ? "d_mul(" + L + ", " + R + ")" : "d_fma(" + L + ", " + R + ", " + P + ")";
+        const std::string cl = wide ? "U(" + lit(c) + ")" : lit(c);
+        const std::string prod = "d_mul(" + L + ", " + R + ")";
+        return p_zero ? "d_mul(" + prod + ", " + cl + ")" : "d_fma(" + prod + ", " + cl + ", " + P + ")";
     }
 
     bool skip_in_this_kernel(const Node& n) const {
@@ -357,13 +401,17 @@ struct Gen {
         Node& n = nodes[id];
         if (is_leaf(n) || (!in_prologue && n.uniform && n.export_idx >= 0)) {
             emitted[id] = 1;
-            emit_node_line(id);
+            if (!(n.k == N_LOAD && n.reload && !n.uniform && !in_prologue)) emit_node_line(id);
             return;
         }
         if (n.k == N_ACC) {
             const Policy pol = (in_prologue || n.uniform) ? P_GATHER : op_policy[n.op];
             if (pol == P_TABLE) {
                 emit_op_table(n.op);
+                return;
+            }
+            if (pol == P_BLOCKED) {
+                emit_op_blocked(n.op);
                 return;
             }
             // GATHER: walk the chain back to its first un-emitted link, then forward
@@ -402,8 +450,120 @@ struct Gen {
             emit(n.c.id);
             emitted[id] = 1;
             emit_node_line(id);
+            store_if_root(id);
         }
     }
+
+    // Root components are stored (and batch-summed) as soon as their value
+    // exists, so that finished outputs do not occupy registers.
+    struct RootSlot {
+        size_t stream;
+        uint32_t row, col;
+        bool neg;
+    };
+    std::multimap<int, RootSlot> root_of;  // node id -> root slots holding it
+    std::vector<char> root_done;
+    void emit_root(const RootSlot& rs, int id) {
+        if (in_prologue || root_done[rs.col]) return;
+        root_done[rs.col] = 1;
+        const std::string val = opnd(Ref{id, rs.neg}, true);
+        if (opt.store_out)
+            line("d_store(s" + std::to_string(rs.stream) + " + " + std::to_string(rs.row) + " * r" +
+                 std::to_string(rs.stream) + " + e, " + val + ");");
+        if (opt.with_sum) line("sums[" + std::to_string(rs.col) + " * GAAST_THREADS + tid] += d_hsum(" + val + ");");
+    }
+    void store_if_root(int id) {
+        if (in_prologue) return;
+        auto range = root_of.equal_range(id);
+        for (auto it = range.first; it != range.second; ++it) emit_root(it->second, id);
+    }
+
+    // Dense products: tiles of the Cayley table indexed by the high blade bits
+    // of (output, left).  A tile's outputs form one XOR coset, so it touches at
+    // most 2^h outputs, 2^h left and 2^h right components.  The coset's
+    // accumulators stay in registers across the tiles of its row; input rows are
+    // re-loaded per tile (L1 hits after their first touch) into tile-local
+    // variables, so their registers die with the tile.  Changes the summation
+    // order inside a component: never used for GAAST_ARITH_STRICT.
+    int tile_counter = 0;
+    void emit_op_blocked(int op) {
+        const gaast_op& pop = h.ops[op];
+        const int hb = blocked_low_bits;
+        std::map<uint32_t, std::map<uint32_t, std::vector<int>>> tiles;  // out_high -> left_high -> ACC nodes
+        std::map<uint32_t, int> first_link, last_link;                    // out slot -> node
+        for (int id : op_accs[op]) {
+            const Node& n = nodes[id];
+            if (!n.live) continue;
+            tiles[slot_blade[pop.dst][n.out_slot] >> hb][slot_blade[pop.a][n.l_slot] >> hb].push_back(id);
+            if (!first_link.count(n.out_slot)) first_link[n.out_slot] = id;
+            last_link[n.out_slot] = id;
+        }
+        for (auto& row : tiles) {
+            // accumulators of this output coset, initialised with the pre-op value
+            std::set<uint32_t> outs;
+            for (auto& t : row.second)
+                for (int id : t.second) outs.insert(nodes[id].out_slot);
+            std::map<uint32_t, bool> started;
+            for (uint32_t o : outs) {
+                const Ref pre = nodes[first_link[o]].a;
+                emit(pre.id);
+                const std::string q = "q" + std::to_string(last_link[o]);
+                if (is_zero(pre)) {
+                    line("D " + q + ";");
+                    started[o] = false;
+                } else {
+                    line("D " + q + " = " + opnd(pre, true) + ";");
+                    started[o] = true;
+                }
+            }
+            for (auto& t : row.second) {
+                // operands that live in registers are declared at function scope, before the tile's braces
+                for (int id : t.second)
+                    for (Ref r : {nodes[id].b, nodes[id].c})
+                        if (!(nodes[r.id].k == N_LOAD && !nodes[r.id].uniform && nodes[r.id].reload)) emit(r.id);
+                line("{");
+                ++indent;
+                std::map<int, std::string> local;
+                auto name_of = [&](Ref r) -> std::string {
+                    const Node& n = nodes[r.id];
+                    if (n.k == N_LOAD && !n.uniform && n.reload) {
+                        auto it = local.find(r.id);
+                        if (it != local.end()) return it->second;
+                        const std::string s = std::to_string(n.stream);
+                        const std::string nm = "t" + std::to_string(r.id) + "_" + std::to_string(tile_counter);
+                        line("const D " + nm + " = " + smem_read(n) + ";");
+                        (void)s;
+                        local.emplace(r.id, nm);
+                        return nm;
+                    }
+                    emit(r.id);
+                    return std::string();
+                };
+                std::vector<std::pair<std::string, std::string>> names;
+                for (int id : t.second) names.push_back({name_of(nodes[id].b), name_of(nodes[id].c)});
+                size_t i = 0;
+                for (int id : t.second) {
+                    const Node& n = nodes[id];
+                    const std::string q = "q" + std::to_string(last_link[n.out_slot]);
+                    const std::string L = opnd(n.b, true, acc_flip(n), names[i].first);
+                    const std::string R = opnd(n.c, true, false, names[i].second);
+                    line(q + " = " + acc_rhs(n, true, L, R, q, !started[n.out_slot]) + ";");
+                    started[n.out_slot] = true;
+                    ++i;
+                }
+                --indent;
+                line("}");
+                ++tile_counter;
+            }
+            for (uint32_t o : outs) {
+                const int fin = last_link[o];
+                line("const D " + var(fin) + " = q" + std::to_string(fin) + ";");
+                store_if_root(fin);
+            }
+        }
+        for (int id : op_accs[op]) emitted[id] = 1;
+    }
+    int blocked_low_bits = 4;
 
 };
 
@@ -426,6 +586,16 @@ __device__ __forceinline__ double d_hsum(D a) { return a.x + a.y; }
 typedef double D;
 __device__ __forceinline__ D U(double x) { return x; }
 __device__ __forceinline__ D d_load(const double* p) { return __ldg(p); }
+template <int OFF>
+__device__ __forceinline__ void xs_st(unsigned base, double v) {
+  asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(base), "n"(OFF), "d"(v) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ double xs_ld(unsigned base) {
+  double v;
+  asm volatile("ld.volatile.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(base), "n"(OFF) : "memory");
+  return v;
+}
 __device__ __forceinline__ void d_store(double* p, D v) { *p = v; }
 __device__ __forceinline__ double d_hsum(D a) { return a; }
 #endif
@@ -457,21 +627,82 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     g.op_policy.assign(h.ops.size(), P_TABLE);
     size_t widest = 0;
     std::ostringstream notes;
+    int res_parked = 0, res_parkable = 0;
+    constexpr size_t kDenseBudget = 110;  // doubles: outputs + operands of a product that may all be live
+    constexpr size_t kLiveBudget = 124;   // doubles a thread can hold in 255 registers next to addresses
+    std::vector<int> uses(g.nodes.size(), 0);  // how many live product terms read each node
+    std::set<int> blocked_loads;
+    size_t widest_table = 0;
     for (size_t oi = 0; oi < h.ops.size(); ++oi) {
         if (h.ops[oi].kind != GAAST_OP_MUL_TERMS) continue;
         std::set<uint32_t> outs;
-        size_t live_terms = 0;
-        for (uint32_t t = 0; t < h.ops[oi].term_count; ++t) outs.insert(h.terms[h.ops[oi].term_begin + t].out);
-        for (int id : g.op_accs[oi]) live_terms += g.nodes[id].live;
-        g.op_policy[oi] = outs.size() > kAccBudget ? P_GATHER : P_TABLE;
-        if (opt.variant & 1) g.op_policy[oi] = P_TABLE;
-        if (opt.variant & 2) g.op_policy[oi] = P_GATHER;
+        std::set<int> ls, rs;
+        size_t live_terms = 0, load_opnds = 0;
+        for (int id : g.op_accs[oi]) {
+            const Node& n = g.nodes[id];
+            if (!n.live || n.uniform) continue;
+            ++live_terms;
+            outs.insert(n.out_slot);
+            ls.insert(n.b.id);
+            rs.insert(n.c.id);
+            ++uses[n.b.id];
+            ++uses[n.c.id];
+        }
+        for (int id : ls) load_opnds += g.nodes[id].k == N_LOAD && !g.nodes[id].uniform;
+        for (int id : rs) load_opnds += g.nodes[id].k == N_LOAD && !g.nodes[id].uniform;
+        const bool dense = !g.strict && outs.size() + ls.size() + rs.size() > kDenseBudget &&
+                           live_terms * 4 >= ls.size() * rs.size() && load_opnds * 4 >= (ls.size() + rs.size()) * 3;
+        Policy pol = outs.size() > kAccBudget ? P_GATHER : P_TABLE;
+        if (dense && outs.size() <= 2 * kAccBudget) pol = P_BLOCKED;
+        if (opt.variant & 1) pol = P_TABLE;
+        if (opt.variant & 2) pol = P_GATHER;
+        g.op_policy[oi] = pol;
+        if (pol == P_BLOCKED) {
+            // right operands are re-fetched per tile; left ones too unless variant bit 2 keeps them in registers
+            for (int id : rs)
+                if (g.nodes[id].k == N_LOAD) blocked_loads.insert(id);
+            if (!(opt.variant & 4))
+                for (int id : ls)
+                    if (g.nodes[id].k == N_LOAD) blocked_loads.insert(id);
+        }
+        if (pol == P_TABLE) widest_table = std::max(widest_table, outs.size());
         widest = std::max(widest, outs.size());
-        notes << "op" << oi << ":" << (g.op_policy[oi] == P_TABLE ? "table" : "gather") << "(outs=" << outs.size()
-              << ",terms=" << live_terms << ") ";
+        notes << "op" << oi << ":" << (pol == P_TABLE ? "table" : pol == P_GATHER ? "gather" : "blocked")
+              << "(outs=" << outs.size() << ",terms=" << live_terms << ") ";
     }
+    for (int id : blocked_loads) g.nodes[id].reload = true;
+    // Register pressure of everything else: the widest in-register product plus the
+    // input rows that stay live.  Rows with the fewest uses are re-fetched first.
+    {
+        std::vector<std::pair<int, int>> cand;  // (uses, node)
+        size_t kept = 0;
+        for (size_t id = 0; id < g.nodes.size(); ++id) {
+            const Node& n = g.nodes[id];
+            if (!n.live || n.k != N_LOAD || n.uniform || n.reload) continue;
+            ++kept;
+            if (uses[id] > 1) cand.push_back({uses[id], int(id)});
+        }
+        size_t pressure = widest_table + kept + 12;
+        size_t want = pressure > kLiveBudget ? pressure - kLiveBudget : 0;
+        if (opt.variant >> 8) want = size_t(opt.variant >> 8) - 1;  // tuning override: variant = (count + 1) << 8
+        want += size_t(opt.extra_parked);  // raised by the compile-and-check loop while ptxas reports spills
+        std::sort(cand.begin(), cand.end());
+        size_t n_reload = 0;
+        for (auto& c : cand) {
+            if (n_reload >= want) break;
+            g.nodes[c.second].reload = true;
+            ++n_reload;
+        }
+        if (n_reload) notes << "parked=" << n_reload << " ";
+        res_parked = int(n_reload);
+        res_parkable = int(cand.size());
+    }
+    int n_smem_rows = 0;
+    for (Node& n : g.nodes)
+        if (n.live && n.k == N_LOAD && n.reload && !n.uniform) n.smem_row = n_smem_rows++;
     int ept = opt.elems_per_thread;
     if (ept != 1 && ept != 2) ept = (live_loads + root_cols + widest <= 48) ? 2 : 1;
+    if (n_smem_rows) ept = 1;  // the staging area holds one double per row and thread
     g.ept = ept;
     const int threads = 128;
 
@@ -481,7 +712,9 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     res.elems_per_thread = ept;
     res.n_uniform = g.n_export;
     res.n_sum_cols = opt.with_sum ? int(root_cols) : 0;
-    res.smem_bytes = size_t(res.n_sum_cols) * threads * sizeof(double);
+    res.smem_bytes = size_t(res.n_sum_cols + n_smem_rows) * threads * sizeof(double);
+    res.parked = res_parked;
+    res.parkable = res_parkable;
 
     std::ostringstream src;
     src << "// generated by gaast_b200 codegen: n=" << h.n << " terms=" << h.total_terms << " arith="
@@ -549,30 +782,30 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         g.indent = 2;
     }
     // root components, in slot order
-    std::ostringstream stores;
     {
+        std::vector<Gen::RootSlot> slots;
         uint32_t col = 0;
-        for (size_t si = h.n_in_streams; si < h.streams.size(); ++si) {
-            const Stream& st = h.streams[si];
-            for (uint32_t r = 0; r < st.rows; ++r, ++col) {
-                const Ref v = g.buf[0][col];
-                g.emit(v.id);
-                const std::string val = g.opnd(v, true);
-                if (opt.store_out)
-                    g.line("d_store(s" + std::to_string(si) + " + " + std::to_string(r) + " * r" + std::to_string(si) +
-                           " + e, " + val + ");");
-                if (opt.with_sum)
-                    g.line("sums[" + std::to_string(col) + " * GAAST_THREADS + tid] += d_hsum(" + val + ");");
-            }
+        for (size_t si = h.n_in_streams; si < h.streams.size(); ++si)
+            for (uint32_t r = 0; r < h.streams[si].rows; ++r, ++col)
+                slots.push_back(Gen::RootSlot{si, r, col, g.buf[0][col].neg});
+        g.root_done.assign(slots.size(), 0);
+        g.root_of.clear();
+        g.emit_staging();
+        for (const auto& rs : slots) g.root_of.emplace(g.buf[0][rs.col].id, rs);
+        for (const auto& rs : slots) {
+            const int id = g.buf[0][rs.col].id;
+            g.emit(id);            // products store their outputs as soon as they are complete ...
+            g.emit_root(rs, id);   // ... everything else (leaves, sums, unary results) is stored here
         }
     }
     src << "extern \"C\" __global__ void __launch_bounds__(GAAST_THREADS) gaast_eval(const __grid_constant__ EvalArgs a) {\n";
     src << "  const int tid = threadIdx.x;\n";
     stream_decls(src, false);
-    if (opt.with_sum) {
-        src << "  extern __shared__ double sums[];\n";
-        src << "  for (int c = 0; c < " << root_cols << "; ++c) sums[c * GAAST_THREADS + tid] = 0.0;\n";
-    }
+    if (opt.with_sum || n_smem_rows) src << "  extern __shared__ double sums[];\n";
+    if (opt.with_sum) src << "  for (int c = 0; c < " << root_cols << "; ++c) sums[c * GAAST_THREADS + tid] = 0.0;\n";
+    if (n_smem_rows)
+        src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << res.n_sum_cols
+            << " * GAAST_THREADS + tid);\n";
     src << uni.str();
     src << "  for (long long e = ((long long)blockIdx.x * GAAST_THREADS + tid) * GAAST_EPT; e < a.n;\n"
            "       e += (long long)gridDim.x * GAAST_THREADS * GAAST_EPT) {\n";

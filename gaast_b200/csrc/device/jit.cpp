@@ -9,6 +9,8 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -75,7 +77,7 @@ Nvrtc& nvrtc() {
 }
 
 const char* kOptions[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true",
-                          "--extra-device-vectorization"};
+                          "--extra-device-vectorization", "--ptxas-options=-v"};
 constexpr int kNumOptions = int(sizeof kOptions / sizeof kOptions[0]);
 
 std::string hash_key(const std::string& src) {
@@ -148,6 +150,8 @@ std::vector<char> jit_cubin(const CodegenResult& cg, std::string* key_out, std::
     std::vector<char> cubin;
     if (!std::getenv("GAAST_NO_KERNEL_CACHE") && read_file(base + ".cubin", cubin)) {
         if (origin) *origin = "cache";
+        std::vector<char> cached_log;
+        if (log_out && read_file(base + ".log", cached_log)) log_out->assign(cached_log.begin(), cached_log.end());
         return cubin;
     }
     Nvrtc& n = nvrtc();
@@ -181,8 +185,44 @@ std::vector<char> jit_cubin(const CodegenResult& cg, std::string* key_out, std::
     n.DestroyProgram(&prog);
     if (rc != 0 || cubin.empty()) throw Error(GAAST_ERR_JIT, "NVRTC produced no cubin");
     write_file_atomic(base + ".cubin", cubin.data(), cubin.size());
+    if (!log.empty()) write_file_atomic(base + ".log", log.data(), log.size());
     if (origin) *origin = "nvrtc";
     return cubin;
+}
+
+// ptxas -v prints, per entry point, "... Function properties for <name>" followed
+// by "N bytes stack frame, N bytes spill stores, N bytes spill loads".
+size_t spill_bytes_from_log(const std::string& log, const std::string& kernel) {
+    size_t pos = log.find("Function properties for " + kernel);
+    if (pos == std::string::npos) return 0;
+    const size_t end = log.find("Function properties for ", pos + 1);
+    const std::string part = log.substr(pos, end == std::string::npos ? std::string::npos : end - pos);
+    size_t spill = 0;
+    for (const char* what : {"bytes spill stores", "bytes spill loads"}) {
+        const size_t w = part.find(what);
+        if (w == std::string::npos) continue;
+        size_t b = w;
+        while (b > 0 && (part[b - 1] == ' ' || std::isdigit(static_cast<unsigned char>(part[b - 1])))) --b;
+        spill = std::max(spill, size_t(std::strtoull(part.c_str() + b, nullptr, 10)));
+    }
+    return spill;
+}
+
+std::vector<char> build_specialized(const DevicePlanHost& h, CodegenOptions opt, CodegenResult* cg_out,
+                                    std::string* key, std::string* origin) {
+    std::vector<char> cubin;
+    for (int attempt = 0;; ++attempt) {
+        CodegenResult cg = generate_kernel(h, opt);
+        std::string log;
+        cubin = jit_cubin(cg, key, origin, &log);
+        const size_t spill = spill_bytes_from_log(log, cg.kernel_name);
+        const bool can_park_more = cg.parked < cg.parkable && cg.elems_per_thread == 1;
+        if (spill == 0 || !can_park_more || attempt >= 8) {
+            *cg_out = std::move(cg);
+            return cubin;
+        }
+        opt.extra_parked += spill > 256 ? 16 : 8;
+    }
 }
 
 std::shared_ptr<JitKernel> jit_load(const CodegenResult& cg, const std::vector<char>& cubin) {

@@ -288,10 +288,10 @@ gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, i
         opt.store_out = store_out != 0;
         opt.elems_per_thread = plan->force_ept;
         opt.variant = plan->variant;
-        gaast::CodegenResult cg = gaast::generate_kernel(plan->h, opt);
-        std::string key, origin, log;
-        gaast::jit_cubin(cg, &key, &origin, &log);
-        plan->last_kernel = cg.kernel_name + " key=" + key + " origin=" + origin;
+        gaast::CodegenResult cg;
+        std::string key, origin;
+        gaast::build_specialized(plan->h, opt, &cg, &key, &origin);
+        plan->last_kernel = cg.kernel_name + " key=" + key + " origin=" + origin + " " + cg.notes;
     });
 }
 
@@ -416,9 +416,9 @@ static std::shared_ptr<gaast::JitKernel> get_specialized(gaast_plan* plan, const
                                opt.elems_per_thread, opt.variant);
     auto it = plan->jit.find(key);
     if (it != plan->jit.end()) return it->second;
-    gaast::CodegenResult cg = gaast::generate_kernel(plan->h, opt);
-    std::string ckey, origin, log;
-    std::vector<char> cubin = gaast::jit_cubin(cg, &ckey, &origin, &log);
+    gaast::CodegenResult cg;
+    std::string ckey, origin;
+    std::vector<char> cubin = gaast::build_specialized(plan->h, opt, &cg, &ckey, &origin);
     auto k = gaast::jit_load(cg, cubin);
     k->key = ckey;
     k->origin = origin;

@@ -41,6 +41,7 @@ struct CodegenOptions {
     bool store_out = true;
     int elems_per_thread = 0;  // 0 = choose
     int variant = 0;           // GAAST_CODEGEN_* bit flags (tuning knobs; 0 = defaults)
+    int extra_parked = 0;      // more input rows parked in shared memory (raised while ptxas reports spills)
 };
 
 struct CodegenResult {
@@ -53,6 +54,7 @@ struct CodegenResult {
     int n_uniform = 0;
     int n_sum_cols = 0;
     size_t smem_bytes = 0;
+    int parked = 0, parkable = 0;  // input rows parked in shared memory / rows that could be
     std::string notes;  // human-readable summary of the decisions taken
 };
 
@@ -63,6 +65,11 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
 bool jit_available(std::string* why);
 // Compiles (or finds in the cache) without touching a device.  Returns the cubin.
 std::vector<char> jit_cubin(const CodegenResult& cg, std::string* key, std::string* origin, std::string* log);
+// Generates and compiles the kernel for `opt`, parking more input rows in shared
+// memory while ptxas reports register spills.  `cg` receives the final source.
+std::vector<char> build_specialized(const DevicePlanHost& h, CodegenOptions opt, CodegenResult* cg, std::string* key,
+                                    std::string* origin);
+size_t spill_bytes_from_log(const std::string& ptxas_log, const std::string& kernel);
 // Loads a cubin on the current device.
 std::shared_ptr<JitKernel> jit_load(const CodegenResult& cg, const std::vector<char>& cubin);
 std::string jit_cache_dir();
