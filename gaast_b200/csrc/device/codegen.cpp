@@ -355,7 +355,9 @@ struct Gen {
     }
     // All parked rows are fetched at the top of the element body (one burst of
     // independent loads), then stored to shared memory.
+    bool pipelined = false;  // parked rows arrive by TMA (persistent block, double buffered), not by LDG + STS
     void emit_staging() {
+        if (pipelined) return;
         std::vector<int> ids;
         for (size_t id = 0; id < nodes.size(); ++id)
             if (nodes[id].live && nodes[id].k == N_LOAD && nodes[id].reload && !nodes[id].uniform) ids.push_back(int(id));
@@ -467,10 +469,12 @@ struct Gen {
         if (in_prologue || root_done[rs.col]) return;
         root_done[rs.col] = 1;
         const std::string val = opnd(Ref{id, rs.neg}, true);
+        const std::string guard = pipelined ? "if (active) " : "";
         if (opt.store_out)
-            line("d_store(s" + std::to_string(rs.stream) + " + " + std::to_string(rs.row) + " * r" +
+            line(guard + "d_store(s" + std::to_string(rs.stream) + " + " + std::to_string(rs.row) + " * r" +
                  std::to_string(rs.stream) + " + e, " + val + ");");
-        if (opt.with_sum) line("sums[" + std::to_string(rs.col) + " * GAAST_THREADS + tid] += d_hsum(" + val + ");");
+        if (opt.with_sum)
+            line(guard + "sums[" + std::to_string(rs.col) + " * GAAST_THREADS + tid] += d_hsum(" + val + ");");
     }
     void store_if_root(int id) {
         if (in_prologue) return;
@@ -596,6 +600,34 @@ __device__ __forceinline__ double xs_ld(unsigned base) {
   asm volatile("ld.volatile.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(base), "n"(OFF) : "memory");
   return v;
 }
+// TMA (bulk async copy) + mbarrier plumbing of the pipelined kernels
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_row(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_row(const double* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GAAST_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra GAAST_DONE;\n"
+      "bra GAAST_WAIT;\n"
+      "GAAST_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void d_store(double* p, D v) { *p = v; }
 __device__ __forceinline__ double d_hsum(D a) { return a; }
 #endif
@@ -712,7 +744,12 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     res.elems_per_thread = ept;
     res.n_uniform = g.n_export;
     res.n_sum_cols = opt.with_sum ? int(root_cols) : 0;
-    res.smem_bytes = size_t(res.n_sum_cols + n_smem_rows) * threads * sizeof(double);
+    const bool pipelined = opt.pipelined && n_smem_rows > 0 && ept == 1;
+    g.pipelined = pipelined;
+    res.pipelined = pipelined;
+    res.smem_bytes = pipelined ? size_t(res.n_sum_cols + 2 * n_smem_rows) * threads * sizeof(double) + 16
+                               : size_t(res.n_sum_cols + n_smem_rows) * threads * sizeof(double);
+    if (pipelined) notes << "tma-pipelined ";
     res.parked = res_parked;
     res.parkable = res_parkable;
 
@@ -723,6 +760,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     src << "#define GAAST_EPT " << ept << "\n#define GAAST_THREADS " << threads << "\n";
     src << kEvalArgsText << "\nusing gaast::EvalArgs;\n" << kPrelude << "\n";
 
+    std::ostringstream loop_strides;
     auto stream_decls = [&](std::ostringstream& o, bool prologue) {
         std::set<int> used;
         for (const Node& n : g.nodes)
@@ -732,7 +770,11 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         for (int s : used) {
             const bool out = size_t(s) >= h.n_in_streams;
             o << "  " << (out ? "double* __restrict__ s" : "const double* __restrict__ s") << s << " = a.sptr[" << s
-              << "]; const long long r" << s << " = a.srow[" << s << "];\n";
+              << "]; const long long R" << s << " = a.srow[" << s << "]; const long long r" << s << " = R" << s << ";\n";
+            // Inside the element loop the stride is made opaque: otherwise the compiler hoists
+            // every `row * stride` out of the loop and keeps dozens of 64-bit offsets live.
+            if (!prologue)
+                loop_strides << "    long long r" << s << " = R" << s << "; asm volatile(\"\" : \"+l\"(r" << s << "));\n";
         }
     };
 
@@ -803,14 +845,70 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     stream_decls(src, false);
     if (opt.with_sum || n_smem_rows) src << "  extern __shared__ double sums[];\n";
     if (opt.with_sum) src << "  for (int c = 0; c < " << root_cols << "; ++c) sums[c * GAAST_THREADS + tid] = 0.0;\n";
-    if (n_smem_rows)
-        src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << res.n_sum_cols
-            << " * GAAST_THREADS + tid);\n";
     src << uni.str();
-    src << "  for (long long e = ((long long)blockIdx.x * GAAST_THREADS + tid) * GAAST_EPT; e < a.n;\n"
-           "       e += (long long)gridDim.x * GAAST_THREADS * GAAST_EPT) {\n";
-    src << g.body.str();
-    src << "  }\n";
+    if (pipelined) {
+        // Persistent block, two staging buffers.  The TMA unit copies the parked rows
+        // of tile t+2 into the buffer tile t has just released (one bulk copy per row:
+        // a row's 128-element segment is contiguous in the batch-innermost layout),
+        // completion is signalled on an mbarrier; the rows a thread keeps in registers
+        // are pulled into L2 two tiles ahead with bulk prefetches.
+        const int P = n_smem_rows;
+        std::vector<const Node*> parked(size_t(P), nullptr), in_regs;
+        for (const Node& n : g.nodes) {
+            if (!n.live || n.k != N_LOAD || n.uniform) continue;
+            if (n.reload) parked[size_t(n.smem_row)] = &n;
+            else in_regs.push_back(&n);
+        }
+        src << "  double* const stage0 = sums + " << res.n_sum_cols << " * GAAST_THREADS;\n";
+        src << "  unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(stage0 + 2 * " << P
+            << " * GAAST_THREADS);\n";
+        src << "  const long long n_tiles = (a.n + GAAST_THREADS - 1) / GAAST_THREADS;\n";
+        src << "  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_mbar_init(); }\n";
+        src << "  __syncthreads();\n";
+        src << "  auto issue = [&](long long tile, int s) {\n";
+        src << "    const long long e0 = tile * GAAST_THREADS;\n";
+        src << "    const long long left = a.n - e0;\n";
+        src << "    const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * 8);\n";
+        src << "    double* const dst = stage0 + s * " << P << " * GAAST_THREADS;\n";
+        src << "    fence_proxy_async();\n";
+        src << "    mbar_expect_tx(&mbar[s], bytes * " << P << "u);\n";
+        for (int r = 0; r < P; ++r)
+            src << "    tma_row(dst + " << r << " * GAAST_THREADS, s" << parked[size_t(r)]->stream << " + "
+                << parked[size_t(r)]->row << " * r" << parked[size_t(r)]->stream << " + e0, bytes, &mbar[s]);\n";
+        for (const Node* n : in_regs)
+            src << "    l2_prefetch_row(s" << n->stream << " + " << n->row << " * r" << n->stream << " + e0, bytes);\n";
+        src << "  };\n";
+        src << "  if (tid == 0) {\n";
+        src << "    if ((long long)blockIdx.x < n_tiles) issue(blockIdx.x, 0);\n";
+        src << "    if ((long long)blockIdx.x + gridDim.x < n_tiles) issue((long long)blockIdx.x + gridDim.x, 1);\n";
+        src << "  }\n";
+        src << "  int it = 0;\n";
+        src << "  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {\n";
+        src << loop_strides.str();
+        src << "    const int s = it & 1;\n";
+        src << "    const long long e_raw = tile * GAAST_THREADS + tid;\n";
+        src << "    const bool active = e_raw < a.n;\n";
+        src << "    const long long e = active ? e_raw : a.n - 1;  // idle lanes of the last tile shadow a valid element\n";
+        src << "    const unsigned xb = (unsigned)__cvta_generic_to_shared(stage0 + s * " << P
+            << " * GAAST_THREADS + (int)(e - tile * GAAST_THREADS));\n";
+        src << "    mbar_wait(&mbar[s], (unsigned)(it >> 1) & 1u);\n";
+        src << g.body.str();
+        src << "    __syncthreads();  // every thread is done with buffer s: refill it for tile + 2 * gridDim\n";
+        src << "    if (tid == 0) {\n";
+        src << "      const long long nt = tile + 2LL * gridDim.x;\n";
+        src << "      if (nt < n_tiles) issue(nt, s);\n";
+        src << "    }\n";
+        src << "  }\n";
+    } else {
+        if (n_smem_rows)
+            src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << res.n_sum_cols
+                << " * GAAST_THREADS + tid);\n";
+        src << "  for (long long e = ((long long)blockIdx.x * GAAST_THREADS + tid) * GAAST_EPT; e < a.n;\n"
+               "       e += (long long)gridDim.x * GAAST_THREADS * GAAST_EPT) {\n";
+        src << loop_strides.str();
+        src << g.body.str();
+        src << "  }\n";
+    }
     if (opt.with_sum) {
         src << "  __syncthreads();\n";
         src << "  for (int c = tid; c < " << root_cols << "; c += GAAST_THREADS) {\n";

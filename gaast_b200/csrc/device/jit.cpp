@@ -217,11 +217,14 @@ std::vector<char> build_specialized(const DevicePlanHost& h, CodegenOptions opt,
         cubin = jit_cubin(cg, key, origin, &log);
         const size_t spill = spill_bytes_from_log(log, cg.kernel_name);
         const bool can_park_more = cg.parked < cg.parkable && cg.elems_per_thread == 1;
-        if (spill == 0 || !can_park_more || attempt >= 8) {
+        if (std::getenv("GAAST_CODEGEN_DEBUG"))
+            std::fprintf(stderr, "[gaast codegen] attempt %d: parked=%d/%d spill=%zuB smem=%zuB %s\n", attempt, cg.parked,
+                         cg.parkable, spill, cg.smem_bytes, cg.notes.c_str());
+        if (spill <= 48 || !can_park_more || attempt >= 8) {
             *cg_out = std::move(cg);
             return cubin;
         }
-        opt.extra_parked += spill > 256 ? 16 : 8;
+        opt.extra_parked += spill > 256 ? 16 : (spill > 96 ? 8 : 4);  // a few spilled doubles are cheaper than a lost block per SM
     }
 }
 
@@ -241,6 +244,7 @@ std::shared_ptr<JitKernel> jit_load(const CodegenResult& cg, const std::vector<c
     k->min_blocks = cg.min_blocks;
     k->n_uniform = cg.n_uniform;
     k->smem_bytes = cg.smem_bytes;
+    k->pipelined = cg.pipelined;
     if (k->smem_bytes > 48 * 1024) {
         e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k->kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(k->smem_bytes));

@@ -288,6 +288,7 @@ gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, i
         opt.store_out = store_out != 0;
         opt.elems_per_thread = plan->force_ept;
         opt.variant = plan->variant;
+        opt.pipelined = !(opt.variant & 8);
         gaast::CodegenResult cg;
         std::string key, origin;
         gaast::build_specialized(plan->h, opt, &cg, &key, &origin);
@@ -413,7 +414,7 @@ gaast_status gaast_batch_zero(gaast_batch* b) {
 // ---------------------------------------------------------------- eval ----
 static std::shared_ptr<gaast::JitKernel> get_specialized(gaast_plan* plan, const gaast::CodegenOptions& opt) {
     auto key = std::make_tuple(opt.broadcast_slots, opt.arith, int(opt.with_sum), int(opt.store_out),
-                               opt.elems_per_thread, opt.variant);
+                               opt.elems_per_thread, opt.variant, int(opt.pipelined));
     auto it = plan->jit.find(key);
     if (it != plan->jit.end()) return it->second;
     gaast::CodegenResult cg;
@@ -465,6 +466,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                     if ((a.srow[i] & 1) || (reinterpret_cast<uintptr_t>(a.sptr[i]) & 15)) aligned = false;
                 }
                 if (!aligned) opt.elems_per_thread = 1;
+                opt.pipelined = aligned && !(opt.variant & 8);  // TMA bulk copies need 16-byte aligned row segments
                 jk = get_specialized(plan, opt);
             } catch (const Error& e) {
                 if (engine == GAAST_ENGINE_SPECIALIZED) throw;
@@ -482,10 +484,13 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         const long long blocks = (n + per_block - 1) / per_block;
         if (blocks > 0x7fffffffLL) throw Error(GAAST_ERR_SHAPE, "batch too long for one launch");
         grid = int(blocks);
-        if (with_sum) {
-            // the batch-sum epilogue keeps per-block partials: bound the grid, blocks stride over the batch
+        if (with_sum || jk->pipelined) {
+            // persistent grid: the batch-sum epilogue keeps per-block partials, and the TMA-pipelined
+            // kernels loop over their tiles; blocks stride over the batch
             const long long cap = (long long)ctx->sm_count * jk->blocks_per_sm;
             if (grid > cap) grid = int(cap);
+        }
+        if (with_sum) {
             ensure(plan->d_partials, plan->partials_cap, size_t(grid) * sum_cols);
             a.partials = plan->d_partials;
         }

@@ -27,7 +27,8 @@ struct JitKernel {
     int elems_per_thread = 1;
     int min_blocks = 1;
     int n_uniform = 0;      // doubles the uniform prologue writes
-    size_t smem_bytes = 0;  // dynamic shared memory (batch-sum accumulators)
+    size_t smem_bytes = 0;  // dynamic shared memory (batch-sum accumulators, parked rows)
+    bool pipelined = false; // persistent grid: blocks stride over the tiles
     int regs = 0;
     size_t local_bytes = 0; // spills
     int blocks_per_sm = 1;
@@ -41,6 +42,7 @@ struct CodegenOptions {
     bool store_out = true;
     int elems_per_thread = 0;  // 0 = choose
     int variant = 0;           // GAAST_CODEGEN_* bit flags (tuning knobs; 0 = defaults)
+    bool pipelined = true;     // parked rows arrive by TMA in a persistent, double-buffered block (needs 16-byte aligned rows)
     int extra_parked = 0;      // more input rows parked in shared memory (raised while ptxas reports spills)
 };
 
@@ -54,6 +56,7 @@ struct CodegenResult {
     int n_uniform = 0;
     int n_sum_cols = 0;
     size_t smem_bytes = 0;
+    bool pipelined = false;
     int parked = 0, parkable = 0;  // input rows parked in shared memory / rows that could be
     std::string notes;  // human-readable summary of the decisions taken
 };
@@ -129,7 +132,7 @@ struct gaast_plan {
     size_t uniform_cap = 0;
     std::string last_kernel;
     // specialised kernels, keyed by (broadcast slots, arith, with_sum, store_out, elems/thread, variant)
-    std::map<std::tuple<uint64_t, int, int, int, int, int>, std::shared_ptr<gaast::JitKernel>> jit;
+    std::map<std::tuple<uint64_t, int, int, int, int, int, int>, std::shared_ptr<gaast::JitKernel>> jit;
     std::string jit_error;  // sticky: why the specialised engine is unavailable
     int variant = 0;
     int force_ept = 0;
