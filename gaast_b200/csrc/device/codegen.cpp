@@ -592,12 +592,14 @@ __device__ __forceinline__ D U(double x) { return x; }
 __device__ __forceinline__ D d_load(const double* p) { return __ldg(p); }
 template <int OFF>
 __device__ __forceinline__ void xs_st(unsigned base, double v) {
-  asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(base), "n"(OFF), "d"(v) : "memory");
+  // no "memory" clobber: volatile asm statements keep their order among themselves, which is all
+  // the staging area needs, and ordinary loads / stores may be scheduled across them
+  asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(base), "n"(OFF), "d"(v));
 }
 template <int OFF>
 __device__ __forceinline__ double xs_ld(unsigned base) {
   double v;
-  asm volatile("ld.volatile.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(base), "n"(OFF) : "memory");
+  asm volatile("ld.volatile.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(base), "n"(OFF));
   return v;
 }
 // TMA (bulk async copy) + mbarrier plumbing of the pipelined kernels
@@ -693,7 +695,8 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             // right operands are re-fetched per tile; left ones too unless variant bit 2 keeps them in registers
             for (int id : rs)
                 if (g.nodes[id].k == N_LOAD) blocked_loads.insert(id);
-            if (!(opt.variant & 4))
+            // (measured on cfg3: left operand in registers 19.6 TFLOP/s, both parked 13.4)
+            if ((opt.variant & 4) || ls.size() > kAccBudget)
                 for (int id : ls)
                     if (g.nodes[id].k == N_LOAD) blocked_loads.insert(id);
         }
@@ -744,7 +747,11 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     res.elems_per_thread = ept;
     res.n_uniform = g.n_export;
     res.n_sum_cols = opt.with_sum ? int(root_cols) : 0;
-    const bool pipelined = opt.pipelined && n_smem_rows > 0 && ept == 1;
+    constexpr size_t kSmemLimit = 227 * 1024;
+    const size_t pipe_bytes = size_t(opt.with_sum ? root_cols : 0) * threads * 8 + size_t(2 * n_smem_rows) * threads * 8 + 16;
+    const bool pipelined = opt.pipelined && n_smem_rows > 0 && ept == 1 && pipe_bytes <= kSmemLimit / 2;
+    if (size_t((opt.with_sum ? root_cols : 0) + n_smem_rows) * threads * 8 > kSmemLimit)
+        throw Error(GAAST_ERR_JIT, "plan too wide for the specialised engine (shared-memory staging exceeds 227 KB)");
     g.pipelined = pipelined;
     res.pipelined = pipelined;
     res.smem_bytes = pipelined ? size_t(res.n_sum_cols + 2 * n_smem_rows) * threads * sizeof(double) + 16
@@ -833,6 +840,14 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         g.root_done.assign(slots.size(), 0);
         g.root_of.clear();
         g.emit_staging();
+        // Rows that stay in registers and are read by several terms are fetched in one
+        // burst at the top of the body: loads issued lazily in the middle of a
+        // register-bound body expose one full memory latency each.
+        if (!(opt.variant & 16))
+            for (size_t id = 0; id < g.nodes.size(); ++id) {
+                const Node& n = g.nodes[id];
+                if (n.live && n.k == N_LOAD && !n.uniform && !n.reload && uses[id] >= 2) g.emit(int(id));
+            }
         for (const auto& rs : slots) g.root_of.emplace(g.buf[0][rs.col].id, rs);
         for (const auto& rs : slots) {
             const int id = g.buf[0][rs.col].id;

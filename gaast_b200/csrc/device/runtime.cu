@@ -1,6 +1,7 @@
 // C ABI of the device side (include/gaast_b200.h): ctx, batch, plan, eval.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../runtime.hpp"
@@ -288,7 +289,7 @@ gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, i
         opt.store_out = store_out != 0;
         opt.elems_per_thread = plan->force_ept;
         opt.variant = plan->variant;
-        opt.pipelined = !(opt.variant & 8);
+        opt.pipelined = (opt.variant & 8) != 0;
         gaast::CodegenResult cg;
         std::string key, origin;
         gaast::build_specialized(plan->h, opt, &cg, &key, &origin);
@@ -466,7 +467,8 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                     if ((a.srow[i] & 1) || (reinterpret_cast<uintptr_t>(a.sptr[i]) & 15)) aligned = false;
                 }
                 if (!aligned) opt.elems_per_thread = 1;
-                opt.pipelined = aligned && !(opt.variant & 8);  // TMA bulk copies need 16-byte aligned row segments
+                // TMA-pipelined staging is opt-in (variant bit 3): measured slower than plain blocks on cfg3 / cfg5
+                opt.pipelined = aligned && (opt.variant & 8);  // TMA bulk copies need 16-byte aligned row segments
                 jk = get_specialized(plan, opt);
             } catch (const Error& e) {
                 if (engine == GAAST_ENGINE_SPECIALIZED) throw;
@@ -487,7 +489,9 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         if (with_sum || jk->pipelined) {
             // persistent grid: the batch-sum epilogue keeps per-block partials, and the TMA-pipelined
             // kernels loop over their tiles; blocks stride over the batch
-            const long long cap = (long long)ctx->sm_count * jk->blocks_per_sm;
+            long long mult = jk->pipelined ? 1 : 16;  // sum-only kernels: many short-lived blocks overlap better
+            if (const char* e = std::getenv("GAAST_GRID_MULT")) mult = std::max(1, std::atoi(e));
+            const long long cap = (long long)ctx->sm_count * jk->blocks_per_sm * mult;
             if (grid > cap) grid = int(cap);
         }
         if (with_sum) {
