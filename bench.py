@@ -36,10 +36,14 @@ def _peaks():
 
 
 # FP64 FMA-pipe peak measured with profiles/fp64_peak.cu on this pool; nominal 40 TFLOP/s
-FP64_PEAK_TFLOPS = float(os.environ.get("GAAST_FP64_PEAK_TFLOPS", "0") or 0) or None
+FP64_PEAK_TFLOPS = float(os.environ.get("GAAST_FP64_PEAK_TFLOPS", "0") or 0) or 36.84  # profiles/r1_fp64_peak.txt
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (profiles/), per workload
-NCU_TRAFFIC_BYTES = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the BASELINE batch, from the committed
+# `ncu --set full` captures (profiles/r1_*_ncu.txt; captures taken at batch 4M are scaled to the full batch)
+NCU_TRAFFIC_BYTES = {
+    "cfg2": 5321087000,                    # profiles/r1_cfg2_ncu.txt (algorithmic 5368709120)
+    "cfg3": int(6409129000 * 4),           # profiles/r1_cfg3_ncu.txt at 4M elements (algorithmic 6442450944 at 4M)
+}
 
 
 class ClockSampler:
@@ -293,7 +297,8 @@ def run_gpu(args):
         "gpu_launches": res["launches"],
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
                      "traffic": NCU_TRAFFIC_BYTES.get(w.name), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": n * res["bytes_per_elem"], "fp64_tflops": tflops},
+                     "algorithmic_bytes_per_launch": n * res["bytes_per_elem"], "fp64_tflops": tflops,
+                     "fp64_peak_tflops": FP64_PEAK_TFLOPS, "fp64_frac": tflops / FP64_PEAK_TFLOPS},
     }
     if clocks is not None:
         line["clocks"] = clocks
@@ -338,6 +343,8 @@ def run_gpu(args):
                                 "ms_per_step": r["ms_per_step"], "hbm_gbs": r["elements"] * r["bytes_per_elem"] / s / 1e9,
                                 "hbm_frac": r["elements"] * r["bytes_per_elem"] / s / 1e9 / peak_gbs,
                                 "fp64_tflops": r["elements"] * r["flops_per_elem"] / s / 1e12,
+                                "fp64_frac": r["elements"] * r["flops_per_elem"] / s / 1e12 / FP64_PEAK_TFLOPS,
+                                "bound": ow.bound, "ncu_traffic_bytes": NCU_TRAFFIC_BYTES.get(name),
                                 "batch": r["elements"], "kernel": r["kernel"]}
                 del r
             except Exception as ex:

@@ -193,11 +193,19 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
 // out[c] = sum over blocks of partials[b][c], in block order (deterministic).
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int n_blocks, int n_cols,
                                        double* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cols) return;
+    // one block per column; thread t adds blocks t, t+256, ... in order, then a fixed tree:
+    // the result depends on the launch shape only, never on timing
+    __shared__ double tree[256];
+    const int c = blockIdx.x;
     double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += partials[size_t(b) * n_cols + c];
-    out[c] = s;
+    for (int b = threadIdx.x; b < n_blocks; b += 256) s += partials[size_t(b) * n_cols + c];
+    tree[threadIdx.x] = s;
+    __syncthreads();
+    for (int half = 128; half > 0; half >>= 1) {
+        if (threadIdx.x < half) tree[threadIdx.x] += tree[threadIdx.x + half];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = tree[0];
 }
 
 template <bool kStrict, bool kSum>
@@ -248,7 +256,7 @@ cudaError_t table_engine_launch(const EvalArgs& args, const TableLaunch& shape, 
 cudaError_t reduce_partials_launch(const double* partials, int n_blocks, int n_cols, double* out,
                                    cudaStream_t stream) {
     if (n_cols <= 0) return cudaSuccess;
-    reduce_partials_kernel<<<(n_cols + 127) / 128, 128, 0, stream>>>(partials, n_blocks, n_cols, out);
+    reduce_partials_kernel<<<n_cols, 256, 0, stream>>>(partials, n_blocks, n_cols, out);
     return cudaGetLastError();
 }
 
