@@ -356,6 +356,9 @@ struct Gen {
     // All parked rows are fetched at the top of the element body (one burst of
     // independent loads), then stored to shared memory.
     bool pipelined = false;  // parked rows arrive by TMA (persistent block, double buffered), not by LDG + STS
+    bool guard_stores = false;  // block-uniform tile loop: lanes past the end of the batch compute but do not store
+    bool sum_in_smem = false;   // batch-sum kept as per-thread column sums in shared memory
+    bool sum_in_tmem = false;   // ... or in tensor memory (tcgen05.ld / tcgen05.st), the default when it fits
     void emit_staging() {
         if (pipelined) return;
         std::vector<int> ids;
@@ -469,12 +472,14 @@ struct Gen {
         if (in_prologue || root_done[rs.col]) return;
         root_done[rs.col] = 1;
         const std::string val = opnd(Ref{id, rs.neg}, true);
-        const std::string guard = pipelined ? "if (active) " : "";
+        const std::string guard = guard_stores ? "if (active) " : "";
         if (opt.store_out)
             line(guard + "d_store(s" + std::to_string(rs.stream) + " + " + std::to_string(rs.row) + " * r" +
                  std::to_string(rs.stream) + " + e, " + val + ");");
-        if (opt.with_sum)
+        if (sum_in_smem)
             line(guard + "sums[" + std::to_string(rs.col) + " * GAAST_THREADS + tid] += d_hsum(" + val + ");");
+        if (sum_in_tmem)  // warp-collective: idle lanes add zero
+            line("tm_add(tb + " + std::to_string(2 * rs.col) + "u, active ? d_hsum(" + val + ") : 0.0);");
     }
     void store_if_root(int id) {
         if (in_prologue) return;
@@ -602,6 +607,30 @@ __device__ __forceinline__ double xs_ld(unsigned base) {
   asm volatile("ld.volatile.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(base), "n"(OFF));
   return v;
 }
+// Tensor memory (TMEM) as per-thread scratch: one lane per thread, 32-bit columns
+__device__ __forceinline__ void tm_alloc(unsigned* slot, unsigned cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(slot)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tm_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;"); }
+__device__ __forceinline__ void tm_dealloc(unsigned taddr, unsigned cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tm_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_put(unsigned taddr, double v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__double2loint(v)),
+               "r"(__double2hiint(v)));
+}
+__device__ __forceinline__ double tm_get(unsigned taddr) {
+  unsigned lo, hi;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return __hiloint2double((int)hi, (int)lo);
+}
+__device__ __forceinline__ void tm_add(unsigned taddr, double v) { tm_put(taddr, tm_get(taddr) + v); }
 // TMA (bulk async copy) + mbarrier plumbing of the pipelined kernels
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -748,14 +777,28 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     res.n_uniform = g.n_export;
     res.n_sum_cols = opt.with_sum ? int(root_cols) : 0;
     constexpr size_t kSmemLimit = 227 * 1024;
-    const size_t pipe_bytes = size_t(opt.with_sum ? root_cols : 0) * threads * 8 + size_t(2 * n_smem_rows) * threads * 8 + 16;
+    // Batch-sum with the per-element result also stored: the block sums its own freshly
+    // written output tile back from L2 (row segments are contiguous), instead of keeping
+    // per-thread column sums in shared memory (measured: MIO-bound, profiles/r1_cfg5_sum_v2_ncu.txt).
+    // Batch-sum accumulators in tensor memory (2 columns per component and lane; allocations are
+    // powers of two >= 32 columns, and two resident blocks must share the SM's 512 columns).
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < 2 * root_cols) tmem_cols *= 2;
+    const bool tmem_sum = opt.with_sum && ept == 1 && !opt.pipelined && !(opt.variant & 32) && tmem_cols <= 256;
+    const size_t sum_doubles = !opt.with_sum ? 0
+                               : tmem_sum   ? ((threads / 32) * root_cols + 2 + 15) / 16 * 16
+                                            : root_cols * size_t(threads);
+    const size_t pipe_bytes = sum_doubles * 8 + size_t(2 * n_smem_rows) * threads * 8 + 16;
     const bool pipelined = opt.pipelined && n_smem_rows > 0 && ept == 1 && pipe_bytes <= kSmemLimit / 2;
-    if (size_t((opt.with_sum ? root_cols : 0) + n_smem_rows) * threads * 8 > kSmemLimit)
+    if (sum_doubles * 8 + size_t(n_smem_rows) * threads * 8 > kSmemLimit)
         throw Error(GAAST_ERR_JIT, "plan too wide for the specialised engine (shared-memory staging exceeds 227 KB)");
     g.pipelined = pipelined;
+    g.guard_stores = pipelined || tmem_sum;
+    g.sum_in_smem = opt.with_sum && !tmem_sum;
+    g.sum_in_tmem = tmem_sum;
     res.pipelined = pipelined;
-    res.smem_bytes = pipelined ? size_t(res.n_sum_cols + 2 * n_smem_rows) * threads * sizeof(double) + 16
-                               : size_t(res.n_sum_cols + n_smem_rows) * threads * sizeof(double);
+    res.smem_bytes = pipelined ? pipe_bytes : sum_doubles * 8 + size_t(n_smem_rows) * threads * sizeof(double);
+    if (tmem_sum) notes << "sum-in-tmem(" << tmem_cols << "cols) ";
     if (pipelined) notes << "tma-pipelined ";
     res.parked = res_parked;
     res.parkable = res_parkable;
@@ -859,7 +902,19 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     src << "  const int tid = threadIdx.x;\n";
     stream_decls(src, false);
     if (opt.with_sum || n_smem_rows) src << "  extern __shared__ double sums[];\n";
-    if (opt.with_sum) src << "  for (int c = 0; c < " << root_cols << "; ++c) sums[c * GAAST_THREADS + tid] = 0.0;\n";
+    if (g.sum_in_smem) src << "  for (int c = 0; c < " << root_cols << "; ++c) sums[c * GAAST_THREADS + tid] = 0.0;\n";
+    if (tmem_sum) {
+        // Batch-sum accumulators live in TENSOR MEMORY: each thread owns one TMEM lane, 2 columns
+        // per root component.  Registers are full and shared memory (MIO) is the saturated
+        // resource of these kernels (profiles/r1_cfg5_sum_v2_ncu.txt); TMEM has its own datapath.
+        src << "  const int lane = tid & 31, warp = tid >> 5;\n";
+        src << "  unsigned* const tslot = reinterpret_cast<unsigned*>(sums + " << (threads / 32) * root_cols << ");\n";
+        src << "  if (warp == 0) { tm_alloc(tslot, " << tmem_cols << "u); tm_relinquish(); }\n";
+        src << "  tm_fence_before_sync();\n  __syncthreads();\n  tm_fence_after_sync();\n";
+        src << "  const unsigned tmem_base = *tslot;\n";
+        src << "  const unsigned tb = tmem_base + ((unsigned)(warp * 32) << 16);\n";
+        src << "  for (int c = 0; c < " << root_cols << "; ++c) tm_put(tb + 2u * c, 0.0);\n";
+    }
     src << uni.str();
     if (pipelined) {
         // Persistent block, two staging buffers.  The TMA unit copies the parked rows
@@ -874,7 +929,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             if (n.reload) parked[size_t(n.smem_row)] = &n;
             else in_regs.push_back(&n);
         }
-        src << "  double* const stage0 = sums + " << res.n_sum_cols << " * GAAST_THREADS;\n";
+        src << "  double* const stage0 = sums + " << sum_doubles << ";\n";
         src << "  unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(stage0 + 2 * " << P
             << " * GAAST_THREADS);\n";
         src << "  const long long n_tiles = (a.n + GAAST_THREADS - 1) / GAAST_THREADS;\n";
@@ -914,17 +969,45 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         src << "      if (nt < n_tiles) issue(nt, s);\n";
         src << "    }\n";
         src << "  }\n";
+    } else if (tmem_sum) {
+        if (n_smem_rows)
+            src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << sum_doubles << " + tid);\n";
+        src << "  const long long n_tiles = (a.n + GAAST_THREADS - 1) / GAAST_THREADS;\n";
+        src << "  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n";
+        src << loop_strides.str();
+        src << "    const long long e0 = tile * GAAST_THREADS;\n";
+        src << "    const bool active = e0 + tid < a.n;\n";
+        src << "    const long long e = active ? e0 + tid : a.n - 1;  // idle lanes of the last tile shadow a valid element\n";
+        src << "    tm_wait_st();  // the previous tile's sum updates have landed in tensor memory\n";
+        src << g.body.str();
+        src << "  }\n";
     } else {
         if (n_smem_rows)
-            src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << res.n_sum_cols
-                << " * GAAST_THREADS + tid);\n";
+            src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << sum_doubles << " + tid);\n";
         src << "  for (long long e = ((long long)blockIdx.x * GAAST_THREADS + tid) * GAAST_EPT; e < a.n;\n"
                "       e += (long long)gridDim.x * GAAST_THREADS * GAAST_EPT) {\n";
         src << loop_strides.str();
         src << g.body.str();
         src << "  }\n";
     }
-    if (opt.with_sum) {
+    if (tmem_sum) {
+        // per-lane sums -> warp (shuffle tree) -> block (fixed warp order) -> partials
+        src << "  tm_wait_st();\n";
+        src << "  for (int c = 0; c < " << root_cols << "; ++c) {\n";
+        src << "    double v = tm_get(tb + 2u * c);\n";
+        src << "    #pragma unroll\n";
+        src << "    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);\n";
+        src << "    if (lane == 0) sums[warp * " << root_cols << " + c] = v;\n";
+        src << "  }\n";
+        src << "  tm_fence_before_sync();\n";
+        src << "  __syncthreads();\n";
+        src << "  for (int c = tid; c < " << root_cols << "; c += GAAST_THREADS) {\n";
+        src << "    double v = 0.0;\n";
+        src << "    for (int w = 0; w < GAAST_THREADS / 32; ++w) v += sums[w * " << root_cols << " + c];\n";
+        src << "    a.partials[(long long)blockIdx.x * " << root_cols << " + c] = v;\n";
+        src << "  }\n";
+        src << "  if (warp == 0) tm_dealloc(tmem_base, " << tmem_cols << "u);\n";
+    } else if (opt.with_sum) {
         src << "  __syncthreads();\n";
         src << "  for (int c = tid; c < " << root_cols << "; c += GAAST_THREADS) {\n";
         src << "    double s = 0.0;\n";

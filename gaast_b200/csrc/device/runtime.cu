@@ -486,7 +486,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         const long long blocks = (n + per_block - 1) / per_block;
         if (blocks > 0x7fffffffLL) throw Error(GAAST_ERR_SHAPE, "batch too long for one launch");
         grid = int(blocks);
-        if (with_sum || jk->pipelined) {
+        if (with_sum || jk->pipelined || std::getenv("GAAST_FORCE_PERSISTENT")) {
             // persistent grid: the batch-sum epilogue keeps per-block partials, and the TMA-pipelined
             // kernels loop over their tiles; blocks stride over the batch
             long long mult = jk->pipelined ? 1 : 16;  // sum-only kernels: many short-lived blocks overlap better
