@@ -678,6 +678,15 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     Gen g(h, opt);
     g.build();
     g.mark_live();
+    {
+        // Straight-line code costs ~16 bytes and a few compiler milliseconds per term: beyond
+        // ~24k live terms (a 1.5 MB kernel) the table engine is the better engine.
+        size_t live_terms = 0;
+        for (const Node& n : g.nodes) live_terms += n.live && n.k == N_ACC;
+        if (live_terms > 24576 && !(opt.variant & 64))
+            throw Error(GAAST_ERR_JIT, "plan too large for the specialised engine (" + std::to_string(live_terms) +
+                                           " live terms): use the table engine");
+    }
     g.mark_exports();
     g.compute_blades();
 

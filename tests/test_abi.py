@@ -77,3 +77,15 @@ def test_no_device_means_no_compute():
     with pytest.raises(g.GaastError) as ei:
         g.Ctx(0)
     assert ei.value.status == L.ERR_NO_DEVICE
+
+
+def test_huge_plans_are_left_to_the_table_engine():
+    """G(8,0) A*B has 65 536 terms: the code generator refuses, AUTO falls back to the table engine."""
+    from gaast_b200.expr import Input, mv
+    full = tuple(range(9))
+    ast = (mv(Input(0, full)) * mv(Input(1, full))).specialize([1.0] * 8)
+    plan = g.Plan(None, ast)
+    assert plan.cost() == (8 * 3 * 256, 2 * 65536)
+    with pytest.raises(g.GaastError) as ei:
+        plan.kernel_source()
+    assert ei.value.status == L.ERR_JIT and "table engine" in str(ei.value)

@@ -182,3 +182,24 @@ def test_wrap_torch_tensors(ctx):
     want = oracle_eval(w.build, w.metric, host, [False] * 3, batch)
     scale = oracle_abs_scale(w.build, w.metric, host, [False] * 3, batch)
     assert_close({2: out_t.cpu().numpy()}, want, scale)
+
+
+def test_wide_plan_auto_engine_uses_table_engine_with_global_workspace(ctx):
+    """G(9,0) full product: 262 144 terms and 1 536 workspace columns -- too large to
+    specialise and too wide for shared memory: AUTO runs the table engine with its
+    workspace in global memory; results still bit-identical to the oracle."""
+    n = 9
+    full = tuple(range(n + 1))
+    batch = 40
+    rng = np.random.default_rng(11)
+    host = [{k: rng.uniform(-1, 1, (comb(n, k), batch)) for k in full} for _ in range(2)]
+    build = lambda a, b: a * b  # noqa: E731
+    want = oracle_eval(build, [1.0] * n, host, [False, False], batch)
+    plan = g.Plan(ctx, build(pmv(Input(0, full)), pmv(Input(1, full))).specialize([1.0] * n))
+    dev = [g.DeviceBatch.from_host(ctx, n, h) for h in host]
+    out = plan.eval(dev, engine=L.ENGINE_AUTO, arith=L.ARITH_STRICT)
+    ctx.sync()
+    assert "engine=table" in plan.last_kernel() and "ws=global" in plan.last_kernel()
+    assert_bit_exact(out.to_host(), want, "G(9) full product, table engine, global workspace")
+    with pytest.raises(g.GaastError):
+        plan.eval(dev, engine=L.ENGINE_SPECIALIZED)
