@@ -396,11 +396,6 @@ struct Gen {
         return p_zero ? "d_mul(" + prod + ", " + cl + ")" : "d_fma(" + prod + ", " + cl + ", " + P + ")";
     }
 
-    bool skip_in_this_kernel(const Node& n) const {
-        // main kernel: uniform inner nodes are never computed, only exported ones are loaded
-        return !in_prologue && n.uniform && !is_leaf(n) && n.export_idx < 0;
-    }
-
     void emit(int id) {
         if (emitted[id]) return;
         Node& n = nodes[id];

@@ -124,8 +124,6 @@ void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_input
     a.store_out = out ? 1 : 0;
 }
 
-const char* engine_name(int e) { return e == GAAST_ENGINE_TABLE ? "table" : "specialized"; }
-
 }  // namespace
 
 gaast::JitKernel::~JitKernel() {
@@ -546,7 +544,6 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                    "launch partial-sum reduction");
         ctx->launches++;
     }
-    (void)engine_name;
 }
 
 gaast_status gaast_eval(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out, int engine,

@@ -61,15 +61,17 @@ __device__ __forceinline__ double term_acc(double acc, double l, double r, doubl
     return fma(l * c, r, acc);
 }
 
-template <bool kStrict, bool kSum>
+// kGlobalWs is a template parameter so that, in the common case, the compiler knows the
+// workspace is shared memory and emits LDS/STS instead of generic loads and stores.
+template <bool kStrict, bool kSum, bool kGlobalWs>
 __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant__ EvalArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TermChunk* stage = reinterpret_cast<TermChunk*>(smem_raw);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + kBarOffset);
     const int T = blockDim.x, tid = threadIdx.x;
     const int cols = a.total_cols + (kSum ? a.n_sum_cols : 0);
-    double* ws = a.ws_global ? a.ws_global + size_t(blockIdx.x) * cols * T
-                             : reinterpret_cast<double*>(smem_raw + kWsOffset);
+    double* ws = kGlobalWs ? a.ws_global + size_t(blockIdx.x) * cols * T
+                           : reinterpret_cast<double*>(smem_raw + kWsOffset);
     double* w = ws + tid;  // column c of this thread's element: w[c * T]
 
     if (tid == 0) {
@@ -134,6 +136,20 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
                             const uint32_t end = ch.run_start[r + 1];
                             double* o = wd + size_t(ch.terms[s].out) * T;
                             double acc = *o;
+                            // four terms per trip: their 4 table reads and 8 operand reads are
+                            // independent, only the accumulator chains (reference order kept)
+                            for (; s + 4 <= end; s += 4) {
+                                const gaast_term t0 = ch.terms[s], t1 = ch.terms[s + 1], t2 = ch.terms[s + 2],
+                                                 t3 = ch.terms[s + 3];
+                                const double l0 = wl[size_t(t0.a) * T], r0 = wr[size_t(t0.b) * T];
+                                const double l1 = wl[size_t(t1.a) * T], r1 = wr[size_t(t1.b) * T];
+                                const double l2 = wl[size_t(t2.a) * T], r2 = wr[size_t(t2.b) * T];
+                                const double l3 = wl[size_t(t3.a) * T], r3 = wr[size_t(t3.b) * T];
+                                acc = term_acc<kStrict>(acc, l0, r0, t0.coeff);
+                                acc = term_acc<kStrict>(acc, l1, r1, t1.coeff);
+                                acc = term_acc<kStrict>(acc, l2, r2, t2.coeff);
+                                acc = term_acc<kStrict>(acc, l3, r3, t3.coeff);
+                            }
                             for (; s < end; ++s) {
                                 const gaast_term t = ch.terms[s];
                                 acc = term_acc<kStrict>(acc, wl[size_t(t.a) * T], wr[size_t(t.b) * T], t.coeff);
@@ -208,13 +224,18 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
     if (threadIdx.x == 0) out[c] = tree[0];
 }
 
-template <bool kStrict, bool kSum>
-cudaError_t launch_t(const EvalArgs& args, const TableLaunch& shape, cudaStream_t stream) {
-    auto k = table_engine_kernel<kStrict, kSum>;
+template <bool kStrict, bool kSum, bool kGlobalWs>
+cudaError_t launch_g(const EvalArgs& args, const TableLaunch& shape, cudaStream_t stream) {
+    auto k = table_engine_kernel<kStrict, kSum, kGlobalWs>;
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shape.smem));
     if (err != cudaSuccess) return err;
     k<<<shape.grid, shape.threads, shape.smem, stream>>>(args);
     return cudaGetLastError();
+}
+template <bool kStrict, bool kSum>
+cudaError_t launch_t(const EvalArgs& args, const TableLaunch& shape, cudaStream_t stream) {
+    return shape.global_ws ? launch_g<kStrict, kSum, true>(args, shape, stream)
+                           : launch_g<kStrict, kSum, false>(args, shape, stream);
 }
 
 }  // namespace

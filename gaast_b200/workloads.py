@@ -208,10 +208,15 @@ def torch_inputs(w: Workload, length: int, device, seed: int = None):
 
 
 # ---- build-time kernel cache --------------------------------------------------------
-def precompile_all(verbose: bool = False) -> int:
+def precompile_all(verbose: bool = False, fresh: bool = True) -> int:
     """Generate + compile the specialised kernels of every workload (no device needed)."""
+    import os
+    import shutil
     from . import _lib as L
     from .device import Plan
+    if fresh and "GAAST_KERNEL_CACHE" not in os.environ:
+        # entries are keyed by a hash of their source: drop the ones older generators left behind
+        shutil.rmtree(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kernel_cache"), ignore_errors=True)
     count = 0
     for w in WORKLOADS.values():
         plan = Plan(None, specialize(w))
