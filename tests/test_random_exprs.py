@@ -1,0 +1,159 @@
+"""Differential testing on random expressions: random algebra (dimension, mixed
+signature incl. degenerate and non-unit metrics), random input grade sets, random
+operator trees built from the reference's operators.
+
+CPU (always): host mirror + lowering, executed literally with numpy, must equal the
+oracle bit for bit -- or both must reject the expression (the reference panics on
+some trees, e.g. additions whose children cannot produce the wanted grades).
+GPU: both CUDA engines in strict arithmetic must equal the oracle bit for bit."""
+import random
+from math import comb
+
+import numpy as np
+import pytest
+
+import gaast_b200 as g
+from gaast_b200 import _lib as L
+from gaast_b200.expr import Input, mv as pmv
+from oracle import gaast_oracle as go
+from tests.helpers import assert_bit_exact, oracle_expr, run_plan_numpy
+
+BATCH = 19
+
+
+def random_case(seed):
+    rnd = random.Random(seed)
+    n = rnd.choice([2, 3, 3, 4, 4, 5, 6])
+    metric = [rnd.choice([1.0, 1.0, 1.0, -1.0, -1.0, 0.0, 2.0, -0.5]) for _ in range(n)]
+    n_slots = rnd.choice([1, 2, 2, 3])
+    slots = []
+    for _ in range(n_slots):
+        kind = rnd.random()
+        if kind < 0.35:
+            grades = tuple(range(n + 1))
+        elif kind < 0.6:
+            grades = (rnd.randrange(0, n + 1),)
+        else:
+            grades = tuple(sorted(rnd.sample(range(n + 1), rnd.randint(1, min(3, n + 1)))))
+        slots.append((grades, rnd.random() < 0.15))
+    program = []  # a tiny stack machine, replayed identically on both expression APIs
+
+    def gen(depth):
+        if depth == 0 or rnd.random() < 0.25:
+            program.append(("leaf", rnd.randrange(n_slots)))
+            return
+        op = rnd.choice(["mul", "mul", "wedge", "inner", "lc", "rc", "add", "sub", "neg", "rev", "ginvol", "conj",
+                         "g", "scal", "norm_sq", "scale", "div", "vinv_vec", "sqrt_norm", "clone_twice"])
+        if op in ("mul", "wedge", "inner", "lc", "rc", "add", "sub", "scal"):
+            gen(depth - 1)
+            gen(depth - 1)
+            program.append((op,))
+        elif op == "g":
+            gen(depth - 1)
+            program.append(("g", rnd.randrange(0, n + 1)))
+        elif op == "scale":
+            gen(depth - 1)
+            program.append(("scale", rnd.choice([2.0, -0.5, 3.25])))
+        elif op == "div":
+            gen(depth - 1)
+            program.append(("div", rnd.choice([2.0, 4.0, -8.0])))
+        elif op == "vinv_vec":
+            program.append(("leaf", rnd.randrange(n_slots)))
+            program.append(("g", 1))
+            program.append(("vinv",))
+        elif op == "sqrt_norm":
+            gen(depth - 1)
+            program.append(("norm_sq",))
+            program.append(("sqrt",))
+        elif op == "clone_twice":
+            gen(depth - 1)
+            program.append(("dup_mul",))
+        else:
+            gen(depth - 1)
+            program.append((op,))
+
+    gen(rnd.choice([1, 2, 2, 3]))
+    return n, metric, slots, program
+
+
+def replay(program, leaves):
+    st = []
+    for ins in program:
+        op = ins[0]
+        if op == "leaf":
+            st.append(leaves[ins[1]].clone())
+        elif op in ("mul", "wedge", "inner", "lc", "rc", "add", "sub", "scal"):
+            b, a = st.pop(), st.pop()
+            st.append({"mul": lambda: a * b, "wedge": lambda: a ^ b, "inner": lambda: a & b, "lc": lambda: a << b,
+                       "rc": lambda: a >> b, "add": lambda: a + b, "sub": lambda: a - b,
+                       "scal": lambda: a.scal(b)}[op]())
+        elif op == "g":
+            st.append(st.pop().g(ins[1]))
+        elif op == "scale":
+            st.append(st.pop() * ins[1])
+        elif op == "div":
+            st.append(st.pop() / ins[1])
+        elif op == "dup_mul":
+            a = st.pop()
+            st.append(a.clone() * a.rev())
+        else:
+            a = st.pop()
+            st.append({"neg": lambda: -a, "rev": a.rev, "ginvol": a.ginvol, "conj": a.conj, "norm_sq": a.norm_sq,
+                       "vinv": a.vinv, "sqrt": a.sqrt}[op]())
+    assert len(st) == 1
+    return st[0]
+
+
+def evaluate_case(seed):
+    """Returns (plan_dict or None, inputs, want or None, (n, metric, slots, ast))."""
+    n, metric, slots, program = random_case(seed)
+    rng = np.random.default_rng(seed)
+    inputs = [{k: rng.uniform(-1, 1, (comb(n, k), 1 if bc else BATCH)) for k in grades} for grades, bc in slots]
+    bcs = [bc for _, bc in slots]
+    oracle_error = mine_error = None
+    want = ast = None
+    try:
+        oast = oracle_expr(lambda *lv: replay(program, lv), inputs, bcs).specialize(go.Algebra(metric))
+        res = oast.eval(BATCH)
+        want = {k: (v if v.ndim == 2 else np.repeat(v[:, None], BATCH, 1)) for k, v in res.m.items()}
+    except (AssertionError, NotImplementedError, KeyError) as e:
+        oracle_error = type(e).__name__
+    try:
+        leaves = [pmv(Input(s, grades)) for s, (grades, _) in enumerate(slots)]
+        ast = replay(program, leaves).specialize(metric)
+        ast.lower()
+    except g.GaastError as e:
+        mine_error = e.status
+        ast = None
+    return n, metric, slots, inputs, want, ast, oracle_error, mine_error
+
+
+SEEDS = list(range(120))
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_random_expression_cpu(seed):
+    n, metric, slots, inputs, want, ast, oracle_error, mine_error = evaluate_case(seed)
+    if oracle_error is not None:
+        # the reference panics (assert / unwrap / todo!) on this tree: the mirror must refuse it too
+        assert mine_error in (L.ERR_PANIC, L.ERR_UNSUPPORTED), (oracle_error, mine_error)
+        return
+    assert mine_error is None, f"mirror rejected an expression the oracle accepts (status {mine_error})"
+    got = run_plan_numpy(ast.plan_dict(), inputs, BATCH)
+    assert_bit_exact(got, want, f"seed {seed}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", SEEDS[:60])
+def test_random_expression_gpu(seed):
+    n, metric, slots, inputs, want, ast, oracle_error, mine_error = evaluate_case(seed)
+    if oracle_error is not None or ast is None:
+        pytest.skip("the reference rejects this expression")
+    ctx = g.Ctx(0)
+    plan = g.Plan(ctx, ast)
+    dev = [g.DeviceBatch.from_host(ctx, n, inputs[s], broadcast=bc) for s, (_, bc) in enumerate(slots)]
+    dev = dev[:plan.num_slots()]
+    for engine in (L.ENGINE_TABLE, L.ENGINE_SPECIALIZED):
+        out = plan.eval(dev, engine=engine, arith=L.ARITH_STRICT)
+        ctx.sync()
+        assert_bit_exact(out.to_host(), want, f"seed {seed} engine {engine}")
