@@ -60,11 +60,12 @@ struct Node {
     bool uniform = false;
     bool reload = false;  // LOAD: parked in the thread's shared-memory column, re-read at every use
     int smem_row = -1;    // reload: its row in the per-block staging area
+    bool pinned = false;  // LOAD: must stay in a register (statically indexed operand of a rolled product)
     bool live = false;
     int export_idx = -1;  // uniform boundary node: index in EvalArgs::uniform
 };
 
-enum Policy { P_TABLE, P_GATHER, P_BLOCKED };
+enum Policy { P_TABLE, P_GATHER, P_BLOCKED, P_DENSE };
 
 std::string lit(double v) {
     char buf[64];
@@ -414,6 +415,10 @@ struct Gen {
                 emit_op_blocked(n.op);
                 return;
             }
+            if (pol == P_DENSE) {
+                emit_op_dense(n.op);
+                return;
+            }
             // GATHER: walk the chain back to its first un-emitted link, then forward
             std::vector<int> chain;
             int cur = id;
@@ -569,6 +574,177 @@ struct Gen {
     }
     int blocked_low_bits = 4;
 
+    // ---- DENSE: a full geometric product written straight to the root, as a ROLLED loop ----
+    // G(n) = G(hi) (x) G(lo) with lo = the 4 lowest basis vectors.  For blades a = (ah, al),
+    // b = (bh, bl) the coefficient factorises:  c(a,b) = sigma(ah,bh) * (-1)^(|ah||bl|) * lambda(al,bl)
+    // (pairs (i in a, j in b, i > j): hi-hi, hi-lo = all of them, lo-hi = none, lo-lo).
+    // So all tiles of the Cayley table are the SAME 256-FMA lo-product up to a per-tile factor
+    // and a grade involution of the right operand's lo part.  The kernel loops over the output
+    // coset oh (not unrolled: the right operand's rows, the tile factor and the output rows are
+    // looked up), with the 2^hi left cosets unrolled (left operand in registers).  Code size
+    // drops from 2^(2n) to 2^hi * 256 FMAs (cfg3: 64 KB -> 16 KB, inside the instruction cache:
+    // the straight-line version lost 1.25 of 5.3 stall cycles per instruction to `no_instruction`).
+    struct Dense {
+        int op = -1, n = 0, H = 1;
+        std::vector<Ref> left;          // [blade]
+        std::vector<int> right;         // [blade] parked load nodes
+        std::vector<int> out_col;       // [blade] root column
+        std::vector<char> out_neg;      // [blade]
+        std::vector<double> sigma;      // [ah * H + bh]
+        std::vector<double> lambda;     // [al * 16 + bl]
+        bool unit_sigma = true;
+    } dense;
+    std::ostringstream file_scope, kernel_setup;
+    size_t setup_doubles = 0;  // shared memory reserved ahead of the sums / staging areas
+
+    bool plan_dense(int op, const std::vector<int>& refcount) {
+        const gaast_op& pop = h.ops[op];
+        const int n = int(h.n), hb = blocked_low_bits;
+        if (n <= hb || n > 6 || pop.dst != 0) return false;
+        const size_t B = size_t(1) << n;
+        Dense d;
+        d.op = op;
+        d.n = n;
+        d.H = 1 << (n - hb);
+        d.left.assign(B, Ref{-1, false});
+        d.right.assign(B, -1);
+        d.out_col.assign(B, -1);
+        d.out_neg.assign(B, 0);
+        d.sigma.assign(size_t(d.H) * d.H, 0.0);
+        d.lambda.assign(256, 0.0);
+        std::vector<double> coeff(B * B, 0.0);
+        std::vector<char> seen(B * B, 0);
+        std::vector<int> last(B, -1);
+        size_t count = 0;
+        for (int id : op_accs[op]) {
+            const Node& nd = nodes[id];
+            if (!nd.live || nd.uniform) return false;
+            const uint32_t a = slot_blade[pop.a][nd.l_slot], b = slot_blade[pop.b][nd.r_slot];
+            const uint32_t o = slot_blade[pop.dst][nd.out_slot];
+            if ((a ^ b) != o || seen[a * B + b]) return false;
+            seen[a * B + b] = 1;
+            coeff[a * B + b] = nd.cval;
+            ++count;
+            if (d.left[a].id >= 0 && (d.left[a].id != nd.b.id || d.left[a].neg != nd.b.neg)) return false;
+            d.left[a] = nd.b;
+            const Node& r = nodes[nd.c.id];
+            if (r.k != N_LOAD || r.uniform || nd.c.neg) return false;
+            if (d.right[b] >= 0 && d.right[b] != nd.c.id) return false;
+            d.right[b] = nd.c.id;
+            if (last[o] < 0 && !is_zero(nd.a)) return false;  // accumulators must start from zero
+            last[o] = id;
+        }
+        if (count != B * B) return false;
+        // every output must be a root component, used by nothing else
+        for (size_t o = 0; o < B; ++o) {
+            if (last[o] < 0 || refcount[last[o]] != 0) return false;
+            for (size_t col = 0; col < buf[0].size(); ++col)
+                if (buf[0][col].id == last[o]) {
+                    if (d.out_col[o] >= 0 || buf[0][col].neg) return false;
+                    d.out_col[o] = int(col);
+                }
+            if (d.out_col[o] < 0) return false;
+        }
+        // factorisation, verified term by term
+        const uint32_t lo = (1u << hb) - 1;
+        for (int ah = 0; ah < d.H; ++ah)
+            for (int bh = 0; bh < d.H; ++bh) {
+                d.sigma[ah * d.H + bh] = coeff[(size_t(ah) << hb) * B + (size_t(bh) << hb)];
+                if (std::fabs(d.sigma[ah * d.H + bh]) != 1.0) d.unit_sigma = false;
+            }
+        for (uint32_t al = 0; al <= lo; ++al)
+            for (uint32_t bl = 0; bl <= lo; ++bl) d.lambda[al * 16 + bl] = coeff[size_t(al) * B + bl];
+        for (size_t a = 0; a < B; ++a)
+            for (size_t b = 0; b < B; ++b) {
+                const int ah = int(a >> hb), bh = int(b >> hb);
+                const uint32_t al = uint32_t(a) & lo, bl = uint32_t(b) & lo;
+                const double chi = (__builtin_popcount(ah) * __builtin_popcount(bl)) & 1 ? -1.0 : 1.0;
+                if (coeff[a * B + b] != d.sigma[ah * d.H + bh] * chi * d.lambda[al * 16 + bl]) return false;
+            }
+        dense = d;
+        return true;
+    }
+
+    void emit_op_dense(int op) {
+        const Dense& d = dense;
+        const int hb = blocked_low_bits, B = 1 << d.n;
+        // root column -> (stream, row)
+        std::vector<std::pair<size_t, uint32_t>> col_at;
+        for (size_t si = h.n_in_streams; si < h.streams.size(); ++si)
+            for (uint32_t r = 0; r < h.streams[si].rows; ++r) col_at.push_back({si, r});
+        const size_t root0 = h.n_in_streams;
+        // ---- lookup tables (constant memory) ----
+        file_scope << "__constant__ unsigned kDenseB[" << B << "] = {";
+        for (int b = 0; b < B; ++b)
+            file_scope << (b ? ", " : "") << size_t(nodes[d.right[b]].smem_row) * 8 << " * GAAST_THREADS";
+        file_scope << "};\n__constant__ unsigned short kDenseOutStream[" << B << "] = {";
+        for (int o = 0; o < B; ++o) file_scope << (o ? ", " : "") << col_at[d.out_col[o]].first;
+        file_scope << "};\n__constant__ unsigned short kDenseOutRow[" << B << "] = {";
+        for (int o = 0; o < B; ++o) file_scope << (o ? ", " : "") << col_at[d.out_col[o]].second;
+        file_scope << "};\n";
+        if (d.unit_sigma) {
+            file_scope << "__constant__ unsigned kDenseSigma[" << d.H * d.H << "] = {";  // [ah][oh] sign-bit masks
+            for (int ah = 0; ah < d.H; ++ah)
+                for (int oh = 0; oh < d.H; ++oh)
+                    file_scope << ((ah || oh) ? ", " : "") << (d.sigma[ah * d.H + (oh ^ ah)] < 0 ? "0x80000000u" : "0u");
+        } else {
+            file_scope << "__constant__ double kDenseSigma[" << d.H * d.H << "] = {";
+            for (int ah = 0; ah < d.H; ++ah)
+                for (int oh = 0; oh < d.H; ++oh) file_scope << ((ah || oh) ? ", " : "") << lit(d.sigma[ah * d.H + (oh ^ ah)]);
+        }
+        file_scope << "};\n";
+        // ---- per-block table of output offsets (the root's grade arrays are separate allocations) ----
+        kernel_setup << "  long long* const dense_out = reinterpret_cast<long long*>(sums);\n";
+        kernel_setup << "  if (tid < " << B << ")\n    dense_out[tid] = (long long)(a.sptr[kDenseOutStream[tid]] - a.sptr[" << root0
+                     << "]) + (long long)kDenseOutRow[tid] * a.srow[kDenseOutStream[tid]];\n  __syncthreads();\n";
+        // ---- left operand: registers ----
+        for (int a = 0; a < B; ++a) emit(d.left[a].id);
+        line("#pragma unroll 1");
+        line("for (int oh = 0; oh < " + std::to_string(d.H) + "; ++oh) {");
+        ++indent;
+        for (int ol = 0; ol < 16; ++ol) line("double q" + std::to_string(ol) + " = 0.0;");
+        for (int ah = 0; ah < d.H; ++ah) {
+            line("{");
+            ++indent;
+            line("const unsigned* const rows = kDenseB + ((oh ^ " + std::to_string(ah) + ") << " + std::to_string(hb) + ");");
+            line((d.unit_sigma ? std::string("const unsigned sg = ") : std::string("const double sg = ")) + "kDenseSigma[" +
+                 std::to_string(ah * d.H) + " + oh];");
+            const bool odd = __builtin_popcount(ah) & 1;
+            for (int bl = 0; bl < 16; ++bl) {
+                const std::string raw = "xs_ldd(xb + rows[" + std::to_string(bl) + "])";
+                if (d.unit_sigma)
+                    line("const double b" + std::to_string(bl) + " = flip_sign(" + raw + ", sg);");
+                else
+                    line("const double b" + std::to_string(bl) + " = " + raw + " * sg;");
+            }
+            for (int al = 0; al < 16; ++al)
+                for (int bl = 0; bl < 16; ++bl) {
+                    double cc = d.lambda[al * 16 + bl];
+                    if (odd && (__builtin_popcount(bl) & 1)) cc = -cc;
+                    if (cc == 0.0) continue;
+                    const std::string q = "q" + std::to_string(al ^ bl);
+                    const std::string A = opnd(d.left[(ah << hb) + al], true, cc < 0);
+                    const std::string Bv = "b" + std::to_string(bl);
+                    if (std::fabs(cc) == 1.0)
+                        line(q + " = d_fma(" + A + ", " + Bv + ", " + q + ");");
+                    else
+                        line(q + " = d_fma(d_mul(" + A + ", " + Bv + "), " + lit(std::fabs(cc)) + ", " + q + ");");
+                }
+            --indent;
+            line("}");
+        }
+        // ---- store the finished coset ----
+        if (opt.store_out) {
+            line("double* const ro = s" + std::to_string(root0) + " + e;");
+            for (int ol = 0; ol < 16; ++ol)
+                line("ro[dense_out[(oh << " + std::to_string(hb) + ") + " + std::to_string(ol) + "]] = q" + std::to_string(ol) + ";");
+        }
+        --indent;
+        line("}");
+        for (int id : op_accs[op]) emitted[id] = 1;
+        for (int o = 0; o < B; ++o) root_done[d.out_col[o]] = 1;
+    }
+
 };
 
 const char kPrelude[] = R"GAAST(
@@ -601,6 +777,14 @@ __device__ __forceinline__ double xs_ld(unsigned base) {
   double v;
   asm volatile("ld.volatile.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(base), "n"(OFF));
   return v;
+}
+__device__ __forceinline__ double xs_ldd(unsigned addr) {
+  double v;
+  asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double flip_sign(double v, unsigned mask) {
+  return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
 }
 // Tensor memory (TMEM) as per-thread scratch: one lane per thread, 32-bit columns
 __device__ __forceinline__ void tm_alloc(unsigned* slot, unsigned cols) {
@@ -723,7 +907,21 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         if (dense && outs.size() <= 2 * kAccBudget) pol = P_BLOCKED;
         if (opt.variant & 1) pol = P_TABLE;
         if (opt.variant & 2) pol = P_GATHER;
+        if (pol == P_BLOCKED && !opt.with_sum && !opt.pipelined && !(opt.variant & 512) && g.dense.op < 0) {
+            std::vector<int> refcount(g.nodes.size(), 0);
+            for (const Node& n : g.nodes) {
+                if (!n.live) continue;
+                if (n.k == N_ACC) { ++refcount[n.a.id]; ++refcount[n.b.id]; ++refcount[n.c.id]; }
+                else if (n.k == N_ADD) { ++refcount[n.a.id]; ++refcount[n.b.id]; }
+                else if (n.k == N_INV || n.k == N_SQRT) ++refcount[n.a.id];
+            }
+            if (g.plan_dense(int(oi), refcount)) pol = P_DENSE;
+        }
         g.op_policy[oi] = pol;
+        if (pol == P_DENSE) {  // right operand parked (rows looked up per tile), left operand in registers
+            for (int id : rs) blocked_loads.insert(id);
+            for (int id : ls) g.nodes[id].pinned = true;
+        }
         if (pol == P_BLOCKED) {
             // right operands are re-fetched per tile; left ones too unless variant bit 2 keeps them in registers
             for (int id : rs)
@@ -735,7 +933,8 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         }
         if (pol == P_TABLE) widest_table = std::max(widest_table, outs.size());
         widest = std::max(widest, outs.size());
-        notes << "op" << oi << ":" << (pol == P_TABLE ? "table" : pol == P_GATHER ? "gather" : "blocked")
+        notes << "op" << oi << ":"
+              << (pol == P_TABLE ? "table" : pol == P_GATHER ? "gather" : pol == P_DENSE ? "dense-rolled" : "blocked")
               << "(outs=" << outs.size() << ",terms=" << live_terms << ") ";
     }
     for (int id : blocked_loads) g.nodes[id].reload = true;
@@ -748,7 +947,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             const Node& n = g.nodes[id];
             if (!n.live || n.k != N_LOAD || n.uniform || n.reload) continue;
             ++kept;
-            if (uses[id] > 1) cand.push_back({uses[id], int(id)});
+            if (uses[id] > 1 && !n.pinned) cand.push_back({uses[id], int(id)});
         }
         size_t pressure = widest_table + kept + 12;
         size_t want = pressure > kLiveBudget ? pressure - kLiveBudget : 0;
@@ -789,19 +988,27 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2 * root_cols) tmem_cols *= 2;
     const bool tmem_sum = opt.with_sum && ept == 1 && !opt.pipelined && !(opt.variant & 32) && tmem_cols <= 256;
-    const size_t sum_doubles = !opt.with_sum ? 0
-                               : tmem_sum   ? ((threads / 32) * root_cols + 2 + 15) / 16 * 16
-                                            : root_cols * size_t(threads);
+    const size_t sum_doubles = g.dense.op >= 0 ? (size_t(1) << h.n)  // table of output offsets (dense excludes the sum)
+                               : !opt.with_sum ? 0
+                               : tmem_sum      ? ((threads / 32) * root_cols + 2 + 15) / 16 * 16
+                                               : root_cols * size_t(threads);
     const size_t pipe_bytes = sum_doubles * 8 + size_t(2 * n_smem_rows) * threads * 8 + 16;
     const bool pipelined = opt.pipelined && n_smem_rows > 0 && ept == 1 && pipe_bytes <= kSmemLimit / 2;
     if (sum_doubles * 8 + size_t(n_smem_rows) * threads * 8 > kSmemLimit)
         throw Error(GAAST_ERR_JIT, "plan too wide for the specialised engine (shared-memory staging exceeds 227 KB)");
+    // TMA staging pays off when most rows are parked (dense products: cfg3 21.2 -> 22.8 TFLOP/s);
+    // with a few dozen parked rows next to register rows, LDG + STS is as fast (cfg5: 0.83 vs 0.80)
+    bool has_dense = false;
+    for (Policy p : g.op_policy) has_dense |= p == P_DENSE || p == P_BLOCKED;
+    const bool tma_stage = opt.tma_stage && has_dense && n_smem_rows > 0 && ept == 1 && !pipelined && !opt.with_sum;
     g.pipelined = pipelined;
     g.guard_stores = pipelined || tmem_sum;
     g.sum_in_smem = opt.with_sum && !tmem_sum;
     g.sum_in_tmem = tmem_sum;
     res.pipelined = pipelined;
-    res.smem_bytes = pipelined ? pipe_bytes : sum_doubles * 8 + size_t(n_smem_rows) * threads * sizeof(double);
+    res.smem_bytes = pipelined ? pipe_bytes : sum_doubles * 8 + size_t(n_smem_rows) * threads * sizeof(double) + (tma_stage ? 16 : 0);
+    res.one_tile_blocks = tma_stage;
+    if (tma_stage) notes << "tma-staged ";
     if (tmem_sum) notes << "sum-in-tmem(" << tmem_cols << "cols) ";
     if (pipelined) notes << "tma-pipelined ";
     res.parked = res_parked;
@@ -886,7 +1093,9 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
                 slots.push_back(Gen::RootSlot{si, r, col, g.buf[0][col].neg});
         g.root_done.assign(slots.size(), 0);
         g.root_of.clear();
-        g.emit_staging();
+        // one-tile blocks with TMA staging: the parked rows are already on their way to shared
+        // memory (bulk copies issued by thread 0 at kernel start); otherwise LDG + STS here
+        if (!tma_stage) g.emit_staging();
         // Rows that stay in registers and are read by several terms are fetched in one
         // burst at the top of the body: loads issued lazily in the middle of a
         // register-bound body expose one full memory latency each.
@@ -895,6 +1104,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
                 const Node& n = g.nodes[id];
                 if (n.live && n.k == N_LOAD && !n.uniform && !n.reload && uses[id] >= 2) g.emit(int(id));
             }
+        if (tma_stage) g.line("mbar_wait(stage_bar, 0u);  // parked rows have landed");
         for (const auto& rs : slots) g.root_of.emplace(g.buf[0][rs.col].id, rs);
         for (const auto& rs : slots) {
             const int id = g.buf[0][rs.col].id;
@@ -902,10 +1112,12 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             g.emit_root(rs, id);   // ... everything else (leaves, sums, unary results) is stored here
         }
     }
+    src << g.file_scope.str();
     src << "extern \"C\" __global__ void __launch_bounds__(GAAST_THREADS) gaast_eval(const __grid_constant__ EvalArgs a) {\n";
     src << "  const int tid = threadIdx.x;\n";
     stream_decls(src, false);
     if (opt.with_sum || n_smem_rows) src << "  extern __shared__ double sums[];\n";
+    src << g.kernel_setup.str();
     if (g.sum_in_smem) src << "  for (int c = 0; c < " << root_cols << "; ++c) sums[c * GAAST_THREADS + tid] = 0.0;\n";
     if (tmem_sum) {
         // Batch-sum accumulators live in TENSOR MEMORY: each thread owns one TMEM lane, 2 columns
@@ -983,6 +1195,35 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         src << "    const bool active = e0 + tid < a.n;\n";
         src << "    const long long e = active ? e0 + tid : a.n - 1;  // idle lanes of the last tile shadow a valid element\n";
         src << "    tm_wait_st();  // the previous tile's sum updates have landed in tensor memory\n";
+        src << g.body.str();
+        src << "  }\n";
+    } else if (tma_stage) {
+        // One tile per block.  Thread 0 hands the tile's parked rows to the TMA unit (one bulk
+        // copy per row segment, completion on an mbarrier) before anything else; every thread
+        // then issues the loads of its register rows and only waits for the TMA data afterwards.
+        const int P = n_smem_rows;
+        std::vector<const Node*> parked(size_t(P), nullptr);
+        for (const Node& n : g.nodes)
+            if (n.live && n.k == N_LOAD && !n.uniform && n.reload) parked[size_t(n.smem_row)] = &n;
+        src << "  double* const stage0 = sums + " << sum_doubles << ";\n";
+        src << "  unsigned long long* const stage_bar = reinterpret_cast<unsigned long long*>(stage0 + " << P
+            << " * GAAST_THREADS);\n";
+        src << "  const long long e0 = (long long)blockIdx.x * GAAST_THREADS;\n";
+        src << "  if (tid == 0) { mbar_init(stage_bar, 1); fence_mbar_init(); }\n";
+        src << "  __syncthreads();\n";
+        src << "  if (tid == 0 && e0 < a.n) {\n";
+        src << "    const long long left = a.n - e0;\n";
+        src << "    const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * 8);\n";
+        src << "    fence_proxy_async();\n";
+        src << "    mbar_expect_tx(stage_bar, bytes * " << P << "u);\n";
+        for (int r = 0; r < P; ++r)
+            src << "    tma_row(stage0 + " << r << " * GAAST_THREADS, s" << parked[size_t(r)]->stream << " + "
+                << parked[size_t(r)]->row << " * r" << parked[size_t(r)]->stream << " + e0, bytes, stage_bar);\n";
+        src << "  }\n";
+        src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(stage0 + tid);\n";
+        src << "  const long long e = e0 + tid;\n";
+        src << "  if (e < a.n) {\n";
+        src << loop_strides.str();
         src << g.body.str();
         src << "  }\n";
     } else {

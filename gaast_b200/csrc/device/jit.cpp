@@ -245,6 +245,7 @@ std::shared_ptr<JitKernel> jit_load(const CodegenResult& cg, const std::vector<c
     k->n_uniform = cg.n_uniform;
     k->smem_bytes = cg.smem_bytes;
     k->pipelined = cg.pipelined;
+    k->one_tile_blocks = cg.one_tile_blocks;
     if (k->smem_bytes > 48 * 1024) {
         e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k->kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(k->smem_bytes));

@@ -288,6 +288,7 @@ gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, i
         opt.elems_per_thread = plan->force_ept;
         opt.variant = plan->variant;
         opt.pipelined = (opt.variant & 8) != 0;
+        opt.tma_stage = !opt.pipelined && !opt.with_sum && !(opt.variant & 1024);
         gaast::CodegenResult cg;
         std::string key, origin;
         gaast::build_specialized(plan->h, opt, &cg, &key, &origin);
@@ -413,7 +414,7 @@ gaast_status gaast_batch_zero(gaast_batch* b) {
 // ---------------------------------------------------------------- eval ----
 static std::shared_ptr<gaast::JitKernel> get_specialized(gaast_plan* plan, const gaast::CodegenOptions& opt) {
     auto key = std::make_tuple(opt.broadcast_slots, opt.arith, int(opt.with_sum), int(opt.store_out),
-                               opt.elems_per_thread, opt.variant, int(opt.pipelined));
+                               opt.elems_per_thread, opt.variant, int(opt.pipelined), int(opt.tma_stage));
     auto it = plan->jit.find(key);
     if (it != plan->jit.end()) return it->second;
     gaast::CodegenResult cg;
@@ -467,6 +468,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                 if (!aligned) opt.elems_per_thread = 1;
                 // TMA-pipelined staging is opt-in (variant bit 3): measured slower than plain blocks on cfg3 / cfg5
                 opt.pipelined = aligned && (opt.variant & 8);  // TMA bulk copies need 16-byte aligned row segments
+                opt.tma_stage = aligned && !opt.pipelined && !with_sum && !(opt.variant & 1024);
                 jk = get_specialized(plan, opt);
             } catch (const Error& e) {
                 if (engine == GAAST_ENGINE_SPECIALIZED) throw;
@@ -484,7 +486,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         const long long blocks = (n + per_block - 1) / per_block;
         if (blocks > 0x7fffffffLL) throw Error(GAAST_ERR_SHAPE, "batch too long for one launch");
         grid = int(blocks);
-        if (with_sum || jk->pipelined || std::getenv("GAAST_FORCE_PERSISTENT")) {
+        if ((with_sum || jk->pipelined || std::getenv("GAAST_FORCE_PERSISTENT")) && !jk->one_tile_blocks) {
             // persistent grid: the batch-sum epilogue keeps per-block partials, and the TMA-pipelined
             // kernels loop over their tiles; blocks stride over the batch
             long long mult = jk->pipelined ? 1 : 16;  // sum-only kernels: many short-lived blocks overlap better

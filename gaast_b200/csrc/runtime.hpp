@@ -29,6 +29,7 @@ struct JitKernel {
     int n_uniform = 0;      // doubles the uniform prologue writes
     size_t smem_bytes = 0;  // dynamic shared memory (batch-sum accumulators, parked rows)
     bool pipelined = false; // persistent grid: blocks stride over the tiles
+    bool one_tile_blocks = false;
     int regs = 0;
     size_t local_bytes = 0; // spills
     int blocks_per_sm = 1;
@@ -43,6 +44,7 @@ struct CodegenOptions {
     int elems_per_thread = 0;  // 0 = choose
     int variant = 0;           // GAAST_CODEGEN_* bit flags (tuning knobs; 0 = defaults)
     bool pipelined = true;     // parked rows arrive by TMA in a persistent, double-buffered block (needs 16-byte aligned rows)
+    bool tma_stage = false;    // one-tile blocks: parked rows copied to shared memory by TMA bulk copies (aligned rows)
     int extra_parked = 0;      // more input rows parked in shared memory (raised while ptxas reports spills)
 };
 
@@ -57,6 +59,7 @@ struct CodegenResult {
     int n_sum_cols = 0;
     size_t smem_bytes = 0;
     bool pipelined = false;
+    bool one_tile_blocks = false;  // the kernel handles exactly one tile per block: the grid must cover the batch
     int parked = 0, parkable = 0;  // input rows parked in shared memory / rows that could be
     std::string notes;  // human-readable summary of the decisions taken
 };
@@ -132,7 +135,7 @@ struct gaast_plan {
     size_t uniform_cap = 0;
     std::string last_kernel;
     // specialised kernels, keyed by (broadcast slots, arith, with_sum, store_out, elems/thread, variant)
-    std::map<std::tuple<uint64_t, int, int, int, int, int, int>, std::shared_ptr<gaast::JitKernel>> jit;
+    std::map<std::tuple<uint64_t, int, int, int, int, int, int, int>, std::shared_ptr<gaast::JitKernel>> jit;
     std::string jit_error;  // sticky: why the specialised engine is unavailable
     int variant = 0;
     int force_ept = 0;
