@@ -520,9 +520,8 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     } else {
         gaast::TableLaunch shape = gaast::table_engine_shape(*ctx, h, n, with_sum);
         grid = shape.grid;
-        const size_t cols = h.total_cols + (with_sum ? sum_cols : 0);
         if (shape.global_ws) {
-            ensure(plan->d_ws, plan->ws_cap, size_t(grid) * cols * shape.threads);
+            ensure(plan->d_ws, plan->ws_cap, size_t(grid) * shape.ws_doubles_per_block);
             a.ws_global = plan->d_ws;
         }
         if (with_sum) {

@@ -61,18 +61,26 @@ __device__ __forceinline__ double term_acc(double acc, double l, double r, doubl
     return fma(l * c, r, acc);
 }
 
+// Thread layout: lane = batch element (32 per block and tile), warp = work group.  The
+// element's workspace is shared by the block's warps: inside a micro-op they split the rows
+// (loads, sign flips, stores) or the output runs of a term chunk (products), so a block
+// keeps 8 warps busy on 32 elements' worth of shared memory -- 4-8x the warps a
+// thread-per-element layout could hold.  Two runs never write the same output inside a
+// chunk, chunks are separated by a barrier, and a run accumulates its terms in table order:
+// every component still sums in the reference's order.
 // kGlobalWs is a template parameter so that, in the common case, the compiler knows the
 // workspace is shared memory and emits LDS/STS instead of generic loads and stores.
+constexpr int kLanes = 32;
 template <bool kStrict, bool kSum, bool kGlobalWs>
 __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant__ EvalArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TermChunk* stage = reinterpret_cast<TermChunk*>(smem_raw);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + kBarOffset);
-    const int T = blockDim.x, tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5, G = blockDim.x >> 5;
     const int cols = a.total_cols + (kSum ? a.n_sum_cols : 0);
-    double* ws = kGlobalWs ? a.ws_global + size_t(blockIdx.x) * cols * T
+    double* ws = kGlobalWs ? a.ws_global + size_t(blockIdx.x) * cols * kLanes
                            : reinterpret_cast<double*>(smem_raw + kWsOffset);
-    double* w = ws + tid;  // column c of this thread's element: w[c * T]
+    double* w = ws + lane;  // column c of this lane's element: w[c * kLanes]
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -80,11 +88,11 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (kSum)
-        for (int c = 0; c < a.n_sum_cols; ++c) w[size_t(a.total_cols + c) * T] = 0.0;
+        for (int c = grp; c < a.n_sum_cols; c += G) w[size_t(a.total_cols + c) * kLanes] = 0.0;
     __syncthreads();
 
-    const long long tile_step = (long long)gridDim.x * T;
-    const long long first = (long long)blockIdx.x * T;
+    const long long tile_step = (long long)gridDim.x * kLanes;
+    const long long first = (long long)blockIdx.x * kLanes;
     long long n_tiles = first < a.n ? (a.n - first + tile_step - 1) / tile_step : 0;
     const long long total_chunks = n_tiles * a.n_chunks;  // chunk loads this block will consume
     long long q = 0;                                       // running chunk sequence number
@@ -98,9 +106,10 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
     if (tid == 0 && total_chunks > 0) issue(0);
 
     for (long long base = first; base < a.n; base += tile_step) {
-        const long long e = base + tid;
+        const long long e = base + lane;
         const bool active = e < a.n;
-        for (int c = 0; c < a.total_cols; ++c) w[size_t(c) * T] = 0.0;  // init_null_mv, eval.rs:27-30
+        for (int c = grp; c < a.total_cols; c += G) w[size_t(c) * kLanes] = 0.0;  // init_null_mv, eval.rs:27-30
+        __syncthreads();
 
         for (int m = 0; m < a.n_micro; ++m) {
             const MicroOp op = a.micro[m];
@@ -109,42 +118,42 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
                     const bool bc = (a.bcast[op.a >> 6] >> (op.a & 63)) & 1;
                     const double* src = a.sptr[op.a] + (long long)op.b * a.srow[op.a] + (bc ? 0 : e);
                     const long long rs = a.srow[op.a];
-                    for (uint32_t r = 0; r < op.count; ++r) {
-                        double* d = &w[size_t(op.dst_col + r) * T];
+                    for (uint32_t r = grp; r < op.count; r += G) {
+                        double* d = &w[size_t(op.dst_col + r) * kLanes];
                         const double v = active ? __ldg(src + r * rs) : 0.0;
                         *d = kStrict ? __dadd_rn(*d, v) : (*d + v);
                     }
                     break;
                 }
                 case MK_CONST_ADD:
-                    for (uint32_t r = 0; r < op.count; ++r) {
-                        double* d = &w[size_t(op.dst_col + r) * T];
+                    for (uint32_t r = grp; r < op.count; r += G) {
+                        double* d = &w[size_t(op.dst_col + r) * kLanes];
                         *d = *d + a.consts[op.a + r];
                     }
                     break;
                 case MK_MUL: {  // eval.rs:61-86
-                    const double* wl = w + size_t(op.a) * T;
-                    const double* wr = w + size_t(op.b) * T;
-                    double* wd = w + size_t(op.dst_col) * T;
+                    const double* wl = w + size_t(op.a) * kLanes;
+                    const double* wr = w + size_t(op.b) * kLanes;
+                    double* wd = w + size_t(op.dst_col) * kLanes;
                     for (uint32_t ci = 0; ci < op.count; ++ci) {
                         if (tid == 0 && q + 1 < total_chunks) issue(q + 1);
                         mbar_wait(&mbar[q & 1], unsigned(q >> 1) & 1);
                         const TermChunk& ch = stage[q & 1];
                         const uint32_t n_runs = ch.n_runs;
-                        uint32_t s = ch.run_start[0];
-                        for (uint32_t r = 0; r < n_runs; ++r) {
+                        for (uint32_t r = grp; r < n_runs; r += G) {  // this warp's output runs
+                            uint32_t s = ch.run_start[r];
                             const uint32_t end = ch.run_start[r + 1];
-                            double* o = wd + size_t(ch.terms[s].out) * T;
+                            double* o = wd + size_t(ch.terms[s].out) * kLanes;
                             double acc = *o;
                             // four terms per trip: their 4 table reads and 8 operand reads are
                             // independent, only the accumulator chains (reference order kept)
                             for (; s + 4 <= end; s += 4) {
                                 const gaast_term t0 = ch.terms[s], t1 = ch.terms[s + 1], t2 = ch.terms[s + 2],
                                                  t3 = ch.terms[s + 3];
-                                const double l0 = wl[size_t(t0.a) * T], r0 = wr[size_t(t0.b) * T];
-                                const double l1 = wl[size_t(t1.a) * T], r1 = wr[size_t(t1.b) * T];
-                                const double l2 = wl[size_t(t2.a) * T], r2 = wr[size_t(t2.b) * T];
-                                const double l3 = wl[size_t(t3.a) * T], r3 = wr[size_t(t3.b) * T];
+                                const double l0 = wl[size_t(t0.a) * kLanes], r0 = wr[size_t(t0.b) * kLanes];
+                                const double l1 = wl[size_t(t1.a) * kLanes], r1 = wr[size_t(t1.b) * kLanes];
+                                const double l2 = wl[size_t(t2.a) * kLanes], r2 = wr[size_t(t2.b) * kLanes];
+                                const double l3 = wl[size_t(t3.a) * kLanes], r3 = wr[size_t(t3.b) * kLanes];
                                 acc = term_acc<kStrict>(acc, l0, r0, t0.coeff);
                                 acc = term_acc<kStrict>(acc, l1, r1, t1.coeff);
                                 acc = term_acc<kStrict>(acc, l2, r2, t2.coeff);
@@ -152,55 +161,58 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
                             }
                             for (; s < end; ++s) {
                                 const gaast_term t = ch.terms[s];
-                                acc = term_acc<kStrict>(acc, wl[size_t(t.a) * T], wr[size_t(t.b) * T], t.coeff);
+                                acc = term_acc<kStrict>(acc, wl[size_t(t.a) * kLanes], wr[size_t(t.b) * kLanes], t.coeff);
                             }
                             *o = acc;
                         }
-                        __syncthreads();  // stage q&1 may be refilled by the load issued next iteration
+                        __syncthreads();  // stage q&1 may be refilled; the next chunk may continue an output
                         ++q;
                     }
                     break;
                 }
                 case MK_NEG:  // graded.rs:61-65
-                    for (uint32_t r = 0; r < op.count; ++r) {
-                        double* d = &w[size_t(op.dst_col + r) * T];
+                    for (uint32_t r = grp; r < op.count; r += G) {
+                        double* d = &w[size_t(op.dst_col + r) * kLanes];
                         *d = -*d;
                     }
                     break;
-                case MK_INV: {  // eval.rs:107
-                    double* d = &w[size_t(op.dst_col) * T];
-                    *d = __ddiv_rn(1.0, *d);
+                case MK_INV:  // eval.rs:107
+                    if (grp == 0) {
+                        double* d = &w[size_t(op.dst_col) * kLanes];
+                        *d = __ddiv_rn(1.0, *d);
+                    }
                     break;
-                }
-                case MK_SQRT: {  // eval.rs:108
-                    double* d = &w[size_t(op.dst_col) * T];
-                    *d = __dsqrt_rn(*d);
+                case MK_SQRT:  // eval.rs:108
+                    if (grp == 0) {
+                        double* d = &w[size_t(op.dst_col) * kLanes];
+                        *d = __dsqrt_rn(*d);
+                    }
                     break;
-                }
                 case MK_STORE: {
                     double* dst = a.sptr[op.a] + (long long)op.b * a.srow[op.a] + e;
                     const long long rs = a.srow[op.a];
-                    for (uint32_t r = 0; r < op.count; ++r) {
-                        const double v = w[size_t(op.dst_col + r) * T];
+                    for (uint32_t r = grp; r < op.count; r += G) {
+                        const double v = w[size_t(op.dst_col + r) * kLanes];
                         if (active && a.store_out) dst[r * rs] = v;
                         if (kSum && active) {
-                            double* sc = &w[size_t(a.total_cols + (op.dst_col - a.root_col) + r) * T];
+                            double* sc = &w[size_t(a.total_cols + (op.dst_col - a.root_col) + r) * kLanes];
                             *sc = *sc + v;
                         }
                     }
                     break;
                 }
             }
+            if (op.kind != MK_MUL) __syncthreads();  // the next micro-op may read what other warps wrote
         }
     }
 
     if (kSum) {
-        // Fixed-order block reduction of the per-thread column sums.
+        // Fixed-order block reduction of the per-lane column sums.
         __syncthreads();
-        for (int c = tid; c < a.n_sum_cols; c += T) {
-            const double* col = ws + size_t(a.total_cols + c) * T;
+        for (int c = tid; c < a.n_sum_cols; c += blockDim.x) {
+            const double* col = ws + size_t(a.total_cols + c) * kLanes;
             double s = 0.0;
-            for (int t = 0; t < T; ++t) s += col[t];
+            for (int t = 0; t < kLanes; ++t) s += col[t];
             a.partials[size_t(blockIdx.x) * a.n_sum_cols + c] = s;
         }
     }
@@ -243,27 +255,15 @@ cudaError_t launch_t(const EvalArgs& args, const TableLaunch& shape, cudaStream_
 TableLaunch table_engine_shape(const gaast_ctx& ctx, const DevicePlanHost& h, long long n, bool with_sum) {
     TableLaunch s;
     const size_t cols = h.total_cols + (with_sum ? h.buf_cols[0] : 0);
-    const size_t avail = ctx.smem_optin > kWsOffset ? size_t(ctx.smem_optin - kWsOffset) : 0;
-    int t = int(avail / (cols * sizeof(double))) / 32 * 32;
-    if (t >= 32) {
-        s.threads = t > 256 ? 256 : t;
-        s.smem = kWsOffset + cols * sizeof(double) * s.threads;
-        s.global_ws = false;
-    } else {
-        s.threads = 128;
-        s.smem = kWsOffset;
-        s.global_ws = true;
-    }
-    long long tiles = (n + s.threads - 1) / s.threads;
-    int per_sm = 1;
-    if (!s.global_ws) {
-        per_sm = int(size_t(ctx.smem_optin) / (s.smem + 1024));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm * s.threads > 2048) per_sm = 2048 / s.threads;
-    } else {
-        per_sm = 4;
-    }
-    long long g = (long long)ctx.sm_count * per_sm;
+    const size_t ws_bytes = cols * sizeof(double) * kLanes;  // one tile = 32 elements
+    s.threads = 256;                                         // 8 warps share the tile's work
+    s.global_ws = kWsOffset + ws_bytes > size_t(ctx.smem_optin);
+    s.smem = s.global_ws ? kWsOffset : kWsOffset + ws_bytes;
+    s.ws_doubles_per_block = cols * kLanes;
+    const long long tiles = (n + kLanes - 1) / kLanes;
+    int per_sm = int(size_t(ctx.smem_optin) / (s.smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);  // 2048 threads per SM
+    const long long g = (long long)ctx.sm_count * per_sm;
     s.grid = int(tiles < g ? (tiles > 0 ? tiles : 1) : g);
     return s;
 }

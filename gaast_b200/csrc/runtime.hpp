@@ -86,6 +86,7 @@ struct TableLaunch {
     int grid = 0;
     size_t smem = 0;
     bool global_ws = false;
+    size_t ws_doubles_per_block = 0;  // global workspace: columns x 32 lanes
 };
 TableLaunch table_engine_shape(const gaast_ctx& ctx, const DevicePlanHost& h, long long n, bool with_sum);
 cudaError_t table_engine_launch(const EvalArgs& args, const TableLaunch& shape, bool strict, bool with_sum,
