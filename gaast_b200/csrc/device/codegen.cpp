@@ -212,6 +212,137 @@ struct Gen {
         }
     }
 
+    // ---- shared-operand lowering: the expression as a linear map of its batch inputs ----------
+    // When every operand a batch value meets is shared by the whole batch (a fixed rotor in
+    // R X ~R, a fixed B in B C, literals), each root component is  sum_j M_j x_j + m  with
+    // coefficients M_j, m that depend on the shared operands only.  The coefficients are built
+    // as uniform nodes -- the one-thread prologue kernel evaluates them once per launch -- and
+    // the per-element kernel shrinks to one FMA per (root component, batch component) pair:
+    // cfg2 goes from 160 to 25 FMAs per element.  Summation order differs from the reference
+    // (results stay within the 1e-12 bar); never applied in strict arithmetic.
+    static constexpr int kConstKey = -1;
+    using LinMap = std::map<int, Ref>;  // batch load node (or kConstKey) -> uniform coefficient
+
+    Ref flip(Ref r, bool neg) const { return Ref{r.id, bool(r.neg ^ neg)}; }
+    bool uniform_only(const LinMap& m) const { return m.empty() || (m.size() == 1 && m.begin()->first == kConstKey); }
+
+    // keys-only analysis: false = not linear in the batch inputs
+    bool lin_keys(int id, std::vector<char>& state, std::vector<std::set<int>>& keys) {
+        if (state[id]) return state[id] == 1;
+        const Node& n = nodes[id];
+        std::set<int> k;
+        bool ok = true;
+        auto uni = [](const std::set<int>& s) { return s.empty() || (s.size() == 1 && *s.begin() == kConstKey); };
+        switch (n.k) {
+            case N_ZERO: break;
+            case N_CONST: k.insert(kConstKey); break;
+            case N_LOAD: k.insert(n.uniform ? kConstKey : id); break;
+            case N_ADD:
+                ok = lin_keys(n.a.id, state, keys) && lin_keys(n.b.id, state, keys);
+                if (ok) { k = keys[n.a.id]; k.insert(keys[n.b.id].begin(), keys[n.b.id].end()); }
+                break;
+            case N_ACC:
+                ok = lin_keys(n.a.id, state, keys) && lin_keys(n.b.id, state, keys) && lin_keys(n.c.id, state, keys);
+                if (ok) {
+                    const bool lu = uni(keys[n.b.id]), ru = uni(keys[n.c.id]);
+                    if (!lu && !ru) { ok = false; break; }
+                    k = keys[n.a.id];
+                    if (!keys[n.b.id].empty() && !keys[n.c.id].empty()) {
+                        const std::set<int>& other = lu ? keys[n.c.id] : keys[n.b.id];
+                        k.insert(other.begin(), other.end());
+                    }
+                }
+                break;
+            case N_INV:
+            case N_SQRT:
+                ok = lin_keys(n.a.id, state, keys) && uni(keys[n.a.id]);
+                if (ok) k.insert(kConstKey);
+                break;
+        }
+        state[id] = ok ? 1 : 2;
+        keys[id] = std::move(k);
+        return ok;
+    }
+
+    Ref umul(Ref u, Ref v, double c, int op) {  // uniform * uniform * c
+        if (is_zero(u) || is_zero(v) || c == 0.0) return Ref{0, false};
+        if (nodes[u.id].k == N_CONST && nodes[u.id].cval == 1.0 && std::fabs(c) == 1.0) return flip(v, u.neg ^ (c < 0));
+        if (nodes[v.id].k == N_CONST && nodes[v.id].cval == 1.0 && std::fabs(c) == 1.0) return flip(u, v.neg ^ (c < 0));
+        return make_acc(Ref{0, false}, u, v, c, op);
+    }
+
+    const LinMap& lin_build(int id, std::map<int, LinMap>& memo, Ref one, int op) {
+        auto it = memo.find(id);
+        if (it != memo.end()) return it->second;
+        const Node n = nodes[id];  // copy: `nodes` grows below
+        LinMap m;
+        auto accumulate = [&](LinMap& dst, int key, Ref coef) {
+            if (is_zero(coef)) return;
+            auto f = dst.find(key);
+            if (f == dst.end()) dst.emplace(key, coef);
+            else f->second = make_add(f->second, coef);
+        };
+        switch (n.k) {
+            case N_ZERO: break;
+            case N_CONST: m.emplace(kConstKey, Ref{id, false}); break;
+            case N_LOAD:
+                if (n.uniform) m.emplace(kConstKey, Ref{id, false});
+                else m.emplace(id, one);
+                break;
+            case N_ADD:
+                for (const auto& kv : LinMap(lin_build(n.a.id, memo, one, op))) accumulate(m, kv.first, flip(kv.second, n.a.neg));
+                for (const auto& kv : LinMap(lin_build(n.b.id, memo, one, op))) accumulate(m, kv.first, flip(kv.second, n.b.neg));
+                break;
+            case N_ACC: {
+                for (const auto& kv : LinMap(lin_build(n.a.id, memo, one, op))) accumulate(m, kv.first, flip(kv.second, n.a.neg));
+                const LinMap L = lin_build(n.b.id, memo, one, op), R = lin_build(n.c.id, memo, one, op);
+                if (L.empty() || R.empty()) break;
+                const bool left_uniform = uniform_only(L);
+                const LinMap& U = left_uniform ? L : R;
+                const LinMap& V = left_uniform ? R : L;
+                const Ref u = flip(U.begin()->second, left_uniform ? n.b.neg : n.c.neg);
+                const bool vneg = left_uniform ? n.c.neg : n.b.neg;
+                for (const auto& kv : V) accumulate(m, kv.first, umul(u, flip(kv.second, vneg), n.cval, op));
+                break;
+            }
+            case N_INV:
+            case N_SQRT: m.emplace(kConstKey, Ref{id, false}); break;  // uniform argument (checked by lin_keys)
+        }
+        return memo.emplace(id, std::move(m)).first->second;
+    }
+
+    // Returns the number of root components rewritten (0 = lowering not applicable / not worthwhile).
+    size_t lower_linear(int pseudo_op) {
+        if (strict) return 0;
+        std::vector<char> state(nodes.size(), 0);
+        std::vector<std::set<int>> keys(nodes.size());
+        size_t entries = 0, batch_keys = 0;
+        for (Ref r : buf[0]) {
+            if (!lin_keys(r.id, state, keys)) return 0;
+            entries += keys[r.id].size();
+            for (int k : keys[r.id]) batch_keys += k != kConstKey;
+        }
+        size_t terms = 0;
+        for (const Node& n : nodes) terms += n.live && n.k == N_ACC && !n.uniform;
+        if (batch_keys == 0 || entries > 4096 || terms < 2 * entries) return 0;
+        const Ref one = constant(1.0);
+        std::map<int, LinMap> memo;
+        size_t rewritten = 0;
+        for (Ref& r : buf[0]) {
+            const LinMap m = lin_build(r.id, memo, one, pseudo_op);
+            Ref acc{0, false};
+            auto c = m.find(kConstKey);
+            if (c != m.end()) acc = c->second;
+            for (const auto& kv : m) {
+                if (kv.first == kConstKey) continue;
+                acc = make_acc(acc, kv.second, Ref{kv.first, false}, 1.0, pseudo_op);
+            }
+            r = flip(acc, r.neg);
+            ++rewritten;
+        }
+        return rewritten;
+    }
+
     void mark_live() {
         std::vector<int> stack;
         for (Ref r : buf[0]) stack.push_back(r.id);
@@ -276,6 +407,7 @@ struct Gen {
     std::ostringstream body;
     std::vector<char> emitted;
     bool in_prologue = false;
+    bool in_loop = false;  // emitting the per-element body (not the hoisted shared values)
     int indent = 2;
 
     std::string var(int id) const { return "v" + std::to_string(id); }
@@ -304,7 +436,9 @@ struct Gen {
         const std::string ty = wide ? "const D " : "const double ";
         const std::string v = var(id);
         if (!in_prologue && n.uniform && n.export_idx >= 0) {
-            line("const double " + v + " = __ldg(a.uniform + " + std::to_string(n.export_idx) + ");");
+            // inside the element loop the table pointer is opaque (`uni`), so that the compiler
+            // does not hoist a wide table into registers
+            line("const double " + v + " = __ldg(" + (in_loop ? "uni" : "a.uniform") + " + " + std::to_string(n.export_idx) + ");");
             return;
         }
         switch (n.k) {
@@ -857,6 +991,17 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     Gen g(h, opt);
     g.build();
     g.mark_live();
+    std::ostringstream notes;
+    const int pseudo_op = int(h.ops.size());  // the linear-map lowering's FMAs belong to an extra "op"
+    g.op_accs.resize(h.ops.size() + 1);
+    if (!(opt.variant & 2048)) {
+        const size_t lowered = g.lower_linear(pseudo_op);
+        if (lowered) {
+            for (Node& n : g.nodes) n.live = false;
+            g.mark_live();
+            notes << "linear-map(" << lowered << " outputs) ";
+        }
+    }
     {
         // Straight-line code costs ~16 bytes and a few compiler milliseconds per term: beyond
         // ~24k live terms (a 1.5 MB kernel) the table engine is the better engine.
@@ -875,10 +1020,10 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         if (n.live && n.k == N_LOAD && !n.uniform) ++live_loads;
     const size_t root_cols = h.buf_cols[0];
     constexpr size_t kAccBudget = 72;  // doubles a thread can keep as accumulators next to its operands
-    g.op_policy.assign(h.ops.size(), P_TABLE);
+    g.op_policy.assign(h.ops.size() + 1, P_TABLE);
     size_t widest = 0;
-    std::ostringstream notes;
     int res_parked = 0, res_parkable = 0;
+    size_t live_estimate = 0;  // doubles a thread keeps live (widest in-register product + resident rows)
     constexpr size_t kDenseBudget = 110;  // doubles: outputs + operands of a product that may all be live
     constexpr size_t kLiveBudget = 124;   // doubles a thread can hold in 255 registers next to addresses
     std::vector<int> uses(g.nodes.size(), 0);  // how many live product terms read each node
@@ -937,6 +1082,12 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
               << (pol == P_TABLE ? "table" : pol == P_GATHER ? "gather" : pol == P_DENSE ? "dense-rolled" : "blocked")
               << "(outs=" << outs.size() << ",terms=" << live_terms << ") ";
     }
+    for (int id : g.op_accs[pseudo_op]) {
+        const Node& n = g.nodes[id];
+        if (!n.live || n.uniform) continue;
+        ++uses[n.b.id];
+        ++uses[n.c.id];
+    }
     for (int id : blocked_loads) g.nodes[id].reload = true;
     // Register pressure of everything else: the widest in-register product plus the
     // input rows that stay live.  Rows with the fewest uses are re-fetched first.
@@ -950,8 +1101,9 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             if (uses[id] > 1 && !n.pinned) cand.push_back({uses[id], int(id)});
         }
         size_t pressure = widest_table + kept + 12;
+        live_estimate = pressure;
         size_t want = pressure > kLiveBudget ? pressure - kLiveBudget : 0;
-        if (opt.variant >> 8) want = size_t(opt.variant >> 8) - 1;  // tuning override: variant = (count + 1) << 8
+        if (opt.variant >> 16) want = size_t(opt.variant >> 16) - 1;  // tuning override: variant |= (count + 1) << 16
         want += size_t(opt.extra_parked);  // raised by the compile-and-check loop while ptxas reports spills
         std::sort(cand.begin(), cand.end());
         size_t n_reload = 0;
@@ -1018,7 +1170,14 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     src << "// generated by gaast_b200 codegen: n=" << h.n << " terms=" << h.total_terms << " arith="
         << (g.strict ? "strict" : "fma") << " sum=" << int(opt.with_sum) << " store=" << int(opt.store_out)
         << " bcast=0x" << std::hex << opt.broadcast_slots << std::dec << "\n// " << notes.str() << "\n";
-    src << "#define GAAST_EPT " << ept << "\n#define GAAST_THREADS " << threads << "\n";
+    // Small kernels are pure streaming: ask for several resident blocks so that ptxas does not
+    // trade occupancy for hoisting (cfg2_full: 254 registers without this, 2 blocks per SM).
+    const size_t live_regs = live_estimate * size_t(ept);
+    // (ptxas treats the hint as a register budget to spend: only give it when it is a tight one)
+    const int min_blocks = live_regs <= 40 ? 8 : live_regs <= 64 ? 4 : 1;
+    res.min_blocks = min_blocks;
+    src << "#define GAAST_EPT " << ept << "\n#define GAAST_THREADS " << threads << "\n#define GAAST_MIN_BLOCKS "
+        << min_blocks << "\n";
     src << kEvalArgsText << "\nusing gaast::EvalArgs;\n" << kPrelude << "\n";
 
     std::ostringstream loop_strides;
@@ -1075,7 +1234,14 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             used[n.a.id] = used[n.b.id] = used[n.c.id] = 1;
         }
         for (Ref r : g.buf[0]) used[r.id] = 1;
+        // a handful of shared values live in registers for the whole kernel; a large table of
+        // them (a wide linear map) is read at its point of use instead (uniform, L1-resident)
+        size_t n_shared = 0;
         for (size_t id = 0; id < g.nodes.size(); ++id) {
+            const Node& n = g.nodes[id];
+            n_shared += n.live && n.uniform && used[id] && (n.k == N_LOAD || n.export_idx >= 0);
+        }
+        for (size_t id = 0; id < g.nodes.size() && n_shared <= 32; ++id) {
             const Node& n = g.nodes[id];
             if (!n.live || !n.uniform || !used[id]) continue;
             if (n.k == N_LOAD || n.export_idx >= 0) g.emit(int(id));
@@ -1083,6 +1249,8 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         uni << g.body.str();
         g.body.str("");
         g.indent = 2;
+        g.in_loop = true;
+        if (g.n_export > 0) loop_strides << "    const double* uni = a.uniform; asm volatile(\"\" : \"+l\"(uni));\n";
     }
     // root components, in slot order
     {
@@ -1113,7 +1281,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         }
     }
     src << g.file_scope.str();
-    src << "extern \"C\" __global__ void __launch_bounds__(GAAST_THREADS) gaast_eval(const __grid_constant__ EvalArgs a) {\n";
+    src << "extern \"C\" __global__ void __launch_bounds__(GAAST_THREADS, GAAST_MIN_BLOCKS) gaast_eval(const __grid_constant__ EvalArgs a) {\n";
     src << "  const int tid = threadIdx.x;\n";
     stream_decls(src, false);
     if (opt.with_sum || n_smem_rows) src << "  extern __shared__ double sums[];\n";
