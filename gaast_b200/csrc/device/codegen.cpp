@@ -1281,7 +1281,8 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         }
     }
     src << g.file_scope.str();
-    src << "extern \"C\" __global__ void __launch_bounds__(GAAST_THREADS, GAAST_MIN_BLOCKS) gaast_eval(const __grid_constant__ EvalArgs a) {\n";
+    src << "extern \"C\" __global__ void " << (min_blocks > 1 ? "__launch_bounds__(GAAST_THREADS, GAAST_MIN_BLOCKS)" : "__launch_bounds__(GAAST_THREADS)")
+        << " gaast_eval(const __grid_constant__ EvalArgs a) {\n";
     src << "  const int tid = threadIdx.x;\n";
     stream_decls(src, false);
     if (opt.with_sum || n_smem_rows) src << "  extern __shared__ double sums[];\n";
