@@ -203,3 +203,77 @@ def test_wide_plan_auto_engine_uses_table_engine_with_global_workspace(ctx):
     assert_bit_exact(out.to_host(), want, "G(9) full product, table engine, global workspace")
     with pytest.raises(g.GaastError):
         plan.eval(dev, engine=L.ENGINE_SPECIALIZED)
+
+
+DENSE_METRICS = {
+    "G(6,0)": [1.0] * 6,
+    "G(4,2)": [1.0] * 4 + [-1.0] * 2,
+    "G(3,3)": [1.0, -1.0, 1.0, -1.0, 1.0, -1.0],
+    "G(5,0,1) degenerate": [0.0] + [1.0] * 5,          # zero coefficients: the rolled kernel must not be chosen blindly
+    "G(6) non-unit": [2.0, 1.0, -0.5, 1.0, 3.0, -1.0],  # general diagonal metric
+}
+
+
+@pytest.mark.parametrize("name", sorted(DENSE_METRICS))
+@pytest.mark.parametrize("shape", ["A*B", "A*B+C", "-(A*B)", "(A*B).g(2)", "A.rev()*B"])
+def test_dense_products_every_signature(ctx, name, shape):
+    """Full 64-component geometric products: the DENSE-ROLLED / BLOCKED policies (FMA
+    arithmetic) against the oracle, and strict arithmetic bit for bit."""
+    if shape != "A*B" and name not in ("G(6,0)", "G(3,3)"):
+        pytest.skip("shape variants are exercised on two signatures only (NVRTC time)")
+    metric = DENSE_METRICS[name]
+    n = 6
+    full = tuple(range(n + 1))
+    batch = 258
+    rng = np.random.default_rng(31)
+    host = [{k: rng.uniform(-1, 1, (comb(n, k), batch)) for k in full} for _ in range(3)]
+    build = {"A*B": lambda a, b, c: a * b, "A*B+C": lambda a, b, c: a * b + c, "-(A*B)": lambda a, b, c: -(a * b),
+             "(A*B).g(2)": lambda a, b, c: (a * b).g(2), "A.rev()*B": lambda a, b, c: a.rev() * b}[shape]
+    want = oracle_eval(build, metric, host, [False] * 3, batch)
+    scale = oracle_abs_scale(build, metric, host, [False] * 3, batch)
+    plan = g.Plan(ctx, build(*[pmv(Input(s, full)) for s in range(3)]).specialize(metric))
+    dev = [g.DeviceBatch.from_host(ctx, n, h) for h in host][:plan.num_slots()]
+    out = plan.eval(dev, engine=L.ENGINE_SPECIALIZED, arith=L.ARITH_FMA)
+    ctx.sync()
+    assert_close(out.to_host(), want, scale, what=f"{name} {shape} fma ({plan.last_kernel()[:60]})")
+    out = plan.eval(dev, engine=L.ENGINE_SPECIALIZED, arith=L.ARITH_STRICT)
+    ctx.sync()
+    assert_bit_exact(out.to_host(), want, f"{name} {shape} strict")
+
+
+LINEAR_SHAPES = {
+    "R*X*~R": lambda r, x: r * x * r.rev(),
+    "(R*X*~R).g(1)": lambda r, x: (r * x * r.rev()).g(1),
+    "B*X (fixed left operand)": lambda r, x: r * x,
+    "X*B (fixed right operand)": lambda r, x: x * r,
+    "R*X*~R + 2.5 (affine)": lambda r, x: (r * x * r.rev()).g(0) + 2.5,
+    "(R^X) & R": lambda r, x: (r ^ x) & r,
+    "X*X (not linear)": lambda r, x: x * r * x,
+    "R.norm_sq().sinv() * X": lambda r, x: r.norm_sq().sinv() * x,
+}
+
+
+@pytest.mark.parametrize("shape", sorted(LINEAR_SHAPES))
+@pytest.mark.parametrize("xgrades", [(1,), (0, 1, 2, 3, 4, 5)], ids=["X=vector", "X=full"])
+def test_shared_operand_lowering(ctx, shape, xgrades):
+    """Expressions whose batch input only meets shared (broadcast) operands are lowered to a
+    linear map with hoisted coefficients; results stay within the 1e-12 bar and strict stays exact."""
+    if "affine" in shape and xgrades == (1,):
+        pytest.skip("the reference panics: a sandwiched vector has no grade-0 part to add 2.5 to")
+    metric = [1.0, 1.0, 1.0, 1.0, -1.0]
+    n = 5
+    batch = 1001
+    rng = np.random.default_rng(77)
+    host = [{k: rng.uniform(-1, 1, (comb(n, k), 1)) for k in (0, 2, 4)},
+            {k: rng.uniform(-1, 1, (comb(n, k), batch)) for k in xgrades}]
+    build = LINEAR_SHAPES[shape]
+    want = oracle_eval(build, metric, host, [True, False], batch)
+    scale = oracle_abs_scale(build, metric, host, [True, False], batch)
+    plan = g.Plan(ctx, build(pmv(Input(0, (0, 2, 4))), pmv(Input(1, xgrades))).specialize(metric))
+    dev = [g.DeviceBatch.from_host(ctx, n, host[0], broadcast=True), g.DeviceBatch.from_host(ctx, n, host[1])]
+    out = plan.eval(dev, engine=L.ENGINE_SPECIALIZED, arith=L.ARITH_FMA)
+    ctx.sync()
+    assert_close(out.to_host(), want, scale, rel=4e-12, what=f"{shape} fma")
+    out = plan.eval(dev, engine=L.ENGINE_SPECIALIZED, arith=L.ARITH_STRICT)
+    ctx.sync()
+    assert_bit_exact(out.to_host(), want, f"{shape} strict")
