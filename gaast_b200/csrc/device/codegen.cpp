@@ -311,6 +311,99 @@ struct Gen {
         return memo.emplace(id, std::move(m)).first->second;
     }
 
+    // ---- factoring a common scalar out of a product -------------------------------------------
+    // In  T * (Y s)  where the right operand is a buffer of single-term products with ONE common
+    // factor s (the versor inverse V^-1 = ~V * (1 / |V|^2) of cfg5), every term carries s:
+    // sum_t T_t (Y_w s) c  ==  s * sum_t T_t Y_w c.  The scaled buffer then never exists -- its
+    // registers are freed (12 doubles in cfg5, i.e. 12 fewer parked rows) -- at the price of one
+    // multiplication per output.  Exact in real arithmetic, a different rounding sequence:
+    // FMA arithmetic only.  Returns the number of products rewritten.
+    size_t factor_common_scalars(int pseudo_op) {
+        if (strict) return 0;
+        std::vector<int> refs(nodes.size(), 0);
+        auto count_refs = [&]() {
+            std::fill(refs.begin(), refs.end(), 0);
+            refs.resize(nodes.size(), 0);
+            for (const Node& n : nodes) {
+                if (n.k == N_ACC) { ++refs[n.a.id]; ++refs[n.b.id]; ++refs[n.c.id]; }
+                else if (n.k == N_ADD) { ++refs[n.a.id]; ++refs[n.b.id]; }
+                else if (n.k == N_INV || n.k == N_SQRT) ++refs[n.a.id];
+            }
+            for (Ref r : buf[0]) ++refs[r.id];  // only the root buffer is read after the symbolic run
+        };
+        size_t rewritten = 0;
+        for (size_t oi = 0; oi < h.ops.size(); ++oi) {
+            if (h.ops[oi].kind != GAAST_OP_MUL_TERMS || op_accs[oi].size() < 8) continue;
+            // candidate common factor: an operand shared by every right operand's defining product
+            std::set<int> common;
+            bool ok = true, first = true;
+            std::map<int, int> uses_of_right;  // right operand node -> how many of this op's terms read it
+            std::set<uint32_t> started;
+            for (int id : op_accs[oi]) {
+                const Node& nd = nodes[id];
+                const Node& r = nodes[nd.c.id];
+                if (r.k != N_ACC || !is_zero(r.a) || r.uniform) { ok = false; break; }
+                std::set<int> here{r.b.id, r.c.id};
+                if (first) common = here;
+                else {
+                    std::set<int> both;
+                    for (int x : common) if (here.count(x)) both.insert(x);
+                    common = both;
+                }
+                first = false;
+                if (common.empty()) { ok = false; break; }
+                ++uses_of_right[nd.c.id];
+                if (!started.count(nd.out_slot)) {
+                    if (!is_zero(nd.a)) { ok = false; break; }  // accumulators must start from zero
+                    started.insert(nd.out_slot);
+                }
+            }
+            if (!ok || common.size() != 1 || uses_of_right.size() < 2) continue;
+            const int s = *common.begin();
+            count_refs();
+            for (const auto& kv : uses_of_right)
+                if (refs[kv.first] != kv.second) ok = false;  // the scaled buffer must have no other reader
+            if (!ok) continue;
+            // rewrite the terms: right operand Y instead of (Y s), coefficient absorbs the inner one
+            std::map<uint32_t, int> last;  // out slot -> last link
+            for (int id : op_accs[oi]) {
+                Node& nd = nodes[id];
+                const Node r = nodes[nd.c.id];
+                const bool y_is_left = r.c.id == s;
+                const Ref y = y_is_left ? r.b : r.c;
+                const Ref sr = y_is_left ? r.c : r.b;
+                const bool neg = nd.c.neg ^ y.neg ^ sr.neg;
+                nd.cval = nd.cval * r.cval * (neg ? -1.0 : 1.0);
+                nd.c = Ref{y.id, false};
+                nd.uniform = nodes[nd.a.id].uniform && nodes[nd.b.id].uniform && nodes[y.id].uniform;
+                last[nd.out_slot] = id;
+            }
+            // one multiplication by s per output, and every reader of the output sees the product
+            std::map<int, int> replace;
+            for (const auto& kv : last) {
+                const Ref scaled = make_acc(Ref{0, false}, Ref{kv.second, false}, Ref{s, false}, 1.0, pseudo_op);
+                replace[kv.second] = scaled.id;
+            }
+            auto fix = [&](Ref& r, int self) {
+                auto it = replace.find(r.id);
+                if (it != replace.end() && it->second != self) r.id = it->second;
+            };
+            for (size_t id = 0; id < nodes.size(); ++id) {
+                Node& n = nodes[id];
+                if (n.k == N_ACC && n.op == int(oi)) { fix(n.b, int(id)); fix(n.c, int(id)); continue; }  // own chain links stay
+                if (n.k == N_ACC || n.k == N_ADD || n.k == N_INV || n.k == N_SQRT) {
+                    fix(n.a, int(id));
+                    if (n.k == N_ACC || n.k == N_ADD) fix(n.b, int(id));
+                    if (n.k == N_ACC) fix(n.c, int(id));
+                }
+            }
+            for (auto& b : buf)
+                for (Ref& r : b) fix(r, -1);
+            ++rewritten;
+        }
+        return rewritten;
+    }
+
     // Returns the number of root components rewritten (0 = lowering not applicable / not worthwhile).
     size_t lower_linear(int pseudo_op) {
         if (strict) return 0;
@@ -994,6 +1087,17 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     std::ostringstream notes;
     const int pseudo_op = int(h.ops.size());  // the linear-map lowering's FMAs belong to an extra "op"
     g.op_accs.resize(h.ops.size() + 1);
+    // Opt-in (variant bit 12): measured on cfg5 it frees 12 register rows but does not pay --
+    // 7.20 ms vs 7.15 ms at 36 parked rows, and with fewer parked rows (20-28, still no spills)
+    // ptxas has no slack left to overlap loads and FMAs: 9.1-9.4 ms.
+    if (opt.variant & 4096) {
+        const size_t factored = g.factor_common_scalars(pseudo_op);
+        if (factored) {
+            for (Node& n : g.nodes) n.live = false;
+            g.mark_live();
+            notes << "scalar-factored(" << factored << " products) ";
+        }
+    }
     if (!(opt.variant & 2048)) {
         const size_t lowered = g.lower_linear(pseudo_op);
         if (lowered) {
