@@ -175,6 +175,8 @@ def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=
     # L2 hygiene: a step must not find its inputs in the 126 MB L2.  Large workloads are larger
     # than L2 by themselves; small ones (cfg1: 185 MB) rotate over several input/output sets.
     n_sets = max(1, min(8, -(-(1 << 30) // max(1, n * bytes_per_elem))))
+    if os.environ.get("GAAST_BENCH_NO_ROTATE"):
+        n_sets = 1  # diagnostic only: lets a small batch stay L2-resident
     sets = []
     for k in range(n_sets):
         t = W.torch_inputs(w, n, dev, seed=None if k == 0 else W.seed_of(w) + 1000 * k)

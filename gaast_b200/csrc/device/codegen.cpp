@@ -822,6 +822,7 @@ struct Gen {
         bool unit_sigma = true;
     } dense;
     std::ostringstream file_scope, kernel_setup;
+    bool dense_tmem = false;  // DENSE: left operand parked in tensor memory (3 blocks per SM instead of 2)
     size_t setup_doubles = 0;  // shared memory reserved ahead of the sums / staging areas
 
     bool plan_dense(int op, const std::vector<int>& refcount) {
@@ -924,6 +925,56 @@ struct Gen {
         kernel_setup << "  long long* const dense_out = reinterpret_cast<long long*>(sums);\n";
         kernel_setup << "  if (tid < " << B << ")\n    dense_out[tid] = (long long)(a.sptr[kDenseOutStream[tid]] - a.sptr[" << root0
                      << "]) + (long long)kDenseOutRow[tid] * a.srow[kDenseOutStream[tid]];\n  __syncthreads();\n";
+        if (dense_tmem) {
+            // ---- left operand: TENSOR MEMORY.  With the left operand in registers (128 of them)
+            // only 2 blocks fit an SM and 8 warps cannot keep the FP64 pipe busy (63 %).  Parked in
+            // the thread's TMEM lane (2 columns per component, blade b at column 2b) the kernel
+            // needs ~130 registers: 3 blocks, 12 warps.  Both loops are rolled; a tile's 16 left
+            // components arrive with ONE tcgen05.ld (32x32b.x32).
+            for (int ah = 0; ah < d.H; ++ah) {
+                for (int al = 0; al < 16; ++al) emit(d.left[(ah << hb) + al].id);
+                std::string args;
+                for (int al = 0; al < 16; ++al) args += ", " + opnd(d.left[(ah << hb) + al], true);
+                line("tm_put16(tb + " + std::to_string(32 * ah) + "u" + args + ");");
+            }
+            line("tm_wait_st();");
+            line("#pragma unroll 1");
+            line("for (int oh = 0; oh < " + std::to_string(d.H) + "; ++oh) {");
+            ++indent;
+            for (int ol = 0; ol < 16; ++ol) line("double q" + std::to_string(ol) + " = 0.0;");
+            line("#pragma unroll 1");
+            line("for (int ah = 0; ah < " + std::to_string(d.H) + "; ++ah) {");
+            ++indent;
+            line("double a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15;");
+            line("tm_get16(tb + 32u * ah, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15);");
+            line("const unsigned* const rows = kDenseB + ((oh ^ ah) << " + std::to_string(hb) + ");");
+            line((d.unit_sigma ? std::string("const unsigned sg = ") : std::string("const double sg = ")) +
+                 "kDenseSigma[ah * " + std::to_string(d.H) + " + oh];");
+            // (-1)^(|ah||bl|): a grade involution of the right operand's lo part when |ah| is odd
+            line("const unsigned inv = (__popc(ah) & 1) ? 0x80000000u : 0u;");
+            for (int bl = 0; bl < 16; ++bl) {
+                const std::string raw = "xs_ldd(xb + rows[" + std::to_string(bl) + "])";
+                const bool oddbl = __builtin_popcount(bl) & 1;
+                if (d.unit_sigma)
+                    line("const double b" + std::to_string(bl) + " = flip_sign(" + raw + ", sg" + (oddbl ? " ^ inv" : "") + ");");
+                else
+                    line("const double b" + std::to_string(bl) + " = " + (oddbl ? "flip_sign(" + raw + ", inv)" : raw) + " * sg;");
+            }
+            for (int al = 0; al < 16; ++al)
+                for (int bl = 0; bl < 16; ++bl) {
+                    const double cc = d.lambda[al * 16 + bl];
+                    if (cc == 0.0) continue;
+                    const std::string q = "q" + std::to_string(al ^ bl);
+                    const std::string A = std::string(cc < 0 ? "-" : "") + "a" + std::to_string(al);
+                    const std::string Bv = "b" + std::to_string(bl);
+                    if (std::fabs(cc) == 1.0)
+                        line(q + " = fma(" + A + ", " + Bv + ", " + q + ");");
+                    else
+                        line(q + " = fma(" + A + " * " + Bv + ", " + lit(std::fabs(cc)) + ", " + q + ");");
+                }
+            --indent;
+            line("}");
+        } else {
         // ---- left operand: registers ----
         for (int a = 0; a < B; ++a) emit(d.left[a].id);
         line("#pragma unroll 1");
@@ -960,11 +1011,13 @@ struct Gen {
             --indent;
             line("}");
         }
+        }
         // ---- store the finished coset ----
         if (opt.store_out) {
             line("double* const ro = s" + std::to_string(root0) + " + e;");
             for (int ol = 0; ol < 16; ++ol)
-                line("ro[dense_out[(oh << " + std::to_string(hb) + ") + " + std::to_string(ol) + "]] = q" + std::to_string(ol) + ";");
+                line(std::string(guard_stores ? "if (active) " : "") + "ro[dense_out[(oh << " + std::to_string(hb) + ") + " +
+                     std::to_string(ol) + "]] = q" + std::to_string(ol) + ";");
         }
         --indent;
         line("}");
@@ -1037,6 +1090,37 @@ __device__ __forceinline__ double tm_get(unsigned taddr) {
   return __hiloint2double((int)hi, (int)lo);
 }
 __device__ __forceinline__ void tm_add(unsigned taddr, double v) { tm_put(taddr, tm_get(taddr) + v); }
+#define GAAST_LOHI(v) "r"(__double2loint(v)), "r"(__double2hiint(v))
+__device__ __forceinline__ void tm_put16(unsigned taddr, double v0, double v1, double v2, double v3, double v4, double v5,
+                                         double v6, double v7, double v8, double v9, double v10, double v11, double v12,
+                                         double v13, double v14, double v15) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      GAAST_LOHI(v0), GAAST_LOHI(v1), GAAST_LOHI(v2), GAAST_LOHI(v3), GAAST_LOHI(v4), GAAST_LOHI(v5), GAAST_LOHI(v6),
+      GAAST_LOHI(v7), GAAST_LOHI(v8), GAAST_LOHI(v9), GAAST_LOHI(v10), GAAST_LOHI(v11), GAAST_LOHI(v12), GAAST_LOHI(v13),
+      GAAST_LOHI(v14), GAAST_LOHI(v15));
+}
+__device__ __forceinline__ void tm_get16(unsigned taddr, double& v0, double& v1, double& v2, double& v3, double& v4,
+                                         double& v5, double& v6, double& v7, double& v8, double& v9, double& v10,
+                                         double& v11, double& v12, double& v13, double& v14, double& v15) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v0 = __hiloint2double(r[1], r[0]);    v1 = __hiloint2double(r[3], r[2]);    v2 = __hiloint2double(r[5], r[4]);
+  v3 = __hiloint2double(r[7], r[6]);    v4 = __hiloint2double(r[9], r[8]);    v5 = __hiloint2double(r[11], r[10]);
+  v6 = __hiloint2double(r[13], r[12]);  v7 = __hiloint2double(r[15], r[14]);  v8 = __hiloint2double(r[17], r[16]);
+  v9 = __hiloint2double(r[19], r[18]);  v10 = __hiloint2double(r[21], r[20]); v11 = __hiloint2double(r[23], r[22]);
+  v12 = __hiloint2double(r[25], r[24]); v13 = __hiloint2double(r[27], r[26]); v14 = __hiloint2double(r[29], r[28]);
+  v15 = __hiloint2double(r[31], r[30]);
+}
 // TMA (bulk async copy) + mbarrier plumbing of the pipelined kernels
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -1257,8 +1341,9 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     bool has_dense = false;
     for (Policy p : g.op_policy) has_dense |= p == P_DENSE || p == P_BLOCKED;
     const bool tma_stage = opt.tma_stage && has_dense && n_smem_rows > 0 && ept == 1 && !pipelined && !opt.with_sum;
+    g.dense_tmem = tma_stage && g.dense.op >= 0 && (opt.variant & 8192);
     g.pipelined = pipelined;
-    g.guard_stores = pipelined || tmem_sum;
+    g.guard_stores = pipelined || tmem_sum || g.dense_tmem;
     g.sum_in_smem = opt.with_sum && !tmem_sum;
     g.sum_in_tmem = tmem_sum;
     res.pipelined = pipelined;
@@ -1278,7 +1363,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     // trade occupancy for hoisting (cfg2_full: 254 registers without this, 2 blocks per SM).
     const size_t live_regs = live_estimate * size_t(ept);
     // (ptxas treats the hint as a register budget to spend: only give it when it is a tight one)
-    const int min_blocks = live_regs <= 40 ? 8 : live_regs <= 64 ? 4 : 1;
+    const int min_blocks = g.dense_tmem ? 3 : live_regs <= 40 ? 8 : live_regs <= 64 ? 4 : 1;
     res.min_blocks = min_blocks;
     src << "#define GAAST_EPT " << ept << "\n#define GAAST_THREADS " << threads << "\n#define GAAST_MIN_BLOCKS "
         << min_blocks << "\n";
@@ -1494,11 +1579,30 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
                 << parked[size_t(r)]->row << " * r" << parked[size_t(r)]->stream << " + e0, bytes, stage_bar);\n";
         src << "  }\n";
         src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(stage0 + tid);\n";
-        src << "  const long long e = e0 + tid;\n";
-        src << "  if (e < a.n) {\n";
-        src << loop_strides.str();
-        src << g.body.str();
-        src << "  }\n";
+        if (g.dense_tmem) {
+            // whole warps run the tcgen05 instructions: lanes past the end of the batch shadow the
+            // last element and do not store
+            src << "  const int warp = tid >> 5;\n";
+            src << "  unsigned* const tslot = reinterpret_cast<unsigned*>(stage_bar + 1);\n";
+            src << "  if (warp == 0) { tm_alloc(tslot, 128u); tm_relinquish(); }\n";
+            src << "  tm_fence_before_sync();\n  __syncthreads();\n  tm_fence_after_sync();\n";
+            src << "  const unsigned tmem_base = *tslot;\n";
+            src << "  const unsigned tb = tmem_base + ((unsigned)(warp * 32) << 16);\n";
+            src << "  const bool active = e0 + tid < a.n;\n";
+            src << "  const long long e = active ? e0 + tid : a.n - 1;\n";
+            src << "  {\n";
+            src << loop_strides.str();
+            src << g.body.str();
+            src << "  }\n";
+            src << "  tm_fence_before_sync();\n  __syncthreads();\n";
+            src << "  if (warp == 0) tm_dealloc(tmem_base, 128u);\n";
+        } else {
+            src << "  const long long e = e0 + tid;\n";
+            src << "  if (e < a.n) {\n";
+            src << loop_strides.str();
+            src << g.body.str();
+            src << "  }\n";
+        }
     } else {
         if (n_smem_rows)
             src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << sum_doubles << " + tid);\n";
