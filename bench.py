@@ -206,10 +206,25 @@ def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=
     torch.cuda.synchronize()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
+    # Launch-bound steps (cfg1: 185 MB, ~30 us per kernel) are captured once into a CUDA graph and
+    # replayed: the evaluation is stream-ordered and allocates nothing after its first call, so the
+    # C ABI is capturable as it is.  Everything else is launched directly.
+    expect_us = n * bytes_per_elem / 6.5e6
+    use_graph = world == 1 and not use_sum and expect_us < 200.0 and not os.environ.get("GAAST_BENCH_NO_GRAPH")
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=ctx.torch_stream):
+            for _ in range(steps):
+                step()
+        torch.cuda.synchronize()
+        e0.record()
+        graph.replay()
+        e1.record()
+    else:
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -223,7 +238,7 @@ def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=
     res = {
         "ms_per_step": ms / steps, "elements": n, "bytes_per_elem": bytes_per_elem, "flops_per_elem": flops_per_elem,
         "launches": launches, "kernel": plan.last_kernel(), "plan": plan, "ins": ins, "out": out, "tin": tin,
-        "n_sets": n_sets,
+        "n_sets": n_sets, "cuda_graph": bool(use_graph),
     }
     return res
 
@@ -285,7 +300,12 @@ def run_gpu(args):
     peak_gbs, peak_src = _peaks()
 
     sampler = ClockSampler(local) if rank == 0 else None
-    res = time_workload(ctx, w, args.steps, args.warmup, torch, dist, world, batch=args.batch,
+    batch = args.batch
+    if args.strong and world > 1:
+        from gaast_b200.dist import shard_range
+        b0, b1 = shard_range(batch or w.batch, rank, world)
+        batch = b1 - b0  # the BASELINE batch split into contiguous, 16-byte aligned slices
+    res = time_workload(ctx, w, args.steps, args.warmup, torch, dist, world, batch=batch,
                         engine={'auto': 0, 'table': 1, 'specialized': 2}[args.engine],
                         tuning=(args.ept, args.variant) if (args.ept or args.variant) else None,
                         with_sum=False if args.no_sum else None)
@@ -300,14 +320,14 @@ def run_gpu(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{w.name}: {w.title}", "batch_per_gpu": n, "elements_per_s": elems_per_s,
                    "products_per_element": w.products, "parallelism": f"batch-sharded x{world}, no data-path collective"
                    + (" (+66-double NCCL all-reduce for the batch-sum)" if w.sum_root and world > 1 else ""),
                    "l2": f"inputs+outputs {n * res['bytes_per_elem'] / 1e9:.2f} GB per step (126 MB L2), "
                          f"{res['n_sets']} input/output set(s) used in rotation",
-                   "kernel": res["kernel"]},
+                   "kernel": res["kernel"], "cuda_graph": res["cuda_graph"]},
         "gpu_launches": res["launches"],
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
                      "traffic": NCU_TRAFFIC_BYTES.get(w.name), "peak_source": peak_src,
@@ -359,7 +379,8 @@ def run_gpu(args):
                                 "fp64_tflops": r["elements"] * r["flops_per_elem"] / s / 1e12,
                                 "fp64_frac": r["elements"] * r["flops_per_elem"] / s / 1e12 / FP64_PEAK_TFLOPS,
                                 "bound": ow.bound, "ncu_traffic_bytes": NCU_TRAFFIC_BYTES.get(name),
-                                "batch": r["elements"], "kernel": r["kernel"], "io_sets_rotated": r["n_sets"]}
+                                "batch": r["elements"], "kernel": r["kernel"], "io_sets_rotated": r["n_sets"],
+                                "cuda_graph": r["cuda_graph"]}
                 del r
             except Exception as ex:
                 others[name] = {"error": f"{type(ex).__name__}: {ex}"}
@@ -384,6 +405,7 @@ def main():
     ap.add_argument("--ept", type=int, default=0, help="tuning: elements per thread of the specialised kernel")
     ap.add_argument("--variant", type=int, default=0, help="tuning: code generator policy bits")
     ap.add_argument("--no-sum", action="store_true", help="skip the batch-sum node of cfg5")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: shard ONE BASELINE batch over the ranks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--all", action="store_true", default=True, help="also time the other BASELINE workloads (N=1)")
