@@ -117,6 +117,17 @@ void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_input
             if (b->broadcast) a.bcast[i >> 6] |= 1ull << (i & 63);
         }
     }
+    // results are stored component by component while later components still read the inputs:
+    // an output array overlapping an input array would be read after it was overwritten
+    for (size_t o = h.n_in_streams; o < h.streams.size() && out; ++o) {
+        const char* ob = reinterpret_cast<const char*>(a.sptr[o]);
+        const char* oe = ob + size_t(h.streams[o].rows) * size_t(a.srow[o]) * sizeof(double);
+        for (size_t i = 0; i < h.n_in_streams; ++i) {
+            const char* ib = reinterpret_cast<const char*>(a.sptr[i]);
+            const char* ie = ib + size_t(h.streams[i].rows) * size_t(a.srow[i]) * sizeof(double);
+            if (ob < ie && ib < oe) throw Error(GAAST_ERR_INVALID, "eval: the output batch overlaps an input batch");
+        }
+    }
     a.n = n;
     a.consts = plan->d_consts;
     a.total_cols = int(h.total_cols);

@@ -117,6 +117,14 @@ def test_empty_batch_and_shape_errors(ctx):
     wrong_out = g.DeviceBatch.alloc(ctx, 3, (1, 2), 8)  # root grade set is exactly {2}
     with pytest.raises(g.GaastError):
         plan.eval([a, a, a], out=wrong_out)
+    # in-place evaluation is refused: outputs are stored while later components still read the inputs
+    import torch
+    t = {k: torch.zeros((comb(3, k), 8), dtype=torch.float64, device="cuda:0") for k in range(4)}
+    inp = g.DeviceBatch.wrap_torch(ctx, 3, t)
+    alias = g.DeviceBatch.wrap_torch(ctx, 3, {2: t[2]})
+    with pytest.raises(g.GaastError) as ei:
+        plan.eval([inp, a, a], out=alias)
+    assert "overlaps" in str(ei.value)
 
 
 @pytest.mark.parametrize("engine", ENGINES, ids=[e[0] for e in ENGINES])
