@@ -41,8 +41,11 @@ FP64_PEAK_TFLOPS = float(os.environ.get("GAAST_FP64_PEAK_TFLOPS", "0") or 0) or 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the BASELINE batch, from the committed
 # `ncu --set full` captures (profiles/r1_*_ncu.txt; captures taken at batch 4M are scaled to the full batch)
 NCU_TRAFFIC_BYTES = {
-    "cfg2": 5321087000,                    # profiles/r1_cfg2_ncu.txt (algorithmic 5368709120)
-    "cfg3": int(6409129000 * 4),           # profiles/r1_cfg3_ncu.txt at 4M elements (algorithmic 6442450944 at 4M)
+    "cfg1": 727105280 // 4,        # profiles/r1_cfg1_final_ncu.txt, captured at 4M elements (BASELINE batch is 1M)
+    "cfg2": 5318542000,            # profiles/r1_cfg2_final_ncu.txt at the BASELINE batch (algorithmic 5368709120)
+    "cfg3": 6409480000 * 4,        # profiles/r1_cfg3_final_ncu.txt at 4M elements (algorithmic 6442450944 at 4M)
+    "cfg4": 9169429000 * 2,        # profiles/r1_cfg4_final_ncu.txt at 4M elements (algorithmic 9227468800 at 4M)
+    "cfg5": 4792071000 * 8,        # profiles/r1_cfg5_final_ncu.txt at 4M elements (algorithmic 4831838208 at 4M)
 }
 
 
