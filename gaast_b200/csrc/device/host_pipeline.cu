@@ -3,6 +3,7 @@
 // chunk i+1, the kernel of chunk i and the D2H copy of chunk i-1 overlap
 // (PCIe is full duplex; three streams, events between them).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "../runtime.hpp"
@@ -75,7 +76,9 @@ extern "C" gaast_status gaast_eval_host(gaast_plan* plan, const double* const* h
             if (!in_broadcast[s]) in_rows += rows_of(h.n, in_masks[s]);
         const uint32_t out_rows = h.buf_cols[0];
         const uint32_t wide = std::max<uint32_t>(1, std::max(in_rows, out_rows));
-        uint64_t chunk = (uint64_t(32) << 20) / (8ull * wide);
+        uint64_t chunk_mib = 32;
+        if (const char* e = std::getenv("GAAST_HOST_CHUNK_MIB")) chunk_mib = std::max(1, std::atoi(e));
+        uint64_t chunk = (chunk_mib << 20) / (8ull * wide);
         chunk = std::max<uint64_t>(4096, chunk / 4096 * 4096);
         chunk = std::min<uint64_t>(chunk, (len + 4095) / 4096 * 4096);
         if (chunk == 0) chunk = 4096;

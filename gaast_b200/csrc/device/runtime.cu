@@ -459,7 +459,11 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     }
 
     std::shared_ptr<gaast::JitKernel> jk;
-    if (engine == GAAST_ENGINE_AUTO || engine == GAAST_ENGINE_SPECIALIZED) {
+    // AUTO: a handful of elements of a plan never specialised before is not worth generating and
+    // compiling a kernel for (0.3-3 s): the table engine evaluates it at once.
+    const bool tiny = engine == GAAST_ENGINE_AUTO && plan->jit.empty() &&
+                      double(n) * double(h.total_terms > 0 ? h.total_terms : 1) < 2e6;
+    if ((engine == GAAST_ENGINE_AUTO && !tiny) || engine == GAAST_ENGINE_SPECIALIZED) {
         if (plan->jit_error.empty() || engine == GAAST_ENGINE_SPECIALIZED) {
             try {
                 gaast::CodegenOptions opt;
@@ -487,7 +491,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
             }
         }
         if (!jk && engine == GAAST_ENGINE_SPECIALIZED) throw Error(GAAST_ERR_JIT, plan->jit_error);
-    } else if (engine != GAAST_ENGINE_TABLE) {
+    } else if (engine != GAAST_ENGINE_TABLE && engine != GAAST_ENGINE_AUTO) {
         throw Error(GAAST_ERR_INVALID, "unknown engine");
     }
 

@@ -61,7 +61,10 @@ class Expr:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            L.lib.gaast_expr_free(h)
+            try:
+                L.lib.gaast_expr_free(h)
+            except Exception:  # interpreter shutdown: the library may already be gone
+                pass
 
     def clone(self) -> "Expr":  # same identity, expr.rs:47-53
         return Expr(L.lib.gaast_expr_clone(self._h), self._keep)
@@ -204,7 +207,10 @@ class SpecializedAst:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            L.lib.gaast_spec_free(h)
+            try:
+                L.lib.gaast_spec_free(h)
+            except Exception:
+                pass
 
     def root_id(self) -> int:
         return L.lib.gaast_spec_root(self._h)
