@@ -705,9 +705,22 @@ struct Gen {
                  std::to_string(rs.stream) + " + e, " + val + ");");
         if (sum_in_smem)
             line(guard + "sums[" + std::to_string(rs.col) + " * GAAST_THREADS + tid] += d_hsum(" + val + ");");
-        if (sum_in_tmem)  // warp-collective: idle lanes add zero
-            line("tm_add(tb + " + std::to_string(2 * rs.col) + "u, active ? d_hsum(" + val + ") : 0.0);");
+        if (sum_in_tmem) {
+            // Accumulators are numbered in emission order (column pair 2k for the k-th finished
+            // component).  The first `sum_stash` components only park their value in a second
+            // range of tensor-memory columns (one STTM, nothing to wait for); the running sums
+            // absorb the whole stash at the end of the tile, 16 components per
+            // tcgen05.ld/st.  Components beyond the stash capacity are added one by one.
+            const size_t k = sum_order.size();
+            sum_order.push_back(rs.col);
+            if (k < sum_stash)
+                line("tm_put(tb + " + std::to_string(2 * root_done.size() + 2 * k) + "u, d_hsum(" + val + "));");
+            else  // warp-collective: idle lanes add zero
+                line("tm_add(tb + " + std::to_string(2 * k) + "u, active ? d_hsum(" + val + ") : 0.0);");
+        }
     }
+    size_t sum_stash = 0;             // components whose per-tile value is parked in tensor memory
+    std::vector<uint32_t> sum_order;  // root columns in the order their sums are updated
     void store_if_root(int id) {
         if (in_prologue) return;
         auto range = root_of.equal_range(id);
@@ -1090,6 +1103,45 @@ __device__ __forceinline__ double tm_get(unsigned taddr) {
   return __hiloint2double((int)hi, (int)lo);
 }
 __device__ __forceinline__ void tm_add(unsigned taddr, double v) { tm_put(taddr, tm_get(taddr) + v); }
+// Running sums absorb parked per-tile values: acc[i] += stash[i] for N consecutive components
+// (2 columns each).  FULL = every lane of the tile holds a real element; otherwise idle lanes add zero.
+#define GAAST_TM_ACC(NAME, N, SHAPE, OUTS_A, OUTS_S, INS)                                                         \
+  template <bool FULL>                                                                                            \
+  __device__ __forceinline__ void NAME(unsigned acc, unsigned stash, bool active) {                               \
+    unsigned a[2 * N], s[2 * N];                                                                                   \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b." SHAPE ".b32 {" OUTS_S "}, [%" #INS "];" : GAAST_TM_OUT##N(a) : "r"(acc));   \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b." SHAPE ".b32 {" OUTS_S "}, [%" #INS "];" : GAAST_TM_OUT##N(s) : "r"(stash)); \
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");                                                   \
+    _Pragma("unroll") for (int i = 0; i < N; ++i) {                                                                \
+      const double sv = __hiloint2double((int)s[2 * i + 1], (int)s[2 * i]);                                        \
+      const double r = __hiloint2double((int)a[2 * i + 1], (int)a[2 * i]) + (FULL || active ? sv : 0.0);           \
+      a[2 * i] = (unsigned)__double2loint(r);                                                                      \
+      a[2 * i + 1] = (unsigned)__double2hiint(r);                                                                  \
+    }                                                                                                              \
+    asm volatile("tcgen05.st.sync.aligned.32x32b." SHAPE ".b32 [%0], {" OUTS_A "};" ::"r"(acc), GAAST_TM_IN##N(a)); \
+  }
+#define GAAST_TM_OUT1(r) "=r"(r[0]), "=r"(r[1])
+#define GAAST_TM_OUT4(r) "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+#define GAAST_TM_OUT16(r)                                                                                          \
+  "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),      \
+      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),       \
+      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
+      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+#define GAAST_TM_IN1(r) "r"(r[0]), "r"(r[1])
+#define GAAST_TM_IN4(r) "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+#define GAAST_TM_IN16(r)                                                                                           \
+  "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),    \
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),  \
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),  \
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+GAAST_TM_ACC(tm_acc1, 1, "x2", "%1, %2", "%0, %1", 2)
+GAAST_TM_ACC(tm_acc4, 4, "x8", "%1, %2, %3, %4, %5, %6, %7, %8", "%0, %1, %2, %3, %4, %5, %6, %7", 8)
+GAAST_TM_ACC(tm_acc16, 16, "x32",
+             "%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+             "%25, %26, %27, %28, %29, %30, %31, %32",
+             "%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+             "%24, %25, %26, %27, %28, %29, %30, %31",
+             32)
 #define GAAST_LOHI(v) "r"(__double2loint(v)), "r"(__double2hiint(v))
 __device__ __forceinline__ void tm_put16(unsigned taddr, double v0, double v1, double v2, double v3, double v4, double v5,
                                          double v6, double v7, double v8, double v9, double v10, double v11, double v12,
@@ -1325,8 +1377,11 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     // per-thread column sums in shared memory (measured: MIO-bound, profiles/r1_cfg5_sum_v2_ncu.txt).
     // Batch-sum accumulators in tensor memory (2 columns per component and lane; allocations are
     // powers of two >= 32 columns, and two resident blocks must share the SM's 512 columns).
+    // Room for a stash of per-tile values next to the accumulators is taken when it is free
+    // (an allocation is a power of two anyway) or cheap (at most 256 of the SM's 512 columns).
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2 * root_cols) tmem_cols *= 2;
+    while (tmem_cols < 4 * root_cols && tmem_cols < 256) tmem_cols *= 2;
     const bool tmem_sum = opt.with_sum && ept == 1 && !opt.pipelined && !(opt.variant & 32) && tmem_cols <= 256;
     const size_t sum_doubles = g.dense.op >= 0 ? (size_t(1) << h.n)  // table of output offsets (dense excludes the sum)
                                : !opt.with_sum ? 0
@@ -1346,11 +1401,12 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     g.guard_stores = pipelined || tmem_sum || g.dense_tmem;
     g.sum_in_smem = opt.with_sum && !tmem_sum;
     g.sum_in_tmem = tmem_sum;
+    g.sum_stash = tmem_sum && !(opt.variant & 128) ? std::min<size_t>(root_cols, (tmem_cols - 2 * root_cols) / 2) : 0;
     res.pipelined = pipelined;
     res.smem_bytes = pipelined ? pipe_bytes : sum_doubles * 8 + size_t(n_smem_rows) * threads * sizeof(double) + (tma_stage ? 16 : 0);
     res.one_tile_blocks = tma_stage;
     if (tma_stage) notes << "tma-staged ";
-    if (tmem_sum) notes << "sum-in-tmem(" << tmem_cols << "cols) ";
+    if (tmem_sum) notes << "sum-in-tmem(" << tmem_cols << "cols,stash=" << g.sum_stash << ") ";
     if (pipelined) notes << "tma-pipelined ";
     res.parked = res_parked;
     res.parkable = res_parkable;
@@ -1470,6 +1526,11 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         }
     }
     src << g.file_scope.str();
+    if (tmem_sum) {  // accumulator k (emission order) -> root column
+        src << "__device__ const short gaast_sum_col[" << root_cols << "] = {";
+        for (size_t k = 0; k < g.sum_order.size(); ++k) src << (k ? ", " : "") << g.sum_order[k];
+        src << "};\n";
+    }
     src << "extern \"C\" __global__ void " << (min_blocks > 1 ? "__launch_bounds__(GAAST_THREADS, GAAST_MIN_BLOCKS)" : "__launch_bounds__(GAAST_THREADS)")
         << " gaast_eval(const __grid_constant__ EvalArgs a) {\n";
     src << "  const int tid = threadIdx.x;\n";
@@ -1488,6 +1549,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         src << "  const unsigned tmem_base = *tslot;\n";
         src << "  const unsigned tb = tmem_base + ((unsigned)(warp * 32) << 16);\n";
         src << "  for (int c = 0; c < " << root_cols << "; ++c) tm_put(tb + 2u * c, 0.0);\n";
+        src << "  tm_wait_st();\n";
     }
     src << uni.str();
     if (pipelined) {
@@ -1552,8 +1614,25 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         src << "    const long long e0 = tile * GAAST_THREADS;\n";
         src << "    const bool active = e0 + tid < a.n;\n";
         src << "    const long long e = active ? e0 + tid : a.n - 1;  // idle lanes of the last tile shadow a valid element\n";
-        src << "    tm_wait_st();  // the previous tile's sum updates have landed in tensor memory\n";
+        if (!g.sum_stash) src << "    tm_wait_st();  // the previous tile's sum updates have landed in tensor memory\n";
         src << g.body.str();
+        if (g.sum_stash) {
+            // end of the tile: the running sums absorb the stash (registers are free here)
+            src << "    tm_wait_st();  // stash and earlier sum updates have landed in tensor memory\n";
+            for (int full = 1; full >= 0; --full) {
+                src << (full ? "    if (e0 + GAAST_THREADS <= a.n) {\n" : "    } else {\n");
+                size_t k = 0;
+                auto batch = [&](size_t n, const char* fn) {
+                    for (; k + n <= g.sum_stash; k += n)
+                        src << "      " << fn << "<" << (full ? "true" : "false") << ">(tb + " << 2 * k << "u, tb + "
+                            << 2 * root_cols + 2 * k << "u, active);\n";
+                };
+                batch(16, "tm_acc16");
+                batch(4, "tm_acc4");
+                batch(1, "tm_acc1");
+            }
+            src << "    }\n";
+        }
         src << "  }\n";
     } else if (tma_stage) {
         // One tile per block.  Thread 0 hands the tile's parked rows to the TMA unit (one bulk
@@ -1619,7 +1698,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         src << "    double v = tm_get(tb + 2u * c);\n";
         src << "    #pragma unroll\n";
         src << "    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);\n";
-        src << "    if (lane == 0) sums[warp * " << root_cols << " + c] = v;\n";
+        src << "    if (lane == 0) sums[warp * " << root_cols << " + gaast_sum_col[c]] = v;\n";
         src << "  }\n";
         src << "  tm_fence_before_sync();\n";
         src << "  __syncthreads();\n";
