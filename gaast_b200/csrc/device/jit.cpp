@@ -220,7 +220,7 @@ std::vector<char> build_specialized(const DevicePlanHost& h, CodegenOptions opt,
         if (std::getenv("GAAST_CODEGEN_DEBUG"))
             std::fprintf(stderr, "[gaast codegen] attempt %d: parked=%d/%d spill=%zuB smem=%zuB %s\n", attempt, cg.parked,
                          cg.parkable, spill, cg.smem_bytes, cg.notes.c_str());
-        if (spill <= 16 || !can_park_more || attempt >= 8) {
+        if (spill <= 8 || !can_park_more || attempt >= 8) {
             *cg_out = std::move(cg);
             return cubin;
         }
