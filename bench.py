@@ -164,8 +164,10 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------ GPU arm ----
-def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=None, with_sum=None, tuning=None):
-    """Device-resident timing of one workload: returns dict with ms_per_step etc."""
+def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=None, with_sum=None, tuning=None,
+                  f32=False):
+    """Device-resident timing of one workload: returns dict with ms_per_step etc.
+    f32: the reduced-precision variant (binary32 batches; half the algorithmic bytes)."""
     import gaast_b200 as g
     from gaast_b200 import _lib as L
     from gaast_b200 import workloads as W
@@ -175,6 +177,8 @@ def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=
     if tuning:
         plan.set_tuning(*tuning)
     bytes_per_elem, _ = plan.cost(w.broadcast_mask())
+    if f32:
+        bytes_per_elem //= 2
     # L2 hygiene: a step must not find its inputs in the 126 MB L2.  Large workloads are larger
     # than L2 by themselves; small ones (cfg1: 185 MB) rotate over several input/output sets.
     n_sets = max(1, min(8, -(-(1 << 30) // max(1, n * bytes_per_elem))))
@@ -183,8 +187,10 @@ def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=
     sets = []
     for k in range(n_sets):
         t = W.torch_inputs(w, n, dev, seed=None if k == 0 else W.seed_of(w) + 1000 * k)
+        if f32:
+            t = [{kk: v.float() for kk, v in x.items()} for x in t]
         i = [g.DeviceBatch.wrap_torch(ctx, w.n, x, broadcast=bc) for x, (_, bc) in zip(t, w.inputs)]
-        sets.append((t, i, plan.alloc_output(n)))
+        sets.append((t, i, plan.alloc_output(n, L.F32 if f32 else L.F64)))
     tin, ins, out = sets[0]
     use_sum = w.sum_root if with_sum is None else with_sum
     sums = torch.zeros(_root_cols(plan, w), dtype=torch.float64, device=dev)
@@ -238,6 +244,8 @@ def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     bytes_per_elem, flops_per_elem = plan.cost(w.broadcast_mask())
+    if f32:
+        bytes_per_elem //= 2
     res = {
         "ms_per_step": ms / steps, "elements": n, "bytes_per_elem": bytes_per_elem, "flops_per_elem": flops_per_elem,
         "launches": launches, "kernel": plan.last_kernel(), "plan": plan, "ins": ins, "out": out, "tin": tin,
@@ -311,7 +319,7 @@ def run_gpu(args):
     res = time_workload(ctx, w, args.steps, args.warmup, torch, dist, world, batch=batch,
                         engine={'auto': 0, 'table': 1, 'specialized': 2}[args.engine],
                         tuning=(args.ept, args.variant) if (args.ept or args.variant) else None,
-                        with_sum=False if args.no_sum else None)
+                        with_sum=False if args.no_sum else None, f32=args.dtype == "f32")
     clocks = sampler.stop() if sampler else None
 
     n = res["elements"]
@@ -324,8 +332,9 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{w.name}: {w.title}", "batch_per_gpu": n, "elements_per_s": elems_per_s,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"{w.name}: {w.title}" + (" [f32 variant: not the reference's precision]" if args.dtype == "f32" else ""),
+                   "batch_per_gpu": n, "elements_per_s": elems_per_s,
                    "products_per_element": w.products, "parallelism": f"batch-sharded x{world}, no data-path collective"
                    + (" (+66-double NCCL all-reduce for the batch-sum)" if w.sum_root and world > 1 else ""),
                    "l2": f"inputs+outputs {n * res['bytes_per_elem'] / 1e9:.2f} GB per step (126 MB L2), "
@@ -333,13 +342,19 @@ def run_gpu(args):
                    "kernel": res["kernel"], "cuda_graph": res["cuda_graph"]},
         "gpu_launches": res["launches"],
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
-                     "traffic": NCU_TRAFFIC_BYTES.get(w.name), "peak_source": peak_src,
+                     "traffic": NCU_TRAFFIC_BYTES.get(w.name) if args.dtype == "f64" else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": n * res["bytes_per_elem"], "fp64_tflops": tflops,
                      "fp64_peak_tflops": FP64_PEAK_TFLOPS, "fp64_frac": tflops / FP64_PEAK_TFLOPS},
     }
     if clocks is not None:
         line["clocks"] = clocks
 
+    if args.dtype == "f32":  # the f32 variant is a device-resident API; its FMA-pipe peak is not the f64 one
+        args.no_e2e = args.no_cpu = True
+        args.all = False
+        for key in ("fp64_tflops", "fp64_peak_tflops", "fp64_frac"):
+            line["roofline"].pop(key)
+        line["roofline"]["fp32_tflops"] = tflops
     if rank == 0 and not args.no_e2e:
         try:
             e = measure_e2e(ctx, w, res, max(2, min(args.steps, 3)), torch)
@@ -408,6 +423,8 @@ def main():
     ap.add_argument("--ept", type=int, default=0, help="tuning: elements per thread of the specialised kernel")
     ap.add_argument("--variant", type=int, default=0, help="tuning: code generator policy bits")
     ap.add_argument("--no-sum", action="store_true", help="skip the batch-sum node of cfg5")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="f64 = the reference's precision (default, the BASELINE metric); f32 = the reduced-precision variant")
     ap.add_argument("--strong", action="store_true", help="strong scaling: shard ONE BASELINE batch over the ranks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -27,6 +27,7 @@ STATUS_NAMES = ["OK", "INVALID", "UNSUPPORTED", "PANIC", "NO_DEVICE", "CUDA", "O
 
 ENGINE_AUTO, ENGINE_TABLE, ENGINE_SPECIALIZED = 0, 1, 2
 ARITH_FMA, ARITH_STRICT = 0, 1
+F64, F32 = 0, 1  # gaast_dtype
 
 OP_ADD_INPUT, OP_MUL_TERMS, OP_NEG_GRADES, OP_SCALAR_INV, OP_SCALAR_SQRT = range(5)
 INPUT_BATCH, INPUT_CONST = 0, 1
@@ -103,10 +104,14 @@ PROTOTYPES = {
     "gaast_plan_slot_mask": (u32, vp, u32),
     "gaast_plan_kernel_source": (C.c_size_t, vp, u64, C.c_int, C.c_int, C.c_char_p, C.c_size_t),
     "gaast_plan_precompile": (C.c_int, vp, u64, C.c_int, C.c_int, C.c_int),
+    "gaast_plan_precompile_typed": (C.c_int, vp, u64, C.c_int, C.c_int, C.c_int, C.c_int),
     "gaast_plan_set_tuning": (C.c_int, vp, C.c_int, C.c_int),
     "gaast_plan_last_kernel": (C.c_char_p, vp),
     "gaast_batch_alloc": (C.c_int, vp, u32, u32, u64, C.c_int, C.POINTER(vp)),
     "gaast_batch_wrap": (C.c_int, vp, u32, u32, u64, u64, C.c_int, C.POINTER(vp), C.POINTER(vp)),
+    "gaast_batch_alloc_typed": (C.c_int, vp, u32, u32, u64, C.c_int, C.c_int, C.POINTER(vp)),
+    "gaast_batch_wrap_typed": (C.c_int, vp, u32, u32, u64, u64, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp)),
+    "gaast_batch_dtype": (C.c_int, vp),
     "gaast_batch_free": (C.c_int, vp),
     "gaast_batch_len": (u64, vp),
     "gaast_batch_stride": (u64, vp),
@@ -114,6 +119,8 @@ PROTOTYPES = {
     "gaast_batch_grade_ptr": (vp, vp, u32),
     "gaast_batch_upload": (C.c_int, vp, u32, vp, u64),
     "gaast_batch_download": (C.c_int, vp, u32, vp, u64),
+    "gaast_batch_upload_f32": (C.c_int, vp, u32, vp, u64),
+    "gaast_batch_download_f32": (C.c_int, vp, u32, vp, u64),
     "gaast_batch_zero": (C.c_int, vp),
     "gaast_eval": (C.c_int, vp, C.POINTER(vp), u32, vp, C.c_int, C.c_int),
     "gaast_eval_sum": (C.c_int, vp, C.POINTER(vp), u32, vp, vp, C.c_int, C.c_int),

@@ -87,7 +87,14 @@ struct Gen {
     std::vector<std::vector<uint32_t>> slot_blade;  // per buffer: blade bitmask of every slot
     int ept = 1;
 
-    Gen(const DevicePlanHost& hh, const CodegenOptions& o) : h(hh), opt(o), strict(o.arith == GAAST_ARITH_STRICT) {}
+    // Scalar type of the generated arithmetic: "double", or "float" for the f32 variant.  Every
+    // emitted declaration goes through it, so the f64 text is unchanged by the f32 support.
+    const bool f32;
+    const std::string S;
+    const size_t esize;
+
+    Gen(const DevicePlanHost& hh, const CodegenOptions& o)
+        : h(hh), opt(o), strict(o.arith == GAAST_ARITH_STRICT), f32(o.f32), S(o.f32 ? "float" : "double"), esize(o.f32 ? 4 : 8) {}
 
     int add(const Node& n) {
         nodes.push_back(n);
@@ -526,12 +533,13 @@ struct Gen {
     void emit_node_line(int id) {
         const Node& n = nodes[id];
         const bool wide = !n.uniform;
-        const std::string ty = wide ? "const D " : "const double ";
+        const std::string ty = wide ? "const D " : "const " + S + " ";
         const std::string v = var(id);
         if (!in_prologue && n.uniform && n.export_idx >= 0) {
             // inside the element loop the table pointer is opaque (`uni`), so that the compiler
             // does not hoist a wide table into registers
-            line("const double " + v + " = __ldg(" + (in_loop ? "uni" : "a.uniform") + " + " + std::to_string(n.export_idx) + ");");
+            line("const " + S + " " + v + " = __ldg(" + (in_loop ? "uni" : f32 ? "reinterpret_cast<const float*>(a.uniform)" : "a.uniform") +
+                 " + " + std::to_string(n.export_idx) + ");");
             return;
         }
         switch (n.k) {
@@ -540,7 +548,7 @@ struct Gen {
             case N_LOAD: {
                 const std::string s = std::to_string(n.stream);
                 if (n.uniform)
-                    line("const double " + v + " = __ldg(s" + s + " + " + std::to_string(n.row) + " * r" + s + ");");
+                    line("const " + S + " " + v + " = __ldg(s" + s + " + " + std::to_string(n.row) + " * r" + s + ");");
                 else
                     line("const D " + v + " = d_load(s" + s + " + " + std::to_string(n.row) + " * r" + s + " + e);");
                 return;
@@ -572,7 +580,7 @@ struct Gen {
         return "s" + s + " + " + std::to_string(n.row) + " * r" + s + " + e";
     }
     std::string smem_read(const Node& n) const {
-        return "xs_ld<" + std::to_string(size_t(n.smem_row) * 8) + " * GAAST_THREADS>(xb)";
+        return "xs_ld<" + std::to_string(size_t(n.smem_row) * esize) + " * GAAST_THREADS>(xb)";
     }
     std::string use_name(Ref r) {
         const Node& n = nodes[r.id];
@@ -601,7 +609,7 @@ struct Gen {
             for (size_t j = i; j < end; ++j)
                 line("const D g" + std::to_string(ids[j]) + " = d_load(" + load_addr(nodes[ids[j]]) + ");");
             for (size_t j = i; j < end; ++j)
-                line("xs_st<" + std::to_string(size_t(nodes[ids[j]].smem_row) * 8) + " * GAAST_THREADS>(xb, g" +
+                line("xs_st<" + std::to_string(size_t(nodes[ids[j]].smem_row) * esize) + " * GAAST_THREADS>(xb, g" +
                      std::to_string(ids[j]) + ");");
         }
     }
@@ -1083,7 +1091,10 @@ __device__ __forceinline__ double xs_ldd(unsigned addr) {
 __device__ __forceinline__ double flip_sign(double v, unsigned mask) {
   return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
 }
-// Tensor memory (TMEM) as per-thread scratch: one lane per thread, 32-bit columns
+)GAAST";
+
+// type-independent part of the prelude (tensor memory, TMA, mbarrier), shared by both scalar types
+const char kPreludeShared[] = R"GAAST(// Tensor memory (TMEM) as per-thread scratch: one lane per thread, 32-bit columns
 __device__ __forceinline__ void tm_alloc(unsigned* slot, unsigned cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                    (unsigned)__cvta_generic_to_shared(slot)), "r"(cols) : "memory");
@@ -1205,7 +1216,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "GAAST_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void d_store(double* p, D v) { *p = v; }
+)GAAST";
+
+const char kPreludeTail[] = R"GAAST(__device__ __forceinline__ void d_store(double* p, D v) { *p = v; }
 __device__ __forceinline__ double d_hsum(D a) { return a; }
 #endif
 __device__ __forceinline__ double d_neg(double a) { return -a; }
@@ -1216,6 +1229,54 @@ __device__ __forceinline__ double d_muls(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ double d_adds(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double d_inv(double a) { return __ddiv_rn(1.0, a); }
 __device__ __forceinline__ double d_sqrt(double a) { return __dsqrt_rn(a); }
+)GAAST";
+
+
+// The f32 variant: same generated structure, binary32 arithmetic (FFMA), 4-byte rows.  Batch sums
+// still accumulate in double.  Two elements per thread = one 64-bit access.
+const char kPreludeF32Head[] = R"GAAST(
+typedef float S;
+#if GAAST_EPT == 2
+typedef float2 D;
+__device__ __forceinline__ D U(float x) { return make_float2(x, x); }
+__device__ __forceinline__ D d_load(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ void d_store(float* p, D v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ D d_neg(D a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ D d_fma(D a, D b, D c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ D d_mul(D a, D b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ D d_add(D a, D b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ D d_muls(D a, D b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ D d_adds(D a, D b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ D d_inv(D a) { return make_float2(__fdiv_rn(1.0f, a.x), __fdiv_rn(1.0f, a.y)); }
+__device__ __forceinline__ D d_sqrt(D a) { return make_float2(__fsqrt_rn(a.x), __fsqrt_rn(a.y)); }
+__device__ __forceinline__ double d_hsum(D a) { return (double)a.x + (double)a.y; }
+#else
+typedef float D;
+__device__ __forceinline__ D U(float x) { return x; }
+__device__ __forceinline__ D d_load(const float* p) { return __ldg(p); }
+template <int OFF>
+__device__ __forceinline__ void xs_st(unsigned base, float v) {
+  asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(base), "n"(OFF), "f"(v));
+}
+template <int OFF>
+__device__ __forceinline__ float xs_ld(unsigned base) {
+  float v;
+  asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(base), "n"(OFF));
+  return v;
+}
+)GAAST";
+
+const char kPreludeF32Tail[] = R"GAAST(__device__ __forceinline__ void d_store(float* p, D v) { *p = v; }
+__device__ __forceinline__ double d_hsum(D a) { return (double)a; }
+#endif
+__device__ __forceinline__ float d_neg(float a) { return -a; }
+__device__ __forceinline__ float d_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float d_mul(float a, float b) { return a * b; }
+__device__ __forceinline__ float d_add(float a, float b) { return a + b; }
+__device__ __forceinline__ float d_muls(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float d_adds(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float d_inv(float a) { return __fdiv_rn(1.0f, a); }
+__device__ __forceinline__ float d_sqrt(float a) { return __fsqrt_rn(a); }
 )GAAST";
 
 }  // namespace
@@ -1263,13 +1324,14 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     for (const Node& n : g.nodes)
         if (n.live && n.k == N_LOAD && !n.uniform) ++live_loads;
     const size_t root_cols = h.buf_cols[0];
-    constexpr size_t kAccBudget = 72;  // doubles a thread can keep as accumulators next to its operands
+    // (an f32 value takes one register instead of two: the budgets below nearly double)
+    const size_t kAccBudget = opt.f32 ? 128 : 72;  // values a thread can keep as accumulators next to its operands
     g.op_policy.assign(h.ops.size() + 1, P_TABLE);
     size_t widest = 0;
     int res_parked = 0, res_parkable = 0;
     size_t live_estimate = 0;  // doubles a thread keeps live (widest in-register product + resident rows)
-    constexpr size_t kDenseBudget = 110;  // doubles: outputs + operands of a product that may all be live
-    constexpr size_t kLiveBudget = 124;   // doubles a thread can hold in 255 registers next to addresses
+    const size_t kDenseBudget = opt.f32 ? 200 : 110;  // values: outputs + operands of a product that may all be live
+    const size_t kLiveBudget = opt.f32 ? 224 : 124;   // values a thread can hold in 255 registers next to addresses
     std::vector<int> uses(g.nodes.size(), 0);  // how many live product terms read each node
     std::set<int> blocked_loads;
     size_t widest_table = 0;
@@ -1293,10 +1355,10 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         const bool dense = !g.strict && outs.size() + ls.size() + rs.size() > kDenseBudget &&
                            live_terms * 4 >= ls.size() * rs.size() && load_opnds * 4 >= (ls.size() + rs.size()) * 3;
         Policy pol = outs.size() > kAccBudget ? P_GATHER : P_TABLE;
-        if (dense && outs.size() <= 2 * kAccBudget) pol = P_BLOCKED;
+        if (dense && outs.size() <= 144) pol = P_BLOCKED;  // (up to 2 x the f64 accumulator budget)
         if (opt.variant & 1) pol = P_TABLE;
         if (opt.variant & 2) pol = P_GATHER;
-        if (pol == P_BLOCKED && !opt.with_sum && !opt.pipelined && !(opt.variant & 512) && g.dense.op < 0) {
+        if (pol == P_BLOCKED && !opt.with_sum && !opt.pipelined && !(opt.variant & 512) && g.dense.op < 0 && !opt.f32) {
             std::vector<int> refcount(g.nodes.size(), 0);
             for (const Node& n : g.nodes) {
                 if (!n.live) continue;
@@ -1364,7 +1426,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     for (Node& n : g.nodes)
         if (n.live && n.k == N_LOAD && n.reload && !n.uniform) n.smem_row = n_smem_rows++;
     int ept = opt.elems_per_thread;
-    if (ept != 1 && ept != 2) ept = (live_loads + root_cols + widest <= 48) ? 2 : 1;
+    if (ept != 1 && ept != 2) ept = (live_loads + root_cols + widest <= (opt.f32 ? 96u : 48u)) ? 2 : 1;
     if (n_smem_rows) ept = 1;  // the staging area holds one double per row and thread
     g.ept = ept;
     const int threads = 128;
@@ -1392,14 +1454,15 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
                                : tmem_sum      ? ((threads / 32) * root_cols + 2 + 15) / 16 * 16
                                                : root_cols * size_t(threads);
     const size_t pipe_bytes = sum_doubles * 8 + size_t(2 * n_smem_rows) * threads * 8 + 16;
-    const bool pipelined = opt.pipelined && n_smem_rows > 0 && ept == 1 && pipe_bytes <= kSmemLimit / 2;
-    if (sum_doubles * 8 + size_t(n_smem_rows) * threads * 8 > kSmemLimit)
+    // (TMA staging and the persistent pipeline are f64-only: the f32 variant parks rows with LDG + STS)
+    const bool pipelined = opt.pipelined && n_smem_rows > 0 && ept == 1 && pipe_bytes <= kSmemLimit / 2 && !opt.f32;
+    if (sum_doubles * 8 + size_t(n_smem_rows) * threads * g.esize > kSmemLimit)
         throw Error(GAAST_ERR_JIT, "plan too wide for the specialised engine (shared-memory staging exceeds 227 KB)");
     // TMA staging pays off when most rows are parked (dense products: cfg3 21.2 -> 22.8 TFLOP/s);
     // with a few dozen parked rows next to register rows, LDG + STS is as fast (cfg5: 0.83 vs 0.80)
     bool has_dense = false;
     for (Policy p : g.op_policy) has_dense |= p == P_DENSE || p == P_BLOCKED;
-    const bool tma_stage = opt.tma_stage && has_dense && n_smem_rows > 0 && ept == 1 && !pipelined && !opt.with_sum;
+    const bool tma_stage = opt.tma_stage && has_dense && n_smem_rows > 0 && ept == 1 && !pipelined && !opt.with_sum && !opt.f32;
     g.dense_tmem = tma_stage && g.dense.op >= 0 && (opt.variant & 8192);
     g.pipelined = pipelined;
     g.guard_stores = pipelined || tmem_sum || g.dense_tmem;
@@ -1407,7 +1470,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     g.sum_in_tmem = tmem_sum;
     g.sum_stash = tmem_sum && !(opt.variant & 128) ? std::min<size_t>(root_cols, (tmem_cols - 2 * root_cols) / 2) : 0;
     res.pipelined = pipelined;
-    res.smem_bytes = pipelined ? pipe_bytes : sum_doubles * 8 + size_t(n_smem_rows) * threads * sizeof(double) + (tma_stage ? 16 : 0);
+    res.smem_bytes = pipelined ? pipe_bytes : sum_doubles * 8 + size_t(n_smem_rows) * threads * g.esize + (tma_stage ? 16 : 0);
     res.one_tile_blocks = tma_stage;
     if (tma_stage) notes << "tma-staged ";
     if (tmem_sum) notes << "sum-in-tmem(" << tmem_cols << "cols,stash=" << g.sum_stash << ") ";
@@ -1418,16 +1481,16 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     std::ostringstream src;
     src << "// generated by gaast_b200 codegen: n=" << h.n << " terms=" << h.total_terms << " arith="
         << (g.strict ? "strict" : "fma") << " sum=" << int(opt.with_sum) << " store=" << int(opt.store_out)
-        << " bcast=0x" << std::hex << opt.broadcast_slots << std::dec << "\n// " << notes.str() << "\n";
+        << " bcast=0x" << std::hex << opt.broadcast_slots << std::dec << (opt.f32 ? " dtype=f32" : "") << "\n// " << notes.str() << "\n";
     // Small kernels are pure streaming: ask for several resident blocks so that ptxas does not
     // trade occupancy for hoisting (cfg2_full: 254 registers without this, 2 blocks per SM).
     const size_t live_regs = live_estimate * size_t(ept);
     // (ptxas treats the hint as a register budget to spend: only give it when it is a tight one)
-    const int min_blocks = g.dense_tmem ? 3 : live_regs <= 40 ? 8 : live_regs <= 64 ? 4 : 1;
+    const int min_blocks = g.dense_tmem ? 3 : live_regs <= (opt.f32 ? 80u : 40u) ? 8 : live_regs <= (opt.f32 ? 128u : 64u) ? 4 : 1;
     res.min_blocks = min_blocks;
     src << "#define GAAST_EPT " << ept << "\n#define GAAST_THREADS " << threads << "\n#define GAAST_MIN_BLOCKS "
         << min_blocks << "\n";
-    src << kEvalArgsText << "\nusing gaast::EvalArgs;\n" << kPrelude << "\n";
+    src << kEvalArgsText << "\nusing gaast::EvalArgs;\n" << (opt.f32 ? kPreludeF32Head : kPrelude) << kPreludeShared << (opt.f32 ? kPreludeF32Tail : kPreludeTail) << "\n";
 
     std::ostringstream loop_strides;
     auto stream_decls = [&](std::ostringstream& o, bool prologue) {
@@ -1438,6 +1501,11 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             for (size_t i = h.n_in_streams; i < h.streams.size(); ++i) used.insert(int(i));
         for (int s : used) {
             const bool out = size_t(s) >= h.n_in_streams;
+            if (opt.f32)
+                o << "  " << (out ? "float* __restrict__ s" : "const float* __restrict__ s") << s << " = reinterpret_cast<"
+                  << (out ? "float*" : "const float*") << ">(a.sptr[" << s << "]); const long long R" << s << " = a.srow[" << s
+                  << "]; const long long r" << s << " = R" << s << ";\n";
+            else
             o << "  " << (out ? "double* __restrict__ s" : "const double* __restrict__ s") << s << " = a.sptr[" << s
               << "]; const long long R" << s << " = a.srow[" << s << "]; const long long r" << s << " = R" << s << ";\n";
             // Inside the element loop the stride is made opaque: otherwise the compiler hoists
@@ -1462,7 +1530,8 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         src << "extern \"C\" __global__ void __launch_bounds__(32) gaast_uniform(const __grid_constant__ EvalArgs a) {\n";
         src << "  if (threadIdx.x != 0 || blockIdx.x != 0) return;\n";
         stream_decls(src, true);
-        src << "  double* __restrict__ uo = const_cast<double*>(a.uniform);\n";
+        if (opt.f32) src << "  float* __restrict__ uo = reinterpret_cast<float*>(const_cast<double*>(a.uniform));\n";
+        else src << "  double* __restrict__ uo = const_cast<double*>(a.uniform);\n";
         src << g.body.str();
         for (auto& ex : exports) src << "  uo[" << ex.first << "] = " << g.var(ex.second) << ";\n";
         src << "}\n\n";
@@ -1499,7 +1568,9 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         g.body.str("");
         g.indent = 2;
         g.in_loop = true;
-        if (g.n_export > 0) loop_strides << "    const double* uni = a.uniform; asm volatile(\"\" : \"+l\"(uni));\n";
+        if (g.n_export > 0 && opt.f32)
+            loop_strides << "    const float* uni = reinterpret_cast<const float*>(a.uniform); asm volatile(\"\" : \"+l\"(uni));\n";
+        else if (g.n_export > 0) loop_strides << "    const double* uni = a.uniform; asm volatile(\"\" : \"+l\"(uni));\n";
     }
     // root components, in slot order
     {
@@ -1611,7 +1682,10 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         src << "  }\n";
     } else if (tmem_sum) {
         if (n_smem_rows)
-            src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << sum_doubles << " + tid);\n";
+            {
+                if (opt.f32) src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float*>(sums + " << sum_doubles << ") + tid);\n";
+                else src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << sum_doubles << " + tid);\n";
+            }
         src << "  const long long n_tiles = (a.n + GAAST_THREADS - 1) / GAAST_THREADS;\n";
         src << "  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n";
         src << loop_strides.str();
@@ -1688,7 +1762,10 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         }
     } else {
         if (n_smem_rows)
-            src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << sum_doubles << " + tid);\n";
+            {
+                if (opt.f32) src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float*>(sums + " << sum_doubles << ") + tid);\n";
+                else src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(sums + " << sum_doubles << " + tid);\n";
+            }
         src << "  for (long long e = ((long long)blockIdx.x * GAAST_THREADS + tid) * GAAST_EPT; e < a.n;\n"
                "       e += (long long)gridDim.x * GAAST_THREADS * GAAST_EPT) {\n";
         src << loop_strides.str();

@@ -74,12 +74,18 @@ void ensure(double*& p, size_t& cap, size_t want) {
 
 // Fills the stream table of EvalArgs and validates the bound batches.
 void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out, bool need_out,
-                  gaast::EvalArgs& a, uint64_t* broadcast_slots, long long* n_out) {
+                  gaast::EvalArgs& a, uint64_t* broadcast_slots, long long* n_out, int* dtype_out) {
     const gaast::DevicePlanHost& h = plan->h;
     if (n_inputs != h.n_slots) throw Error(GAAST_ERR_SHAPE, "eval: the plan expects " + std::to_string(h.n_slots) + " input batches");
     if (h.n_slots && !inputs) throw Error(GAAST_ERR_INVALID, "eval: null inputs array");
     long long n = -1;
+    int dtype = -1;  // one scalar type per call
+    auto same_dtype = [&](const gaast_batch* b) {
+        if (dtype < 0) dtype = b->dtype;
+        if (b->dtype != dtype) throw Error(GAAST_ERR_SHAPE, "eval: f64 and f32 batches cannot be mixed in one call");
+    };
     if (out) {
+        same_dtype(out);
         if (out->n != h.n) throw Error(GAAST_ERR_SHAPE, "eval: output batch has another dimension");
         if (out->mask != h.buffer_masks[0])
             throw Error(GAAST_ERR_SHAPE, "eval: output batch must carry exactly the root grade set");
@@ -92,6 +98,7 @@ void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_input
     for (uint32_t s = 0; s < h.n_slots; ++s) {
         const gaast_batch* b = inputs[s];
         if (!b) throw Error(GAAST_ERR_INVALID, "eval: null input batch");
+        same_dtype(b);
         if (b->n != h.n) throw Error(GAAST_ERR_SHAPE, "eval: input batch has another dimension");
         if (h.slot_masks[s] & ~b->mask)
             throw Error(GAAST_ERR_SHAPE, "eval: input batch " + std::to_string(s) + " lacks a grade the plan reads");
@@ -104,6 +111,8 @@ void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_input
     }
     if (n < 0) n = 1;  // everything is broadcast: one element
     *n_out = n;
+    *dtype_out = dtype < 0 ? GAAST_F64 : dtype;
+    const size_t esize = dtype == GAAST_F32 ? 4 : 8;
     std::memset(&a, 0, sizeof a);
     for (size_t i = 0; i < h.streams.size(); ++i) {
         const gaast::Stream& st = h.streams[i];
@@ -121,10 +130,10 @@ void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_input
     // an output array overlapping an input array would be read after it was overwritten
     for (size_t o = h.n_in_streams; o < h.streams.size() && out; ++o) {
         const char* ob = reinterpret_cast<const char*>(a.sptr[o]);
-        const char* oe = ob + size_t(h.streams[o].rows) * size_t(a.srow[o]) * sizeof(double);
+        const char* oe = ob + size_t(h.streams[o].rows) * size_t(a.srow[o]) * esize;
         for (size_t i = 0; i < h.n_in_streams; ++i) {
             const char* ib = reinterpret_cast<const char*>(a.sptr[i]);
-            const char* ie = ib + size_t(h.streams[i].rows) * size_t(a.srow[i]) * sizeof(double);
+            const char* ie = ib + size_t(h.streams[i].rows) * size_t(a.srow[i]) * esize;
             if (ob < ie && ib < oe) throw Error(GAAST_ERR_INVALID, "eval: the output batch overlaps an input batch");
         }
     }
@@ -289,6 +298,11 @@ size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int 
 }
 
 gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, int store_out) {
+    return gaast_plan_precompile_typed(plan, broadcast_slots, arith, with_sum, store_out, GAAST_F64);
+}
+
+gaast_status gaast_plan_precompile_typed(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, int store_out,
+                                         int dtype) {
     return guard([&] {
         if (!plan) throw Error(GAAST_ERR_INVALID, "null plan");
         gaast::CodegenOptions opt;
@@ -300,6 +314,7 @@ gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, i
         opt.variant = plan->variant;
         opt.pipelined = (opt.variant & 8) != 0;
         opt.tma_stage = !opt.pipelined && !opt.with_sum && !(opt.variant & 1024);
+        opt.f32 = dtype == GAAST_F32;
         gaast::CodegenResult cg;
         std::string key, origin;
         gaast::build_specialized(plan->h, opt, &cg, &key, &origin);
@@ -309,7 +324,7 @@ gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, i
 
 // --------------------------------------------------------------- batch ----
 static gaast_status batch_make(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
-                               int broadcast, void* const* grade_ptrs, gaast_batch** out) {
+                               int broadcast, int dtype, void* const* grade_ptrs, gaast_batch** out) {
     return guard([&] {
         if (!out) throw Error(GAAST_ERR_INVALID, "null output pointer");
         *out = nullptr;
@@ -317,7 +332,11 @@ static gaast_status batch_make(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, 
         if (n > GAAST_MAX_DIM) throw Error(GAAST_ERR_INVALID, "dimension above GAAST_MAX_DIM");
         if (grade_mask & ~((2u << n) - 1)) throw Error(GAAST_ERR_INVALID, "grade mask has grades above n");
         if (broadcast && len != 1) throw Error(GAAST_ERR_INVALID, "a broadcast batch holds exactly one element");
+        if (dtype != GAAST_F64 && dtype != GAAST_F32) throw Error(GAAST_ERR_INVALID, "unknown dtype");
         auto b = std::make_unique<gaast_batch>();
+        b->dtype = dtype;
+        const size_t es = b->esize();
+        const uint64_t row_quantum = 128 / es;  // rows start on 128-byte boundaries
         b->ctx = ctx;
         b->n = n;
         b->mask = grade_mask;
@@ -335,17 +354,17 @@ static gaast_status batch_make(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, 
                     b->grade_ptr[k] = static_cast<double*>(grade_ptrs[i++]);
                 }
         } else {
-            b->stride = (len + 15) / 16 * 16;  // rows start on 128-byte boundaries
-            if (b->stride == 0) b->stride = 16;
+            b->stride = (len + row_quantum - 1) / row_quantum * row_quantum;
+            if (b->stride == 0) b->stride = row_quantum;
             const size_t total = size_t(b->rows) * b->stride;
             if (total) {
-                cuda_check(cudaMalloc(&b->base, total * sizeof(double)), "cudaMalloc(batch)");
+                cuda_check(cudaMalloc(&b->base, total * es), "cudaMalloc(batch)");
                 b->owned = true;
             }
             size_t row = 0;
             for (uint32_t k = 0; k <= n; ++k)
                 if (grade_mask >> k & 1) {
-                    b->grade_ptr[k] = b->base + row * b->stride;
+                    b->grade_ptr[k] = reinterpret_cast<double*>(reinterpret_cast<char*>(b->base) + row * b->stride * es);
                     row += gaast::binomial(n, k);
                 }
         }
@@ -355,7 +374,12 @@ static gaast_status batch_make(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, 
 
 gaast_status gaast_batch_alloc(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, int broadcast,
                                gaast_batch** out) {
-    return batch_make(ctx, n, grade_mask, len, 0, broadcast, nullptr, out);
+    return batch_make(ctx, n, grade_mask, len, 0, broadcast, GAAST_F64, nullptr, out);
+}
+
+gaast_status gaast_batch_alloc_typed(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, int broadcast,
+                                     int dtype, gaast_batch** out) {
+    return batch_make(ctx, n, grade_mask, len, 0, broadcast, dtype, nullptr, out);
 }
 
 gaast_status gaast_batch_wrap(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
@@ -364,8 +388,19 @@ gaast_status gaast_batch_wrap(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, u
         gaast::set_last_error("null grade pointer array");
         return GAAST_ERR_INVALID;
     }
-    return batch_make(ctx, n, grade_mask, len, stride, broadcast, grade_ptrs, out);
+    return batch_make(ctx, n, grade_mask, len, stride, broadcast, GAAST_F64, grade_ptrs, out);
 }
+
+gaast_status gaast_batch_wrap_typed(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
+                                    int broadcast, int dtype, void* const* grade_ptrs, gaast_batch** out) {
+    if (!grade_ptrs) {
+        gaast::set_last_error("null grade pointer array");
+        return GAAST_ERR_INVALID;
+    }
+    return batch_make(ctx, n, grade_mask, len, stride, broadcast, dtype, grade_ptrs, out);
+}
+
+int gaast_batch_dtype(const gaast_batch* b) { return b ? b->dtype : GAAST_F64; }
 
 gaast_status gaast_batch_free(gaast_batch* b) {
     return guard([&] {
@@ -386,8 +421,10 @@ void* gaast_batch_grade_ptr(const gaast_batch* b, uint32_t grade) {
     return b->grade_ptr[grade];
 }
 
-static void batch_copy(const gaast_batch* b, uint32_t grade, double* host, uint64_t host_stride, bool to_device) {
+static void batch_copy(const gaast_batch* b, uint32_t grade, void* host, uint64_t host_stride, bool to_device, int dtype) {
     if (!b) throw Error(GAAST_ERR_INVALID, "null batch");
+    if (b->dtype != dtype) throw Error(GAAST_ERR_SHAPE, "the batch holds another scalar type than the host array");
+    const size_t es = b->esize();
     if (grade > b->n || !(b->mask >> grade & 1)) throw Error(GAAST_ERR_SHAPE, "the batch does not hold this grade");
     if (!host) throw Error(GAAST_ERR_INVALID, "null host pointer");
     if (host_stride < b->len) throw Error(GAAST_ERR_INVALID, "host stride smaller than the batch length");
@@ -396,20 +433,26 @@ static void batch_copy(const gaast_batch* b, uint32_t grade, double* host, uint6
     DeviceGuard dg(b->ctx->device);
     double* dev = b->grade_ptr[grade];
     if (to_device)
-        cuda_check(cudaMemcpy2DAsync(dev, b->stride * 8, host, host_stride * 8, b->len * 8, rows, cudaMemcpyHostToDevice,
+        cuda_check(cudaMemcpy2DAsync(dev, b->stride * es, host, host_stride * es, b->len * es, rows, cudaMemcpyHostToDevice,
                                      b->ctx->stream),
                    "batch upload");
     else
-        cuda_check(cudaMemcpy2DAsync(host, host_stride * 8, dev, b->stride * 8, b->len * 8, rows, cudaMemcpyDeviceToHost,
+        cuda_check(cudaMemcpy2DAsync(host, host_stride * es, dev, b->stride * es, b->len * es, rows, cudaMemcpyDeviceToHost,
                                      b->ctx->stream),
                    "batch download");
 }
 
 gaast_status gaast_batch_upload(gaast_batch* b, uint32_t grade, const double* host, uint64_t host_stride) {
-    return guard([&] { batch_copy(b, grade, const_cast<double*>(host), host_stride, true); });
+    return guard([&] { batch_copy(b, grade, const_cast<double*>(host), host_stride, true, GAAST_F64); });
+}
+gaast_status gaast_batch_upload_f32(gaast_batch* b, uint32_t grade, const float* host, uint64_t host_stride) {
+    return guard([&] { batch_copy(b, grade, const_cast<float*>(host), host_stride, true, GAAST_F32); });
+}
+gaast_status gaast_batch_download_f32(const gaast_batch* b, uint32_t grade, float* host, uint64_t host_stride) {
+    return guard([&] { batch_copy(b, grade, host, host_stride, false, GAAST_F32); });
 }
 gaast_status gaast_batch_download(const gaast_batch* b, uint32_t grade, double* host, uint64_t host_stride) {
-    return guard([&] { batch_copy(b, grade, host, host_stride, false); });
+    return guard([&] { batch_copy(b, grade, host, host_stride, false, GAAST_F64); });
 }
 gaast_status gaast_batch_zero(gaast_batch* b) {
     return guard([&] {
@@ -417,7 +460,7 @@ gaast_status gaast_batch_zero(gaast_batch* b) {
         DeviceGuard dg(b->ctx->device);
         for (uint32_t k = 0; k <= b->n; ++k)
             if (b->mask >> k & 1)
-                cuda_check(cudaMemsetAsync(b->grade_ptr[k], 0, gaast::binomial(b->n, k) * b->stride * 8, b->ctx->stream),
+                cuda_check(cudaMemsetAsync(b->grade_ptr[k], 0, gaast::binomial(b->n, k) * b->stride * b->esize(), b->ctx->stream),
                            "batch zero");
     });
 }
@@ -425,7 +468,7 @@ gaast_status gaast_batch_zero(gaast_batch* b) {
 // ---------------------------------------------------------------- eval ----
 static std::shared_ptr<gaast::JitKernel> get_specialized(gaast_plan* plan, const gaast::CodegenOptions& opt) {
     auto key = std::make_tuple(opt.broadcast_slots, opt.arith, int(opt.with_sum), int(opt.store_out),
-                               opt.elems_per_thread, opt.variant, int(opt.pipelined), int(opt.tma_stage));
+                               opt.elems_per_thread, opt.variant, int(opt.pipelined), int(opt.tma_stage), int(opt.f32));
     auto it = plan->jit.find(key);
     if (it != plan->jit.end()) return it->second;
     gaast::CodegenResult cg;
@@ -449,7 +492,9 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     gaast::EvalArgs a;
     uint64_t bslots = 0;
     long long n = 0;
-    bind_streams(plan, inputs, n_inputs, out, !with_sum, a, &bslots, &n);
+    int dtype = GAAST_F64;
+    bind_streams(plan, inputs, n_inputs, out, !with_sum, a, &bslots, &n, &dtype);
+    const bool f32 = dtype == GAAST_F32;
     const gaast::DevicePlanHost& h = plan->h;
     const int sum_cols = int(h.buf_cols[0]);
     a.n_sum_cols = with_sum ? sum_cols : 0;
@@ -473,6 +518,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                 opt.store_out = out != nullptr;
                 opt.elems_per_thread = plan->force_ept;
                 opt.variant = plan->variant;
+                opt.f32 = f32;
                 // 128-bit accesses need even strides and 16-byte aligned rows
                 bool aligned = (n % 2 == 0);
                 for (size_t i = 0; i < h.streams.size(); ++i) {
@@ -533,7 +579,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                       jk->local_bytes, jk->key.c_str());
         plan->last_kernel = desc;
     } else {
-        gaast::TableLaunch shape = gaast::table_engine_shape(*ctx, h, n, with_sum);
+        gaast::TableLaunch shape = gaast::table_engine_shape(*ctx, h, n, with_sum, f32);
         grid = shape.grid;
         if (shape.global_ws) {
             ensure(plan->d_ws, plan->ws_cap, size_t(grid) * shape.ws_doubles_per_block);
@@ -547,7 +593,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         a.chunks = plan->d_chunks;
         a.n_micro = int(h.micro.size());
         a.n_chunks = int(h.chunks.size());
-        cuda_check(gaast::table_engine_launch(a, shape, arith == GAAST_ARITH_STRICT, with_sum, ctx->stream),
+        cuda_check(gaast::table_engine_launch(a, shape, arith == GAAST_ARITH_STRICT, with_sum, f32, ctx->stream),
                    "launch table engine");
         ctx->launches++;
         char desc[256];

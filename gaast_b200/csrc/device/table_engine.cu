@@ -60,6 +60,18 @@ __device__ __forceinline__ double term_acc(double acc, double l, double r, doubl
     if (kStrict) return __dadd_rn(acc, __dmul_rn(__dmul_rn(l, r), c));  // eval.rs:82, no contraction
     return fma(l * c, r, acc);
 }
+// the f32 variant: the same operation sequence in binary32 (coefficients rounded to binary32)
+template <bool kStrict>
+__device__ __forceinline__ float term_acc(float acc, float l, float r, float c) {
+    if (kStrict) return __fadd_rn(acc, __fmul_rn(__fmul_rn(l, r), c));
+    return fmaf(l * c, r, acc);
+}
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double inv_rn(double a) { return __ddiv_rn(1.0, a); }
+__device__ __forceinline__ float inv_rn(float a) { return __fdiv_rn(1.0f, a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
 
 // Thread layout: lane = batch element (32 per block and tile), warp = work group.  The
 // element's workspace is shared by the block's warps: inside a micro-op they split the rows
@@ -71,16 +83,21 @@ __device__ __forceinline__ double term_acc(double acc, double l, double r, doubl
 // kGlobalWs is a template parameter so that, in the common case, the compiler knows the
 // workspace is shared memory and emits LDS/STS instead of generic loads and stores.
 constexpr int kLanes = 32;
-template <bool kStrict, bool kSum, bool kGlobalWs>
+// T = scalar type of the batches and of the workspace (double, or float for the f32 variant);
+// the batch-sum columns are double in both cases and follow the T workspace.
+template <class T, bool kStrict, bool kSum, bool kGlobalWs>
 __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant__ EvalArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TermChunk* stage = reinterpret_cast<TermChunk*>(smem_raw);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + kBarOffset);
     const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5, G = blockDim.x >> 5;
-    const int cols = a.total_cols + (kSum ? a.n_sum_cols : 0);
-    double* ws = kGlobalWs ? a.ws_global + size_t(blockIdx.x) * cols * kLanes
-                           : reinterpret_cast<double*>(smem_raw + kWsOffset);
-    double* w = ws + lane;  // column c of this lane's element: w[c * kLanes]
+    const int cols = a.total_cols + (kSum ? a.n_sum_cols : 0);  // (the global workspace is sized in doubles)
+    T* ws = kGlobalWs ? reinterpret_cast<T*>(a.ws_global + size_t(blockIdx.x) * cols * kLanes)
+                      : reinterpret_cast<T*>(smem_raw + kWsOffset);
+    T* w = ws + lane;  // column c of this lane's element: w[c * kLanes]
+    // sum columns: doubles behind the T columns (8-byte aligned: total_cols * 32 lanes * sizeof(T))
+    double* sum_ws = reinterpret_cast<double*>(ws + size_t(a.total_cols) * kLanes);
+    double* sw = sum_ws + lane;
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -88,7 +105,7 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (kSum)
-        for (int c = grp; c < a.n_sum_cols; c += G) w[size_t(a.total_cols + c) * kLanes] = 0.0;
+        for (int c = grp; c < a.n_sum_cols; c += G) sw[size_t(c) * kLanes] = 0.0;
     __syncthreads();
 
     const long long tile_step = (long long)gridDim.x * kLanes;
@@ -108,7 +125,7 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
     for (long long base = first; base < a.n; base += tile_step) {
         const long long e = base + lane;
         const bool active = e < a.n;
-        for (int c = grp; c < a.total_cols; c += G) w[size_t(c) * kLanes] = 0.0;  // init_null_mv, eval.rs:27-30
+        for (int c = grp; c < a.total_cols; c += G) w[size_t(c) * kLanes] = T(0);  // init_null_mv, eval.rs:27-30
         __syncthreads();
 
         for (int m = 0; m < a.n_micro; ++m) {
@@ -116,25 +133,25 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
             switch (op.kind) {
                 case MK_LOAD_ADD: {  // eval.rs:45-50
                     const bool bc = (a.bcast[op.a >> 6] >> (op.a & 63)) & 1;
-                    const double* src = a.sptr[op.a] + (long long)op.b * a.srow[op.a] + (bc ? 0 : e);
+                    const T* src = reinterpret_cast<const T*>(a.sptr[op.a]) + (long long)op.b * a.srow[op.a] + (bc ? 0 : e);
                     const long long rs = a.srow[op.a];
                     for (uint32_t r = grp; r < op.count; r += G) {
-                        double* d = &w[size_t(op.dst_col + r) * kLanes];
-                        const double v = active ? __ldg(src + r * rs) : 0.0;
-                        *d = kStrict ? __dadd_rn(*d, v) : (*d + v);
+                        T* d = &w[size_t(op.dst_col + r) * kLanes];
+                        const T v = active ? __ldg(src + r * rs) : T(0);
+                        *d = kStrict ? add_rn(*d, v) : (*d + v);
                     }
                     break;
                 }
                 case MK_CONST_ADD:
                     for (uint32_t r = grp; r < op.count; r += G) {
-                        double* d = &w[size_t(op.dst_col + r) * kLanes];
-                        *d = *d + a.consts[op.a + r];
+                        T* d = &w[size_t(op.dst_col + r) * kLanes];
+                        *d = *d + T(a.consts[op.a + r]);
                     }
                     break;
                 case MK_MUL: {  // eval.rs:61-86
-                    const double* wl = w + size_t(op.a) * kLanes;
-                    const double* wr = w + size_t(op.b) * kLanes;
-                    double* wd = w + size_t(op.dst_col) * kLanes;
+                    const T* wl = w + size_t(op.a) * kLanes;
+                    const T* wr = w + size_t(op.b) * kLanes;
+                    T* wd = w + size_t(op.dst_col) * kLanes;
                     for (uint32_t ci = 0; ci < op.count; ++ci) {
                         if (tid == 0 && q + 1 < total_chunks) issue(q + 1);
                         mbar_wait(&mbar[q & 1], unsigned(q >> 1) & 1);
@@ -143,25 +160,25 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
                         for (uint32_t r = grp; r < n_runs; r += G) {  // this warp's output runs
                             uint32_t s = ch.run_start[r];
                             const uint32_t end = ch.run_start[r + 1];
-                            double* o = wd + size_t(ch.terms[s].out) * kLanes;
-                            double acc = *o;
+                            T* o = wd + size_t(ch.terms[s].out) * kLanes;
+                            T acc = *o;
                             // four terms per trip: their 4 table reads and 8 operand reads are
                             // independent, only the accumulator chains (reference order kept)
                             for (; s + 4 <= end; s += 4) {
                                 const gaast_term t0 = ch.terms[s], t1 = ch.terms[s + 1], t2 = ch.terms[s + 2],
                                                  t3 = ch.terms[s + 3];
-                                const double l0 = wl[size_t(t0.a) * kLanes], r0 = wr[size_t(t0.b) * kLanes];
-                                const double l1 = wl[size_t(t1.a) * kLanes], r1 = wr[size_t(t1.b) * kLanes];
-                                const double l2 = wl[size_t(t2.a) * kLanes], r2 = wr[size_t(t2.b) * kLanes];
-                                const double l3 = wl[size_t(t3.a) * kLanes], r3 = wr[size_t(t3.b) * kLanes];
-                                acc = term_acc<kStrict>(acc, l0, r0, t0.coeff);
-                                acc = term_acc<kStrict>(acc, l1, r1, t1.coeff);
-                                acc = term_acc<kStrict>(acc, l2, r2, t2.coeff);
-                                acc = term_acc<kStrict>(acc, l3, r3, t3.coeff);
+                                const T l0 = wl[size_t(t0.a) * kLanes], r0 = wr[size_t(t0.b) * kLanes];
+                                const T l1 = wl[size_t(t1.a) * kLanes], r1 = wr[size_t(t1.b) * kLanes];
+                                const T l2 = wl[size_t(t2.a) * kLanes], r2 = wr[size_t(t2.b) * kLanes];
+                                const T l3 = wl[size_t(t3.a) * kLanes], r3 = wr[size_t(t3.b) * kLanes];
+                                acc = term_acc<kStrict>(acc, l0, r0, T(t0.coeff));
+                                acc = term_acc<kStrict>(acc, l1, r1, T(t1.coeff));
+                                acc = term_acc<kStrict>(acc, l2, r2, T(t2.coeff));
+                                acc = term_acc<kStrict>(acc, l3, r3, T(t3.coeff));
                             }
                             for (; s < end; ++s) {
                                 const gaast_term t = ch.terms[s];
-                                acc = term_acc<kStrict>(acc, wl[size_t(t.a) * kLanes], wr[size_t(t.b) * kLanes], t.coeff);
+                                acc = term_acc<kStrict>(acc, wl[size_t(t.a) * kLanes], wr[size_t(t.b) * kLanes], T(t.coeff));
                             }
                             *o = acc;
                         }
@@ -172,31 +189,31 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
                 }
                 case MK_NEG:  // graded.rs:61-65
                     for (uint32_t r = grp; r < op.count; r += G) {
-                        double* d = &w[size_t(op.dst_col + r) * kLanes];
+                        T* d = &w[size_t(op.dst_col + r) * kLanes];
                         *d = -*d;
                     }
                     break;
                 case MK_INV:  // eval.rs:107
                     if (grp == 0) {
-                        double* d = &w[size_t(op.dst_col) * kLanes];
-                        *d = __ddiv_rn(1.0, *d);
+                        T* d = &w[size_t(op.dst_col) * kLanes];
+                        *d = inv_rn(*d);
                     }
                     break;
                 case MK_SQRT:  // eval.rs:108
                     if (grp == 0) {
-                        double* d = &w[size_t(op.dst_col) * kLanes];
-                        *d = __dsqrt_rn(*d);
+                        T* d = &w[size_t(op.dst_col) * kLanes];
+                        *d = sqrt_rn(*d);
                     }
                     break;
                 case MK_STORE: {
-                    double* dst = a.sptr[op.a] + (long long)op.b * a.srow[op.a] + e;
+                    T* dst = reinterpret_cast<T*>(a.sptr[op.a]) + (long long)op.b * a.srow[op.a] + e;
                     const long long rs = a.srow[op.a];
                     for (uint32_t r = grp; r < op.count; r += G) {
-                        const double v = w[size_t(op.dst_col + r) * kLanes];
+                        const T v = w[size_t(op.dst_col + r) * kLanes];
                         if (active && a.store_out) dst[r * rs] = v;
                         if (kSum && active) {
-                            double* sc = &w[size_t(a.total_cols + (op.dst_col - a.root_col) + r) * kLanes];
-                            *sc = *sc + v;
+                            double* sc = &sw[size_t((op.dst_col - a.root_col) + r) * kLanes];
+                            *sc = *sc + double(v);
                         }
                     }
                     break;
@@ -210,7 +227,7 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
         // Fixed-order block reduction of the per-lane column sums.
         __syncthreads();
         for (int c = tid; c < a.n_sum_cols; c += blockDim.x) {
-            const double* col = ws + size_t(a.total_cols + c) * kLanes;
+            const double* col = sum_ws + size_t(c) * kLanes;
             double s = 0.0;
             for (int t = 0; t < kLanes; ++t) s += col[t];
             a.partials[size_t(blockIdx.x) * a.n_sum_cols + c] = s;
@@ -236,26 +253,32 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
     if (threadIdx.x == 0) out[c] = tree[0];
 }
 
-template <bool kStrict, bool kSum, bool kGlobalWs>
+template <class T, bool kStrict, bool kSum, bool kGlobalWs>
 cudaError_t launch_g(const EvalArgs& args, const TableLaunch& shape, cudaStream_t stream) {
-    auto k = table_engine_kernel<kStrict, kSum, kGlobalWs>;
+    auto k = table_engine_kernel<T, kStrict, kSum, kGlobalWs>;
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shape.smem));
     if (err != cudaSuccess) return err;
     k<<<shape.grid, shape.threads, shape.smem, stream>>>(args);
     return cudaGetLastError();
 }
-template <bool kStrict, bool kSum>
+template <class T, bool kStrict, bool kSum>
 cudaError_t launch_t(const EvalArgs& args, const TableLaunch& shape, cudaStream_t stream) {
-    return shape.global_ws ? launch_g<kStrict, kSum, true>(args, shape, stream)
-                           : launch_g<kStrict, kSum, false>(args, shape, stream);
+    return shape.global_ws ? launch_g<T, kStrict, kSum, true>(args, shape, stream)
+                           : launch_g<T, kStrict, kSum, false>(args, shape, stream);
+}
+template <class T>
+cudaError_t launch_s(const EvalArgs& args, const TableLaunch& shape, bool strict, bool with_sum, cudaStream_t stream) {
+    if (strict) return with_sum ? launch_t<T, true, true>(args, shape, stream) : launch_t<T, true, false>(args, shape, stream);
+    return with_sum ? launch_t<T, false, true>(args, shape, stream) : launch_t<T, false, false>(args, shape, stream);
 }
 
 }  // namespace
 
-TableLaunch table_engine_shape(const gaast_ctx& ctx, const DevicePlanHost& h, long long n, bool with_sum) {
+TableLaunch table_engine_shape(const gaast_ctx& ctx, const DevicePlanHost& h, long long n, bool with_sum, bool f32) {
     TableLaunch s;
     const size_t cols = h.total_cols + (with_sum ? h.buf_cols[0] : 0);
-    const size_t ws_bytes = cols * sizeof(double) * kLanes;  // one tile = 32 elements
+    // one tile = 32 elements; the sum columns are doubles in both variants
+    const size_t ws_bytes = (h.total_cols * (f32 ? sizeof(float) : sizeof(double)) + (with_sum ? h.buf_cols[0] * sizeof(double) : 0)) * kLanes;
     s.threads = 256;                                         // 8 warps share the tile's work
     s.global_ws = kWsOffset + ws_bytes > size_t(ctx.smem_optin);
     s.smem = s.global_ws ? kWsOffset : kWsOffset + ws_bytes;
@@ -268,10 +291,9 @@ TableLaunch table_engine_shape(const gaast_ctx& ctx, const DevicePlanHost& h, lo
     return s;
 }
 
-cudaError_t table_engine_launch(const EvalArgs& args, const TableLaunch& shape, bool strict, bool with_sum,
+cudaError_t table_engine_launch(const EvalArgs& args, const TableLaunch& shape, bool strict, bool with_sum, bool f32,
                                 cudaStream_t stream) {
-    if (strict) return with_sum ? launch_t<true, true>(args, shape, stream) : launch_t<true, false>(args, shape, stream);
-    return with_sum ? launch_t<false, true>(args, shape, stream) : launch_t<false, false>(args, shape, stream);
+    return f32 ? launch_s<float>(args, shape, strict, with_sum, stream) : launch_s<double>(args, shape, strict, with_sum, stream);
 }
 
 cudaError_t reduce_partials_launch(const double* partials, int n_blocks, int n_cols, double* out,

@@ -46,6 +46,7 @@ struct CodegenOptions {
     bool pipelined = true;     // parked rows arrive by TMA in a persistent, double-buffered block (needs 16-byte aligned rows)
     bool tma_stage = false;    // one-tile blocks: parked rows copied to shared memory by TMA bulk copies (aligned rows)
     int extra_parked = 0;      // more input rows parked in shared memory (raised while ptxas reports spills)
+    bool f32 = false;          // binary32 batches and arithmetic (the f32 variant); batch sums stay in double
 };
 
 struct CodegenResult {
@@ -88,8 +89,8 @@ struct TableLaunch {
     bool global_ws = false;
     size_t ws_doubles_per_block = 0;  // global workspace: columns x 32 lanes
 };
-TableLaunch table_engine_shape(const gaast_ctx& ctx, const DevicePlanHost& h, long long n, bool with_sum);
-cudaError_t table_engine_launch(const EvalArgs& args, const TableLaunch& shape, bool strict, bool with_sum,
+TableLaunch table_engine_shape(const gaast_ctx& ctx, const DevicePlanHost& h, long long n, bool with_sum, bool f32);
+cudaError_t table_engine_launch(const EvalArgs& args, const TableLaunch& shape, bool strict, bool with_sum, bool f32,
                                 cudaStream_t stream);
 cudaError_t reduce_partials_launch(const double* partials, int n_blocks, int n_cols, double* out,
                                    cudaStream_t stream);
@@ -117,6 +118,8 @@ struct gaast_batch {
     uint32_t n = 0, mask = 0;
     uint64_t len = 0, stride = 0;
     bool broadcast = false, owned = false;
+    int dtype = GAAST_F64;  // the pointers below address f32 arrays when dtype == GAAST_F32
+    size_t esize() const { return dtype == GAAST_F32 ? 4 : 8; }
     double* base = nullptr;
     double* grade_ptr[GAAST_MAX_DIM + 1] = {};
     uint32_t rows = 0;
@@ -136,7 +139,7 @@ struct gaast_plan {
     size_t uniform_cap = 0;
     std::string last_kernel;
     // specialised kernels, keyed by (broadcast slots, arith, with_sum, store_out, elems/thread, variant)
-    std::map<std::tuple<uint64_t, int, int, int, int, int, int, int>, std::shared_ptr<gaast::JitKernel>> jit;
+    std::map<std::tuple<uint64_t, int, int, int, int, int, int, int, int>, std::shared_ptr<gaast::JitKernel>> jit;
     std::string jit_error;  // sticky: why the specialised engine is unavailable
     int variant = 0;
     int force_ept = 0;

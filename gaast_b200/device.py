@@ -70,8 +70,13 @@ def _torch_stream_ctx(device: int) -> Ctx:
     return ctx
 
 
+def _np_dtype(dtype: int):
+    return np.float32 if dtype == L.F32 else np.float64
+
+
 class DeviceBatch:
-    """gaast_batch: per grade k a [C(n,k)][stride] f64 device array."""
+    """gaast_batch: per grade k a [C(n,k)][stride] device array, f64 (the reference's type) or,
+    with dtype=L.F32, binary32 (the reduced-precision variant)."""
 
     def __init__(self, handle, ctx: Ctx, n: int, keep=()):
         self._h = handle
@@ -80,20 +85,25 @@ class DeviceBatch:
         self._keep = keep
 
     @staticmethod
-    def alloc(ctx: Ctx, n: int, grades: Iterable[int], length: int, broadcast: bool = False) -> "DeviceBatch":
+    def alloc(ctx: Ctx, n: int, grades: Iterable[int], length: int, broadcast: bool = False,
+              dtype: int = L.F64) -> "DeviceBatch":
         out = L.vp()
-        L.check(L.lib.gaast_batch_alloc(ctx._h, n, grade_mask(grades), int(length), int(broadcast), C.byref(out)))
+        L.check(L.lib.gaast_batch_alloc_typed(ctx._h, n, grade_mask(grades), int(length), int(broadcast), int(dtype),
+                                              C.byref(out)))
         return DeviceBatch(out, ctx, n)
 
     @staticmethod
     def wrap_torch(ctx: Ctx, n: int, tensors: Dict[int, "object"], broadcast: bool = False) -> "DeviceBatch":
-        """Wrap caller-owned CUDA float64 tensors {grade: [C(n,k), len]} (row-major)."""
+        """Wrap caller-owned CUDA float64 (or, all of them, float32) tensors {grade: [C(n,k), len]} (row-major)."""
         grades = sorted(tensors)
         length, stride = None, None
         ptrs = []
+        kinds = {str(t.dtype) for t in tensors.values()}
+        assert kinds <= {"torch.float64"} or kinds <= {"torch.float32"}, "one scalar type per batch"
+        dtype = L.F32 if kinds == {"torch.float32"} else L.F64
         for k in grades:
             t = tensors[k]
-            assert t.is_cuda and str(t.dtype) == "torch.float64" and t.dim() == 2 and t.shape[0] == comb(n, k)
+            assert t.is_cuda and t.dim() == 2 and t.shape[0] == comb(n, k)
             assert t.stride(1) == 1 or t.shape[1] == 1
             if length is None:
                 length, stride = t.shape[1], (t.stride(0) if t.shape[0] > 1 else t.shape[1])
@@ -103,20 +113,21 @@ class DeviceBatch:
             ptrs.append(t.data_ptr())
         arr = (L.vp * len(ptrs))(*ptrs)
         out = L.vp()
-        L.check(L.lib.gaast_batch_wrap(ctx._h, n, grade_mask(grades), int(length), int(stride), int(broadcast), arr,
-                                       C.byref(out)))
+        L.check(L.lib.gaast_batch_wrap_typed(ctx._h, n, grade_mask(grades), int(length), int(stride), int(broadcast),
+                                             dtype, arr, C.byref(out)))
         return DeviceBatch(out, ctx, n, keep=tuple(tensors.values()))
 
     @staticmethod
-    def from_host(ctx: Ctx, n: int, data: Dict[int, np.ndarray], broadcast: bool = False) -> "DeviceBatch":
-        """Upload {grade: [C(n,k), len] float64} (a 1-D array is one broadcast element)."""
+    def from_host(ctx: Ctx, n: int, data: Dict[int, np.ndarray], broadcast: bool = False,
+                  dtype: int = L.F64) -> "DeviceBatch":
+        """Upload {grade: [C(n,k), len]} as `dtype` (a 1-D array is one broadcast element)."""
         grades = sorted(data)
-        arrs = {k: np.ascontiguousarray(np.asarray(data[k], dtype=np.float64)) for k in grades}
+        arrs = {k: np.ascontiguousarray(np.asarray(data[k], dtype=_np_dtype(dtype))) for k in grades}
         for k in grades:
             if arrs[k].ndim == 1:
                 arrs[k] = arrs[k].reshape(-1, 1)
         length = arrs[grades[0]].shape[1] if grades else 0
-        b = DeviceBatch.alloc(ctx, n, grades, length, broadcast)
+        b = DeviceBatch.alloc(ctx, n, grades, length, broadcast, dtype)
         for k in grades:
             b.upload(k, arrs[k])
         ctx.sync()
@@ -130,6 +141,10 @@ class DeviceBatch:
     def stride(self) -> int:
         return L.lib.gaast_batch_stride(self._h)
 
+    @property
+    def dtype(self) -> int:
+        return L.lib.gaast_batch_dtype(self._h)
+
     def grade_set(self) -> List[int]:  # Graded::grade_set, graded.rs:20-30
         return grades_of(L.lib.gaast_batch_grade_mask(self._h))
 
@@ -137,14 +152,18 @@ class DeviceBatch:
         return L.lib.gaast_batch_grade_ptr(self._h, k) or 0
 
     def upload(self, k: int, host: np.ndarray):
-        host = np.ascontiguousarray(host, dtype=np.float64)
+        f32 = self.dtype == L.F32
+        host = np.ascontiguousarray(host, dtype=_np_dtype(self.dtype))
         assert host.ndim == 2 and host.shape[0] == comb(self.n, k)
-        L.check(L.lib.gaast_batch_upload(self._h, k, host.ctypes.data_as(L.vp), host.shape[1]))
+        fn = L.lib.gaast_batch_upload_f32 if f32 else L.lib.gaast_batch_upload
+        L.check(fn(self._h, k, host.ctypes.data_as(L.vp), host.shape[1]))
         self.ctx.sync()  # `host` may be a temporary
 
     def download(self, k: int) -> np.ndarray:
-        out = np.empty((comb(self.n, k), self.length), dtype=np.float64)
-        L.check(L.lib.gaast_batch_download(self._h, k, out.ctypes.data_as(L.vp), out.shape[1]))
+        f32 = self.dtype == L.F32
+        out = np.empty((comb(self.n, k), self.length), dtype=_np_dtype(self.dtype))
+        fn = L.lib.gaast_batch_download_f32 if f32 else L.lib.gaast_batch_download
+        L.check(fn(self._h, k, out.ctypes.data_as(L.vp), out.shape[1]))
         self.ctx.sync()
         return out
 
@@ -203,15 +222,16 @@ class Plan:
         return buf.value.decode()
 
     def precompile(self, broadcast_slots: int = 0, arith: int = L.ARITH_FMA, with_sum: bool = False,
-                   store_out: bool = True) -> str:
-        L.check(L.lib.gaast_plan_precompile(self._h, broadcast_slots, arith, int(with_sum), int(store_out)))
+                   store_out: bool = True, dtype: int = L.F64) -> str:
+        L.check(L.lib.gaast_plan_precompile_typed(self._h, broadcast_slots, arith, int(with_sum), int(store_out),
+                                                  int(dtype)))
         return self.last_kernel()
 
     def last_kernel(self) -> str:
         return (L.lib.gaast_plan_last_kernel(self._h) or b"").decode()
 
-    def alloc_output(self, length: int) -> DeviceBatch:
-        return DeviceBatch.alloc(self.ctx, self.n, self.root_grades(), length)
+    def alloc_output(self, length: int, dtype: int = L.F64) -> DeviceBatch:
+        return DeviceBatch.alloc(self.ctx, self.n, self.root_grades(), length, dtype=dtype)
 
     def eval(self, inputs: Sequence[DeviceBatch], out: Optional[DeviceBatch] = None, engine: int = L.ENGINE_AUTO,
              arith: int = L.ARITH_FMA) -> DeviceBatch:
@@ -220,7 +240,7 @@ class Plan:
             raise L.GaastError(L.ERR_NO_DEVICE, "offline plan (created without a ctx): there is no CPU evaluation path")
         if out is None:
             length = next((b.length for b in inputs if not _is_broadcast(b)), 1)
-            out = self.alloc_output(length)
+            out = self.alloc_output(length, inputs[0].dtype if inputs else L.F64)
         arr = (L.vp * max(1, len(inputs)))(*[b._h for b in inputs])
         L.check(L.lib.gaast_eval(self._h, arr, len(inputs), out._h, engine, arith))
         return out

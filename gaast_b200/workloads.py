@@ -220,13 +220,18 @@ def precompile_all(verbose: bool = False, fresh: bool = True) -> int:
     count = 0
     for w in WORKLOADS.values():
         plan = Plan(None, specialize(w))
-        variants = [(L.ARITH_FMA, False, True), (L.ARITH_STRICT, False, True)]
+        variants = [(L.ARITH_FMA, False, True, L.F64), (L.ARITH_STRICT, False, True, L.F64)]
         if w.sum_root:
-            variants += [(L.ARITH_FMA, True, True), (L.ARITH_FMA, True, False)]
-        for arith, with_sum, store in variants:
-            info = plan.precompile(w.broadcast_mask(), arith, with_sum, store)
+            variants += [(L.ARITH_FMA, True, True, L.F64), (L.ARITH_FMA, True, False, L.F64)]
+        # the f32 variant of the same plans (bench.py --dtype f32, tests/test_gpu_f32.py)
+        variants += [(L.ARITH_FMA, False, True, L.F32), (L.ARITH_STRICT, False, True, L.F32)]
+        if w.sum_root:
+            variants += [(L.ARITH_FMA, True, True, L.F32)]
+        for arith, with_sum, store, dtype in variants:
+            info = plan.precompile(w.broadcast_mask(), arith, with_sum, store, dtype)
             count += 1
             if verbose:
-                print(f"  {w.name:10s} arith={'strict' if arith else 'fma':6s} sum={int(with_sum)} store={int(store)}: {info}")
+                print(f"  {w.name:10s} {'f32' if dtype else 'f64'} arith={'strict' if arith else 'fma':6s} sum={int(with_sum)} "
+                      f"store={int(store)}: {info}")
         plan.free()
     return count

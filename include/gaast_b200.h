@@ -131,6 +131,16 @@ typedef enum gaast_arith {
     GAAST_ARITH_STRICT = 1 /* (l*r)*coeff then add, reference order: bit-identical to eval.rs */
 } gaast_arith;
 
+/* Scalar type of a batch.  f64 is the reference's type (eval.rs works on f64 only) and the
+ * type every parity claim is made in.  f32 is this library's reduced-precision variant
+ * (SURVEY.md 8f rank 4): the same plans evaluated in IEEE binary32 -- half the HBM bytes.
+ * All batches of one gaast_eval call must share one dtype; plan literals and term
+ * coefficients are rounded to binary32; batch sums still accumulate in f64. */
+typedef enum gaast_dtype {
+    GAAST_F64 = 0,
+    GAAST_F32 = 1
+} gaast_dtype;
+
 /* Last error message of the calling thread (never NULL). */
 const char* gaast_last_error(void);
 /* Library version string, and the CUDA arch the embedded kernels were built for. */
@@ -166,6 +176,9 @@ size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int 
  * without a device (the plan may have been created with ctx == NULL).  Used
  * by the build step so that the shipped workloads never compile at run time. */
 gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, int store_out);
+/* The same for the kernels of a given gaast_dtype (gaast_plan_precompile = GAAST_F64). */
+gaast_status gaast_plan_precompile_typed(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, int store_out,
+                                         int dtype);
 /* Tuning knobs of the specialised engine: elements per thread (0 = choose,
  * 1, or 2 = 128-bit accesses) and emission-policy bits (0 = choose). */
 gaast_status gaast_plan_set_tuning(gaast_plan* plan, int elems_per_thread, int variant);
@@ -180,6 +193,13 @@ gaast_status gaast_batch_alloc(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, 
  * pointer per grade of the mask, ascending, each [C(n,k)][stride] f64. */
 gaast_status gaast_batch_wrap(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
                               int broadcast, void* const* grade_ptrs, gaast_batch** out);
+/* The same two constructors with an explicit scalar type (gaast_dtype); the arrays are then
+ * [C(n,k)][stride] of that type. */
+gaast_status gaast_batch_alloc_typed(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, int broadcast,
+                                     int dtype, gaast_batch** out);
+gaast_status gaast_batch_wrap_typed(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
+                                    int broadcast, int dtype, void* const* grade_ptrs, gaast_batch** out);
+int gaast_batch_dtype(const gaast_batch* b);
 gaast_status gaast_batch_free(gaast_batch* b);
 uint64_t gaast_batch_len(const gaast_batch* b);
 uint64_t gaast_batch_stride(const gaast_batch* b);
@@ -189,6 +209,9 @@ void* gaast_batch_grade_ptr(const gaast_batch* b, uint32_t grade);
 /* Stream-ordered copies of one grade: host array is [C(n,k)][host_stride]. */
 gaast_status gaast_batch_upload(gaast_batch* b, uint32_t grade, const double* host, uint64_t host_stride);
 gaast_status gaast_batch_download(const gaast_batch* b, uint32_t grade, double* host, uint64_t host_stride);
+/* The same copies for f32 batches (GAAST_ERR_SHAPE on a dtype mismatch, both ways). */
+gaast_status gaast_batch_upload_f32(gaast_batch* b, uint32_t grade, const float* host, uint64_t host_stride);
+gaast_status gaast_batch_download_f32(const gaast_batch* b, uint32_t grade, float* host, uint64_t host_stride);
 /* GradedDataMut::init_null_mv: zero every grade. */
 gaast_status gaast_batch_zero(gaast_batch* b);
 

@@ -17,6 +17,13 @@ import numpy as np
 from oracle import gaast_oracle as go
 
 REL_TOL = 1e-12  # north_star: "within 1e-12 relative error in f64"
+# The f32 variant (include/gaast_b200.h gaast_dtype; no reference definition: gaast is f64-only).
+# Its oracle is the reference's operation sequence replayed in IEEE binary32 (run_plan_numpy with
+# dtype=float32): GAAST_ARITH_STRICT must match it bit for bit.  The default FMA arithmetic, and the
+# f32 result against the f64 oracle on the same (binary32-representable) inputs, are held to
+# 1e-5 x max(|oracle|, sum of |terms|) per component: ~170 ulp(binary32), room for the longest
+# accumulation chains of the BASELINE workloads (64 terms per output in cfg3, three products deep in cfg5).
+REL_TOL_F32 = 1e-5
 
 
 def oracle_expr(build: Callable, inputs: Sequence[Dict[int, np.ndarray]], broadcast: Sequence[bool]):
@@ -80,8 +87,11 @@ def assert_close(got: Dict[int, np.ndarray], want: Dict[int, np.ndarray], scale:
 def assert_bit_exact(got: Dict[int, np.ndarray], want: Dict[int, np.ndarray], what: str = ""):
     assert sorted(got) == sorted(want), f"{what}: grade sets differ"
     for k in want:
-        g = np.ascontiguousarray(got[k], dtype=np.float64).view(np.uint64)
-        w = np.ascontiguousarray(want[k], dtype=np.float64).view(np.uint64)
+        assert np.asarray(got[k]).dtype == np.asarray(want[k]).dtype, f"{what}: grade {k}: scalar types differ"
+        bits = np.uint32 if np.asarray(want[k]).dtype == np.float32 else np.uint64
+        fl = np.float32 if bits is np.uint32 else np.float64
+        g = np.ascontiguousarray(got[k], dtype=fl).view(bits)
+        w = np.ascontiguousarray(want[k], dtype=fl).view(bits)
         # +0.0 and -0.0 compare equal in the reference's assert_eq! on f64
         same = (g == w) | ((np.asarray(got[k]) == 0.0) & (np.asarray(want[k]) == 0.0)) | \
             (np.isnan(got[k]) & np.isnan(want[k]))  # NaN payloads are not part of the contract
@@ -89,9 +99,12 @@ def assert_bit_exact(got: Dict[int, np.ndarray], want: Dict[int, np.ndarray], wh
 
 
 # ---- numpy executor of a lowered plan ---------------------------------------------
-def run_plan_numpy(plan: Dict, inputs: Sequence[Dict[int, np.ndarray]], batch: int) -> Dict[int, np.ndarray]:
+def run_plan_numpy(plan: Dict, inputs: Sequence[Dict[int, np.ndarray]], batch: int,
+                   dtype=np.float64) -> Dict[int, np.ndarray]:
     """Executes plan_dict() literally: zeroed buffers, ops in order, (l*r)*coeff
-    then + per term.  inputs[slot] = {grade: (C, B) or (C, 1)}."""
+    then + per term.  inputs[slot] = {grade: (C, B) or (C, 1)}.
+    dtype=np.float32 replays the same sequence in binary32 (inputs, literals and
+    coefficients rounded to binary32 first): the oracle of the f32 variant."""
     n = plan["n"]
     gd = [comb(n, k) for k in range(n + 1)]
 
@@ -101,8 +114,9 @@ def run_plan_numpy(plan: Dict, inputs: Sequence[Dict[int, np.ndarray]], batch: i
     def col0(mask, k):
         return sum(gd[j] for j in grades(mask) if j < k)
 
-    bufs = [np.zeros((sum(gd[k] for k in grades(m)), batch)) for m in plan["buffer_masks"]]
+    bufs = [np.zeros((sum(gd[k] for k in grades(m)), batch), dtype=dtype) for m in plan["buffer_masks"]]
     consts = plan["const_values"]
+    one = dtype(1.0)
     for kind, dst, a, b, mask, tb, tc in plan["ops"]:
         if kind == 0:  # ADD_INPUT
             ikind, imask, slot, coff = plan["inputs"][a]
@@ -111,16 +125,16 @@ def run_plan_numpy(plan: Dict, inputs: Sequence[Dict[int, np.ndarray]], batch: i
                 if mask >> k & 1:
                     c0 = col0(plan["buffer_masks"][dst], k)
                     if ikind == 0:
-                        src = np.asarray(inputs[slot][k])
+                        src = np.asarray(inputs[slot][k], dtype=dtype)
                         if src.ndim == 1:
                             src = src[:, None]
                     else:
-                        src = np.array(consts[off:off + gd[k]])[:, None]
+                        src = np.array(consts[off:off + gd[k]], dtype=dtype)[:, None]
                     bufs[dst][c0:c0 + gd[k]] = bufs[dst][c0:c0 + gd[k]] + src
                 off += gd[k]
         elif kind == 1:  # MUL_TERMS
             for out, ta, tbb, coeff in plan["terms"][tb:tb + tc]:
-                bufs[dst][out] = bufs[dst][out] + bufs[a][ta] * bufs[b][tbb] * coeff
+                bufs[dst][out] = bufs[dst][out] + bufs[a][ta] * bufs[b][tbb] * dtype(coeff)
         elif kind == 2:  # NEG_GRADES
             for k in grades(mask):
                 c0 = col0(plan["buffer_masks"][dst], k)
@@ -128,7 +142,7 @@ def run_plan_numpy(plan: Dict, inputs: Sequence[Dict[int, np.ndarray]], batch: i
         elif kind in (3, 4):
             c0 = col0(plan["buffer_masks"][dst], 0)
             with np.errstate(divide="ignore", invalid="ignore"):
-                bufs[dst][c0] = 1.0 / bufs[dst][c0] if kind == 3 else np.sqrt(bufs[dst][c0])
+                bufs[dst][c0] = one / bufs[dst][c0] if kind == 3 else np.sqrt(bufs[dst][c0])
     out, c = {}, 0
     for k in grades(plan["buffer_masks"][0]):
         out[k] = bufs[0][c:c + gd[k]]

@@ -163,3 +163,20 @@ def test_node_accessors_mirror_graded_node():
     assert sorted(uses) == [1, 1, 2]
     root = ast.get_node(ast.root_id())
     assert root.minimal_grade_set == 1 << 3 and root.kind == 1
+
+
+def test_f32_replay_tracks_the_f64_oracle():
+    """The oracle of the f32 variant (run_plan_numpy in binary32) against the f64 oracle on the
+    same binary32-representable inputs: within REL_TOL_F32 of max(|oracle|, sum |terms|)."""
+    from tests.helpers import REL_TOL_F32, assert_close, oracle_abs_scale
+    for name in sorted(W.WORKLOADS):
+        w = W.WORKLOADS[name]
+        B = 257
+        host = [{k: v.astype(np.float32) for k, v in d.items()} for d in W.host_inputs(w, B)]
+        as64 = [{k: v.astype(np.float64) for k, v in d.items()} for d in host]
+        bcs = [bc for _, bc in w.inputs]
+        got = run_plan_numpy(W.specialize(w).plan_dict(), host, B, dtype=np.float32)
+        assert all(v.dtype == np.float32 for v in got.values())
+        want = oracle_eval(w.build, w.metric, as64, bcs, B)
+        scale = oracle_abs_scale(w.build, w.metric, as64, bcs, B)
+        assert_close({k: v.astype(np.float64) for k, v in got.items()}, want, scale, rel=REL_TOL_F32, what=f"{name} f32 replay")
