@@ -1429,7 +1429,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     if (ept != 1 && ept != 2) ept = (live_loads + root_cols + widest <= (opt.f32 ? 96u : 48u)) ? 2 : 1;
     if (n_smem_rows) ept = 1;  // the staging area holds one double per row and thread
     g.ept = ept;
-    const int threads = 128;
+    const int threads = (opt.variant & 16384) ? 64 : 128;  // (tuning knob: 64-thread blocks = twice as many, half as large tiles per SM)
 
     CodegenResult res;
     res.kernel_name = "gaast_eval";
@@ -1600,6 +1600,28 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             g.emit_root(rs, id);   // ... everything else (leaves, sums, unary results) is stored here
         }
     }
+    if (tma_stage && (opt.variant & 256)) {  // parked row -> (stream, row), for the lanes that issue the copies
+        std::vector<const Node*> parked(size_t(n_smem_rows), nullptr);
+        for (const Node& n : g.nodes)
+            if (n.live && n.k == N_LOAD && !n.uniform && n.reload) parked[size_t(n.smem_row)] = &n;
+        g.file_scope << "__constant__ unsigned short kStageStream[" << n_smem_rows << "] = {";
+        for (int r = 0; r < n_smem_rows; ++r) g.file_scope << (r ? ", " : "") << parked[size_t(r)]->stream;
+        g.file_scope << "};\n__constant__ unsigned short kStageRow[" << n_smem_rows << "] = {";
+        for (int r = 0; r < n_smem_rows; ++r) g.file_scope << (r ? ", " : "") << parked[size_t(r)]->row;
+        g.file_scope << "};\n";
+        if (opt.variant & 32768) {
+            std::ostringstream ls, lr;
+            bool first = true;
+            for (const Node& n : g.nodes)
+                if (n.live && n.k == N_LOAD && !n.uniform) {
+                    ls << (first ? "" : ", ") << n.stream;
+                    lr << (first ? "" : ", ") << n.row;
+                    first = false;
+                }
+            g.file_scope << "__constant__ unsigned short kLoadStream[] = {" << ls.str() << "};\n__constant__ unsigned short kLoadRow[] = {"
+                         << lr.str() << "};\n";
+        }
+    }
     src << g.file_scope.str();
     if (tmem_sum) {  // accumulator k (emission order) -> root column
         src << "__device__ const short gaast_sum_col[" << root_cols << "] = {";
@@ -1726,6 +1748,19 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         src << "  const long long e0 = (long long)blockIdx.x * GAAST_THREADS;\n";
         src << "  if (tid == 0) { mbar_init(stage_bar, 1); fence_mbar_init(); }\n";
         src << "  __syncthreads();\n";
+        if (opt.variant & 256) {
+            // (opt-in) the 32 lanes of warp 0 issue the row copies side by side -- lane l takes rows
+            // l, l + 32, ... -- instead of thread 0 issuing all of them one after the other
+            src << "  if (tid < 32 && e0 < a.n) {\n";
+            src << "    const long long left = a.n - e0;\n";
+            src << "    const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * 8);\n";
+            src << "    fence_proxy_async();\n";
+            src << "    if (tid == 0) mbar_expect_tx(stage_bar, bytes * " << P << "u);\n";
+            src << "    for (int r = tid; r < " << P << "; r += 32)\n";
+            src << "      tma_row(stage0 + r * GAAST_THREADS, a.sptr[kStageStream[r]] + (long long)kStageRow[r] * "
+                   "a.srow[kStageStream[r]] + e0, bytes, stage_bar);\n";
+            src << "  }\n";
+        } else {
         src << "  if (tid == 0 && e0 < a.n) {\n";
         src << "    const long long left = a.n - e0;\n";
         src << "    const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * 8);\n";
@@ -1735,6 +1770,34 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             src << "    tma_row(stage0 + " << r << " * GAAST_THREADS, s" << parked[size_t(r)]->stream << " + "
                 << parked[size_t(r)]->row << " * r" << parked[size_t(r)]->stream << " + e0, bytes, stage_bar);\n";
         src << "  }\n";
+        }
+        if (opt.variant & 32768) {
+            // L2 look-ahead (opt-in): one lane of the second warp asks the L2 for the input rows of the
+            // tile that will run `a.lookahead` blocks later -- the block that takes this one's place on the
+            // SM -- so that its loads find their data on chip instead of paying an HBM round trip.
+            if (opt.variant & 256) {
+                size_t n_loads = 0;
+                for (const Node& n : g.nodes) n_loads += n.live && n.k == N_LOAD && !n.uniform;
+                src << "  if (tid >= 32 && tid < 64 && a.lookahead > 0) {\n";
+                src << "    const long long pe0 = e0 + (long long)a.lookahead * GAAST_THREADS;\n";
+                src << "    if (pe0 < a.n) {\n";
+                src << "      const long long left = a.n - pe0;\n";
+                src << "      const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * 8);\n";
+                src << "      for (int r = tid - 32; r < " << n_loads << "; r += 32)\n";
+                src << "        l2_prefetch_row(a.sptr[kLoadStream[r]] + (long long)kLoadRow[r] * a.srow[kLoadStream[r]] + pe0, bytes);\n";
+                src << "    }\n  }\n";
+            } else {
+            src << "  if (tid == 32 && a.lookahead > 0) {\n";
+            src << "    const long long pe0 = e0 + (long long)a.lookahead * GAAST_THREADS;\n";
+            src << "    if (pe0 < a.n) {\n";
+            src << "      const long long left = a.n - pe0;\n";
+            src << "      const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * 8);\n";
+            for (const Node& n : g.nodes)
+                if (n.live && n.k == N_LOAD && !n.uniform)
+                    src << "      l2_prefetch_row(s" << n.stream << " + " << n.row << " * r" << n.stream << " + pe0, bytes);\n";
+            src << "    }\n  }\n";
+            }
+        }
         src << "  const unsigned xb = (unsigned)__cvta_generic_to_shared(stage0 + tid);\n";
         if (g.dense_tmem) {
             // whole warps run the tcgen05 instructions: lanes past the end of the batch shadow the

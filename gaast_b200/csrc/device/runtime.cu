@@ -568,6 +568,8 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                        "launch uniform prologue");
             ctx->launches++;
         }
+        a.lookahead = ctx->sm_count * jk->blocks_per_sm;  // resident blocks: the look-ahead distance of the L2 prefetch variant
+        if (const char* e = std::getenv("GAAST_LOOKAHEAD")) a.lookahead = std::atoi(e);
         void* params[] = {&a};
         cuda_check(cudaLaunchKernel(reinterpret_cast<const void*>(jk->kernel), dim3(grid), dim3(jk->threads), params, jk->smem_bytes,
                                     ctx->stream),

@@ -33,7 +33,8 @@ struct EvalArgs {
     int n_sum_cols;
     int root_col;
     int store_out;
-    int pad0, pad1;
+    int lookahead;  // specialised one-tile kernels: number of resident blocks = distance of the L2 look-ahead
+    int pad1;
 };
 
 #ifdef __cplusplus
