@@ -45,7 +45,7 @@ NCU_TRAFFIC_BYTES = {
     "cfg2": 5318542000,            # profiles/r1_cfg2_final_ncu.txt at the BASELINE batch (algorithmic 5368709120)
     "cfg3": 6409480000 * 4,        # profiles/r1_cfg3_final_ncu.txt at 4M elements (algorithmic 6442450944 at 4M)
     "cfg4": 9169429000 * 2,        # profiles/r1_cfg4_final_ncu.txt at 4M elements (algorithmic 9227468800 at 4M)
-    "cfg5": 4792071000 * 8,        # profiles/r1_cfg5_final_ncu.txt at 4M elements (algorithmic 4831838208 at 4M)
+    "cfg5": 4792209000 * 8,        # profiles/r1_cfg5_final_ncu.txt at 4M elements (algorithmic 4831838208 at 4M)
 }
 
 
