@@ -929,7 +929,7 @@ struct Gen {
         // ---- lookup tables (constant memory) ----
         file_scope << "__constant__ unsigned kDenseB[" << B << "] = {";
         for (int b = 0; b < B; ++b)
-            file_scope << (b ? ", " : "") << size_t(nodes[d.right[b]].smem_row) * 8 << " * GAAST_THREADS";
+            file_scope << (b ? ", " : "") << size_t(nodes[d.right[b]].smem_row) * esize << " * GAAST_THREADS";
         file_scope << "};\n__constant__ unsigned short kDenseOutStream[" << B << "] = {";
         for (int o = 0; o < B; ++o) file_scope << (o ? ", " : "") << col_at[d.out_col[o]].first;
         file_scope << "};\n__constant__ unsigned short kDenseOutRow[" << B << "] = {";
@@ -941,13 +941,18 @@ struct Gen {
                 for (int oh = 0; oh < d.H; ++oh)
                     file_scope << ((ah || oh) ? ", " : "") << (d.sigma[ah * d.H + (oh ^ ah)] < 0 ? "0x80000000u" : "0u");
         } else {
-            file_scope << "__constant__ double kDenseSigma[" << d.H * d.H << "] = {";
+            file_scope << "__constant__ " << S << " kDenseSigma[" << d.H * d.H << "] = {";
             for (int ah = 0; ah < d.H; ++ah)
                 for (int oh = 0; oh < d.H; ++oh) file_scope << ((ah || oh) ? ", " : "") << lit(d.sigma[ah * d.H + (oh ^ ah)]);
         }
         file_scope << "};\n";
         // ---- per-block table of output offsets (the root's grade arrays are separate allocations) ----
         kernel_setup << "  long long* const dense_out = reinterpret_cast<long long*>(sums);\n";
+        if (f32)  // EvalArgs carries the array addresses as double*: measure the distance in floats
+            kernel_setup << "  if (tid < " << B << ")\n    dense_out[tid] = (long long)(reinterpret_cast<const float*>(a.sptr[kDenseOutStream[tid]]) - "
+                         << "reinterpret_cast<const float*>(a.sptr[" << root0
+                         << "])) + (long long)kDenseOutRow[tid] * a.srow[kDenseOutStream[tid]];\n  __syncthreads();\n";
+        else
         kernel_setup << "  if (tid < " << B << ")\n    dense_out[tid] = (long long)(a.sptr[kDenseOutStream[tid]] - a.sptr[" << root0
                      << "]) + (long long)kDenseOutRow[tid] * a.srow[kDenseOutStream[tid]];\n  __syncthreads();\n";
         if (dense_tmem) {
@@ -1005,20 +1010,20 @@ struct Gen {
         line("#pragma unroll 1");
         line("for (int oh = 0; oh < " + std::to_string(d.H) + "; ++oh) {");
         ++indent;
-        for (int ol = 0; ol < 16; ++ol) line("double q" + std::to_string(ol) + " = 0.0;");
+        for (int ol = 0; ol < 16; ++ol) line(S + " q" + std::to_string(ol) + " = 0.0;");
         for (int ah = 0; ah < d.H; ++ah) {
             line("{");
             ++indent;
             line("const unsigned* const rows = kDenseB + ((oh ^ " + std::to_string(ah) + ") << " + std::to_string(hb) + ");");
-            line((d.unit_sigma ? std::string("const unsigned sg = ") : std::string("const double sg = ")) + "kDenseSigma[" +
+            line((d.unit_sigma ? std::string("const unsigned sg = ") : "const " + S + " sg = ") + "kDenseSigma[" +
                  std::to_string(ah * d.H) + " + oh];");
             const bool odd = __builtin_popcount(ah) & 1;
             for (int bl = 0; bl < 16; ++bl) {
                 const std::string raw = "xs_ldd(xb + rows[" + std::to_string(bl) + "])";
                 if (d.unit_sigma)
-                    line("const double b" + std::to_string(bl) + " = flip_sign(" + raw + ", sg);");
+                    line("const " + S + " b" + std::to_string(bl) + " = flip_sign(" + raw + ", sg);");
                 else
-                    line("const double b" + std::to_string(bl) + " = " + raw + " * sg;");
+                    line("const " + S + " b" + std::to_string(bl) + " = " + raw + " * sg;");
             }
             for (int al = 0; al < 16; ++al)
                 for (int bl = 0; bl < 16; ++bl) {
@@ -1039,7 +1044,7 @@ struct Gen {
         }
         // ---- store the finished coset ----
         if (opt.store_out) {
-            line("double* const ro = s" + std::to_string(root0) + " + e;");
+            line(S + "* const ro = s" + std::to_string(root0) + " + e;");
             for (int ol = 0; ol < 16; ++ol)
                 line("ro[dense_out[(oh << " + std::to_string(hb) + ") + " +
                      std::to_string(ol) + "]] = q" + std::to_string(ol) + ";");
@@ -1264,9 +1269,22 @@ __device__ __forceinline__ float xs_ld(unsigned base) {
   asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(base), "n"(OFF));
   return v;
 }
+__device__ __forceinline__ float xs_ldd(unsigned addr) {
+  float v;
+  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float flip_sign(float v, unsigned mask) { return __uint_as_float(__float_as_uint(v) ^ mask); }
 )GAAST";
 
-const char kPreludeF32Tail[] = R"GAAST(__device__ __forceinline__ void d_store(float* p, D v) { *p = v; }
+const char kPreludeF32Tail[] = R"GAAST(__device__ __forceinline__ void tma_row(float* dst, const float* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_row(const float* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void d_store(float* p, D v) { *p = v; }
 __device__ __forceinline__ double d_hsum(D a) { return (double)a; }
 #endif
 __device__ __forceinline__ float d_neg(float a) { return -a; }
@@ -1330,7 +1348,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     size_t widest = 0;
     int res_parked = 0, res_parkable = 0;
     size_t live_estimate = 0;  // doubles a thread keeps live (widest in-register product + resident rows)
-    const size_t kDenseBudget = opt.f32 ? 200 : 110;  // values: outputs + operands of a product that may all be live
+    const size_t kDenseBudget = opt.f32 ? 160 : 110;  // values: outputs + operands of a product that may all be live
     const size_t kLiveBudget = opt.f32 ? 224 : 124;   // values a thread can hold in 255 registers next to addresses
     std::vector<int> uses(g.nodes.size(), 0);  // how many live product terms read each node
     std::set<int> blocked_loads;
@@ -1358,7 +1376,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         if (dense && outs.size() <= 144) pol = P_BLOCKED;  // (up to 2 x the f64 accumulator budget)
         if (opt.variant & 1) pol = P_TABLE;
         if (opt.variant & 2) pol = P_GATHER;
-        if (pol == P_BLOCKED && !opt.with_sum && !opt.pipelined && !(opt.variant & 512) && g.dense.op < 0 && !opt.f32) {
+        if (pol == P_BLOCKED && !opt.with_sum && !opt.pipelined && !(opt.variant & 512) && g.dense.op < 0) {
             std::vector<int> refcount(g.nodes.size(), 0);
             for (const Node& n : g.nodes) {
                 if (!n.live) continue;
@@ -1462,8 +1480,10 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     // with a few dozen parked rows next to register rows, LDG + STS is as fast (cfg5: 0.83 vs 0.80)
     bool has_dense = false;
     for (Policy p : g.op_policy) has_dense |= p == P_DENSE || p == P_BLOCKED;
-    const bool tma_stage = opt.tma_stage && has_dense && n_smem_rows > 0 && ept == 1 && !pipelined && !opt.with_sum && !opt.f32;
-    g.dense_tmem = tma_stage && g.dense.op >= 0 && (opt.variant & 8192);
+    const bool tma_stage = opt.tma_stage && has_dense && n_smem_rows > 0 && ept == 1 && !pipelined && !opt.with_sum;
+    const bool par_issue = (opt.variant & 256) && !opt.f32;     // opt-in experiments (f64 only), see DESIGN.md
+    const bool look_ahead = (opt.variant & 32768) && !opt.f32;
+    g.dense_tmem = tma_stage && g.dense.op >= 0 && (opt.variant & 8192) && !opt.f32;
     g.pipelined = pipelined;
     g.guard_stores = pipelined || tmem_sum || g.dense_tmem;
     g.sum_in_smem = opt.with_sum && !tmem_sum;
@@ -1486,7 +1506,10 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     // trade occupancy for hoisting (cfg2_full: 254 registers without this, 2 blocks per SM).
     const size_t live_regs = live_estimate * size_t(ept);
     // (ptxas treats the hint as a register budget to spend: only give it when it is a tight one)
-    const int min_blocks = g.dense_tmem ? 3 : live_regs <= (opt.f32 ? 80u : 40u) ? 8 : live_regs <= (opt.f32 ? 128u : 64u) ? 4 : 1;
+    // (rolled dense product in f32: 64 left components + a 16 x 16 tile = ~110 registers, 4 blocks per SM)
+    const int min_blocks = g.dense_tmem ? 3
+                           : g.dense.op >= 0 ? (opt.f32 ? 4 : 1)
+                           : live_regs <= (opt.f32 ? 80u : 40u) ? 8 : live_regs <= (opt.f32 ? 128u : 64u) ? 4 : 1;
     res.min_blocks = min_blocks;
     src << "#define GAAST_EPT " << ept << "\n#define GAAST_THREADS " << threads << "\n#define GAAST_MIN_BLOCKS "
         << min_blocks << "\n";
@@ -1600,7 +1623,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             g.emit_root(rs, id);   // ... everything else (leaves, sums, unary results) is stored here
         }
     }
-    if (tma_stage && (opt.variant & 256)) {  // parked row -> (stream, row), for the lanes that issue the copies
+    if (tma_stage && par_issue) {  // parked row -> (stream, row), for the lanes that issue the copies
         std::vector<const Node*> parked(size_t(n_smem_rows), nullptr);
         for (const Node& n : g.nodes)
             if (n.live && n.k == N_LOAD && !n.uniform && n.reload) parked[size_t(n.smem_row)] = &n;
@@ -1609,7 +1632,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         g.file_scope << "};\n__constant__ unsigned short kStageRow[" << n_smem_rows << "] = {";
         for (int r = 0; r < n_smem_rows; ++r) g.file_scope << (r ? ", " : "") << parked[size_t(r)]->row;
         g.file_scope << "};\n";
-        if (opt.variant & 32768) {
+        if (look_ahead) {
             std::ostringstream ls, lr;
             bool first = true;
             for (const Node& n : g.nodes)
@@ -1742,18 +1765,19 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         std::vector<const Node*> parked(size_t(P), nullptr);
         for (const Node& n : g.nodes)
             if (n.live && n.k == N_LOAD && !n.uniform && n.reload) parked[size_t(n.smem_row)] = &n;
-        src << "  double* const stage0 = sums + " << sum_doubles << ";\n";
+        if (opt.f32) src << "  float* const stage0 = reinterpret_cast<float*>(sums + " << sum_doubles << ");\n";
+        else src << "  double* const stage0 = sums + " << sum_doubles << ";\n";
         src << "  unsigned long long* const stage_bar = reinterpret_cast<unsigned long long*>(stage0 + " << P
             << " * GAAST_THREADS);\n";
         src << "  const long long e0 = (long long)blockIdx.x * GAAST_THREADS;\n";
         src << "  if (tid == 0) { mbar_init(stage_bar, 1); fence_mbar_init(); }\n";
         src << "  __syncthreads();\n";
-        if (opt.variant & 256) {
+        if (par_issue) {
             // (opt-in) the 32 lanes of warp 0 issue the row copies side by side -- lane l takes rows
             // l, l + 32, ... -- instead of thread 0 issuing all of them one after the other
             src << "  if (tid < 32 && e0 < a.n) {\n";
             src << "    const long long left = a.n - e0;\n";
-            src << "    const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * 8);\n";
+            src << "    const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * " << g.esize << ");\n";
             src << "    fence_proxy_async();\n";
             src << "    if (tid == 0) mbar_expect_tx(stage_bar, bytes * " << P << "u);\n";
             src << "    for (int r = tid; r < " << P << "; r += 32)\n";
@@ -1763,7 +1787,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         } else {
         src << "  if (tid == 0 && e0 < a.n) {\n";
         src << "    const long long left = a.n - e0;\n";
-        src << "    const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * 8);\n";
+        src << "    const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * " << g.esize << ");\n";
         src << "    fence_proxy_async();\n";
         src << "    mbar_expect_tx(stage_bar, bytes * " << P << "u);\n";
         for (int r = 0; r < P; ++r)
@@ -1771,18 +1795,18 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
                 << parked[size_t(r)]->row << " * r" << parked[size_t(r)]->stream << " + e0, bytes, stage_bar);\n";
         src << "  }\n";
         }
-        if (opt.variant & 32768) {
+        if (look_ahead) {
             // L2 look-ahead (opt-in): one lane of the second warp asks the L2 for the input rows of the
             // tile that will run `a.lookahead` blocks later -- the block that takes this one's place on the
             // SM -- so that its loads find their data on chip instead of paying an HBM round trip.
-            if (opt.variant & 256) {
+            if (par_issue) {
                 size_t n_loads = 0;
                 for (const Node& n : g.nodes) n_loads += n.live && n.k == N_LOAD && !n.uniform;
                 src << "  if (tid >= 32 && tid < 64 && a.lookahead > 0) {\n";
                 src << "    const long long pe0 = e0 + (long long)a.lookahead * GAAST_THREADS;\n";
                 src << "    if (pe0 < a.n) {\n";
                 src << "      const long long left = a.n - pe0;\n";
-                src << "      const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * 8);\n";
+                src << "      const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * " << g.esize << ");\n";
                 src << "      for (int r = tid - 32; r < " << n_loads << "; r += 32)\n";
                 src << "        l2_prefetch_row(a.sptr[kLoadStream[r]] + (long long)kLoadRow[r] * a.srow[kLoadStream[r]] + pe0, bytes);\n";
                 src << "    }\n  }\n";
@@ -1791,7 +1815,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             src << "    const long long pe0 = e0 + (long long)a.lookahead * GAAST_THREADS;\n";
             src << "    if (pe0 < a.n) {\n";
             src << "      const long long left = a.n - pe0;\n";
-            src << "      const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * 8);\n";
+            src << "      const unsigned bytes = (unsigned)((left < GAAST_THREADS ? left : GAAST_THREADS) * " << g.esize << ");\n";
             for (const Node& n : g.nodes)
                 if (n.live && n.k == N_LOAD && !n.uniform)
                     src << "      l2_prefetch_row(s" << n.stream << " + " << n.row << " * r" << n.stream << " + pe0, bytes);\n";

@@ -520,11 +520,12 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                 opt.variant = plan->variant;
                 opt.f32 = f32;
                 // 128-bit accesses need even strides and 16-byte aligned rows
-                bool aligned = (n % 2 == 0);
+                const long long quantum = f32 ? 4 : 2;  // elements per 16 bytes
+                bool aligned = (n % quantum == 0);
                 for (size_t i = 0; i < h.streams.size(); ++i) {
                     const bool bc = (a.bcast[i >> 6] >> (i & 63)) & 1;
                     if (bc || !a.sptr[i]) continue;
-                    if ((a.srow[i] & 1) || (reinterpret_cast<uintptr_t>(a.sptr[i]) & 15)) aligned = false;
+                    if ((a.srow[i] % quantum) || (reinterpret_cast<uintptr_t>(a.sptr[i]) & 15)) aligned = false;
                 }
                 if (!aligned) opt.elems_per_thread = 1;
                 // TMA-pipelined staging is opt-in (variant bit 3): measured slower than plain blocks on cfg3 / cfg5

@@ -122,3 +122,23 @@ def test_f32_dtype_errors_and_wrap(ctx):
     torch.cuda.synchronize()
     want = run_plan_numpy(W.specialize(w).plan_dict(), host, 1000, dtype=np.float32)
     assert_bit_exact({2: out_t[2].cpu().numpy()}, want, "wrapped f32 tensors")
+
+
+def test_f32_wide_plan_table_engine_global_workspace(ctx):
+    """G(10,0) full product in f32: 1 048 576 terms, 3 072 workspace columns (393 KB per tile even
+    at 4 bytes): the table engine runs with its workspace in global memory, bit-exact."""
+    from math import comb
+    from gaast_b200.expr import Input, mv as pmv
+    n = 10
+    full = tuple(range(n + 1))
+    batch = 9
+    rng = np.random.default_rng(12)
+    host = [{k: rng.uniform(-1, 1, (comb(n, k), batch)).astype(np.float32) for k in full} for _ in range(2)]
+    ast = (pmv(Input(0, full)) * pmv(Input(1, full))).specialize([1.0] * n)
+    want = run_plan_numpy(ast.plan_dict(), host, batch, dtype=np.float32)
+    plan = g.Plan(ctx, ast)
+    dev = [g.DeviceBatch.from_host(ctx, n, h, dtype=L.F32) for h in host]
+    out = plan.eval(dev, engine=L.ENGINE_AUTO, arith=L.ARITH_STRICT)
+    ctx.sync()
+    assert "engine=table" in plan.last_kernel() and "ws=global" in plan.last_kernel()
+    assert_bit_exact(out.to_host(), want, "G(10) full product in f32, table engine, global workspace")
