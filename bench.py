@@ -26,6 +26,25 @@ if ROOT not in sys.path:
 METRIC = "multivector_products_per_sec"
 UNIT = "products/s"
 
+# stdout carries exactly ONE line, the JSON record.  Libraries print there too (NCCL announces its
+# version on stdout when the process group starts): file descriptor 1 is pointed at stderr for the
+# whole run and the record is written to the original stdout at the end.
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -160,7 +179,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------ GPU arm ----
@@ -405,7 +424,7 @@ def run_gpu(args):
         line["other_workloads"] = others
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -431,6 +450,7 @@ def main():
     ap.add_argument("--all", action="store_true", default=True, help="also time the other BASELINE workloads (N=1)")
     ap.add_argument("--only", dest="all", action="store_false")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
