@@ -157,3 +157,25 @@ def test_random_expression_gpu(seed):
         out = plan.eval(dev, engine=engine, arith=L.ARITH_STRICT)
         ctx.sync()
         assert_bit_exact(out.to_host(), want, f"seed {seed} engine {engine}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", SEEDS[:40])
+def test_random_expression_gpu_f32(seed):
+    """The same random trees in the f32 variant: both engines bit-exact (strict arithmetic)
+    against the plan replayed in binary32 (tests/helpers.run_plan_numpy, dtype=float32).
+    NaN / inf results (sqrt of a negative norm, 1/0) must agree as such."""
+    n, metric, slots, inputs, want, ast, oracle_error, mine_error = evaluate_case(seed)
+    if oracle_error is not None or ast is None:
+        pytest.skip("the reference rejects this expression")
+    inputs32 = [{k: v.astype(np.float32) for k, v in d.items()} for d in inputs]
+    with np.errstate(all="ignore"):
+        want32 = run_plan_numpy(ast.plan_dict(), inputs32, BATCH, dtype=np.float32)
+    ctx = g.Ctx(0)
+    plan = g.Plan(ctx, ast)
+    dev = [g.DeviceBatch.from_host(ctx, n, inputs32[s], broadcast=bc, dtype=L.F32) for s, (_, bc) in enumerate(slots)]
+    dev = dev[:plan.num_slots()]
+    for engine in (L.ENGINE_TABLE, L.ENGINE_SPECIALIZED):
+        out = plan.eval(dev, engine=engine, arith=L.ARITH_STRICT)
+        ctx.sync()
+        assert_bit_exact(out.to_host(), want32, f"seed {seed} engine {engine} f32")
