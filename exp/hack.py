@@ -22,6 +22,42 @@ elif tf == "no_tmem_no_guard":
     out = [l.replace("if (active) ", "") for l in body_only(lambda l: re.match(r"\s+(tm_put\(tb \+ \d+u, d_hsum|tm_add\(|tm_acc\d+<)", l))]
 elif tf == "no_stash_absorb":  # keep stash writes, drop tile-end absorption
     out = body_only(lambda l: re.match(r"\s+(tm_acc\d+<)", l))
+elif tf == "c3_no_loads":   # cfg3: no TMA copies, no waits, no global loads (compute + stores only)
+    out = []
+    for l in lines:
+        if re.match(r"\s+tma_row\(", l) or "mbar_expect_tx(stage_bar" in l or "mbar_wait(stage_bar" in l:
+            continue
+        m = re.match(r"(\s+const D v(\d+) = )d_load\(.*\);", l)
+        if m:
+            l = f"{m.group(1)}__longlong_as_double(e + {m.group(2)}LL) * 1e-300;"
+        out.append(l)
+elif tf == "c3_no_stores":  # cfg3: one store per output coset instead of 16
+    out = []
+    for l in lines:
+        m = re.match(r"(\s+)ro\[dense_out\[\(oh << 4\) \+ (\d+)\]\] = q(\d+);", l)
+        if m:
+            if m.group(2) == "0":
+                l = m.group(1) + "ro[dense_out[(oh << 4)]] = " + " + ".join(f"q{i}" for i in range(16)) + ";"
+            else:
+                continue
+        out.append(l)
+elif tf == "c3_no_sign":    # cfg3: right operand used as loaded (no per-tile sign flip)
+    out = [re.sub(r"flip_sign\((xs_ldd\([^)]*\)\)), sg\)", r"\1", l) for l in lines]
+elif tf == "c3_compute_only":
+    out = []
+    for l in lines:
+        if re.match(r"\s+tma_row\(", l) or "mbar_expect_tx(stage_bar" in l or "mbar_wait(stage_bar" in l:
+            continue
+        m = re.match(r"(\s+const D v(\d+) = )d_load\(.*\);", l)
+        if m:
+            l = f"{m.group(1)}__longlong_as_double(e + {m.group(2)}LL) * 1e-300;"
+        m = re.match(r"(\s+)ro\[dense_out\[\(oh << 4\) \+ (\d+)\]\] = q(\d+);", l)
+        if m:
+            if m.group(2) == "0":
+                l = m.group(1) + "ro[dense_out[(oh << 4)]] = " + " + ".join(f"q{i}" for i in range(16)) + ";"
+            else:
+                continue
+        out.append(l)
 else:
     raise SystemExit("unknown transform")
 d = os.path.join(ROOT, "exp", name)

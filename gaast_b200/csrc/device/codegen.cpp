@@ -848,6 +848,7 @@ struct Gen {
     } dense;
     std::ostringstream file_scope, kernel_setup;
     bool dense_tmem = false;  // DENSE: left operand parked in tensor memory (3 blocks per SM instead of 2)
+    bool dense_by_blade = false;  // DENSE: shared-memory row of a right-operand component = its blade index
     size_t setup_doubles = 0;  // shared memory reserved ahead of the sums / staging areas
 
     bool plan_dense(int op, const std::vector<int>& refcount) {
@@ -1014,12 +1015,17 @@ struct Gen {
         for (int ah = 0; ah < d.H; ++ah) {
             line("{");
             ++indent;
+            if (dense_by_blade)
+                line("const unsigned xr = xb + (unsigned)((oh ^ " + std::to_string(ah) + ") << " + std::to_string(hb) + ") * (unsigned)(" +
+                     std::to_string(esize) + " * GAAST_THREADS);");
+            else
             line("const unsigned* const rows = kDenseB + ((oh ^ " + std::to_string(ah) + ") << " + std::to_string(hb) + ");");
             line((d.unit_sigma ? std::string("const unsigned sg = ") : "const " + S + " sg = ") + "kDenseSigma[" +
                  std::to_string(ah * d.H) + " + oh];");
             const bool odd = __builtin_popcount(ah) & 1;
             for (int bl = 0; bl < 16; ++bl) {
-                const std::string raw = "xs_ldd(xb + rows[" + std::to_string(bl) + "])";
+                const std::string raw = dense_by_blade ? "xs_ld<" + std::to_string(size_t(bl) * esize) + " * GAAST_THREADS>(xr)"
+                                                       : "xs_ldd(xb + rows[" + std::to_string(bl) + "])";
                 if (d.unit_sigma)
                     line("const " + S + " b" + std::to_string(bl) + " = flip_sign(" + raw + ", sg);");
                 else
@@ -1443,6 +1449,22 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     int n_smem_rows = 0;
     for (Node& n : g.nodes)
         if (n.live && n.k == N_LOAD && n.reload && !n.uniform) n.smem_row = n_smem_rows++;
+    // Rolled dense product: the right operand's rows are laid out by blade (row = blade index), so that
+    // a tile's 16 values sit at compile-time offsets from ONE base address (coset * 16 rows) instead
+    // of being looked up row by row in a constant table (GAAST_DENSE_TABLE_ROWS=1 keeps the table: A/B runs).
+    g.dense_by_blade = false;
+    if (g.dense.op >= 0) {
+        bool only_right = true;
+        std::set<int> right(g.dense.right.begin(), g.dense.right.end());
+        for (size_t id = 0; id < g.nodes.size(); ++id) {
+            const Node& n = g.nodes[id];
+            if (n.live && n.k == N_LOAD && n.reload && !n.uniform && !right.count(int(id))) only_right = false;
+        }
+        if (only_right && int(right.size()) == n_smem_rows && !std::getenv("GAAST_DENSE_TABLE_ROWS")) {
+            for (size_t b = 0; b < g.dense.right.size(); ++b) g.nodes[g.dense.right[b]].smem_row = int(b);
+            g.dense_by_blade = true;
+        }
+    }
     int ept = opt.elems_per_thread;
     if (ept != 1 && ept != 2) ept = (live_loads + root_cols + widest <= (opt.f32 ? 96u : 48u)) ? 2 : 1;
     if (n_smem_rows) ept = 1;  // the staging area holds one double per row and thread
