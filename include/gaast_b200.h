@@ -158,7 +158,7 @@ uint64_t gaast_ctx_launch_count(gaast_ctx* ctx);
  * ctx may be NULL for an offline plan (kernel_source / precompile only). */
 gaast_status gaast_plan_create(gaast_ctx* ctx, const gaast_plan_desc* desc, gaast_plan** out);
 gaast_status gaast_plan_destroy(gaast_plan* plan);
-/* Algorithmic bytes and flops per batch element: 8 x (f64 read
+/* Algorithmic bytes and flops per batch element, for f64 batches (f32: half the bytes): 8 x (f64 read
  * from non-broadcast inputs in the grades the plan reads + f64 written in the
  * root grades) and 2 x terms.  `broadcast_slots` bit s = slot s is broadcast. */
 gaast_status gaast_plan_cost(const gaast_plan* plan, uint64_t broadcast_slots, uint64_t* bytes_per_elem,
