@@ -215,14 +215,21 @@ def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=
     sums = torch.zeros(_root_cols(plan, w), dtype=torch.float64, device=dev)
     eng = L.ENGINE_AUTO if engine is None else engine
     counter = [0]
+    comm = None
+    if use_sum and world > 1:
+        # the path's one collective goes through the library's own communicator (gaast_comm, NCCL behind
+        # the C ABI); torch.distributed only ships the 128-byte id and provides the barrier
+        uid = [g.Comm.unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = g.Comm.join(ctx, world, dist.get_rank(), uid[0])
 
     def step():
         _, s_in, s_out = sets[counter[0] % n_sets]
         counter[0] += 1
         if use_sum:
             plan.eval_sum(s_in, sums.data_ptr(), out=s_out, engine=eng)
-            if world > 1:
-                dist.all_reduce(sums)  # the only collective of the path: 66 doubles
+            if comm is not None:
+                comm.allreduce_sum([sums.data_ptr()], sums.numel())  # the only collective of the path: 66 doubles
         else:
             plan.eval(s_in, out=s_out, engine=eng)
 
@@ -257,7 +264,7 @@ def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count - launches0 + (steps if (use_sum and world > 1) else 0)
+    launches = ctx.launch_count - launches0  # this library's kernels only (NCCL's all-reduce kernel is not counted)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -268,7 +275,7 @@ def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=
     res = {
         "ms_per_step": ms / steps, "elements": n, "bytes_per_elem": bytes_per_elem, "flops_per_elem": flops_per_elem,
         "launches": launches, "kernel": plan.last_kernel(), "plan": plan, "ins": ins, "out": out, "tin": tin,
-        "n_sets": n_sets, "cuda_graph": bool(use_graph),
+        "n_sets": n_sets, "cuda_graph": bool(use_graph), "comm": comm,
     }
     return res
 
@@ -355,7 +362,7 @@ def run_gpu(args):
         "config": {"workload": f"{w.name}: {w.title}" + (" [f32 variant: not the reference's precision]" if args.dtype == "f32" else ""),
                    "batch_per_gpu": n, "elements_per_s": elems_per_s,
                    "products_per_element": w.products, "parallelism": f"batch-sharded x{world}, no data-path collective"
-                   + (" (+66-double NCCL all-reduce for the batch-sum)" if w.sum_root and world > 1 else ""),
+                   + (" (+66-double NCCL all-reduce for the batch-sum, gaast_comm_allreduce_sum)" if w.sum_root and world > 1 else ""),
                    "l2": f"inputs+outputs {n * res['bytes_per_elem'] / 1e9:.2f} GB per step (126 MB L2), "
                          f"{res['n_sets']} input/output set(s) used in rotation",
                    "kernel": res["kernel"], "cuda_graph": res["cuda_graph"]},

@@ -11,7 +11,8 @@ import importlib
 _EXPORTS = {
     "ARITH_FMA": "_lib", "ARITH_STRICT": "_lib", "ENGINE_AUTO": "_lib", "ENGINE_SPECIALIZED": "_lib",
     "ENGINE_TABLE": "_lib", "GaastError": "_lib",
-    "Ctx": "device", "DeviceBatch": "device", "Plan": "device",
+    "F32": "_lib", "F64": "_lib",
+    "Comm": "device", "Ctx": "device", "DeviceBatch": "device", "Plan": "device",
     "Expr": "expr", "Input": "expr", "OrthoEuclidN": "expr", "SpecializedAst": "expr", "mv": "expr",
 }
 

@@ -32,6 +32,7 @@ SOURCES = [
     "host/host_capi.cpp",
     "device/codegen.cpp",
     "device/jit.cpp",
+    "device/comm.cpp",
     "device/table_engine.cu",
     "device/runtime.cu",
     "device/host_pipeline.cu",

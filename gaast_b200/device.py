@@ -275,6 +275,54 @@ class Plan:
             pass
 
 
+class Comm:
+    """gaast_comm: the all-reduce of batch-sum vectors across the GPUs of one node (NCCL behind the
+    C ABI).  `Comm(ctxs)` = one process driving several devices; `Comm.join(ctx, n, rank, id)` =
+    one process per device, `Comm.unique_id()` drawn on rank 0 and shipped by the caller."""
+
+    def __init__(self, ctxs: Sequence[Ctx], _handle=None):
+        self.ctxs = list(ctxs)
+        if _handle is None:
+            arr = (L.vp * len(self.ctxs))(*[c._h for c in self.ctxs])
+            out = L.vp()
+            L.check(L.lib.gaast_comm_create(arr, len(self.ctxs), C.byref(out)))
+            _handle = out
+        self._h = _handle
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        L.check(L.lib.gaast_comm_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def join(ctx: Ctx, n_ranks: int, rank: int, uid: bytes) -> "Comm":
+        out = L.vp()
+        L.check(L.lib.gaast_comm_create_rank(ctx._h, int(n_ranks), int(rank), uid, C.byref(out)))
+        return Comm([ctx], _handle=out)
+
+    @property
+    def size(self) -> int:
+        return L.lib.gaast_comm_size(self._h)
+
+    def allreduce_sum(self, dev_ptrs: Sequence[int], count: int):
+        """In place on every local device: dev_ptrs[i] -> `count` doubles on self.ctxs[i]'s device."""
+        assert len(dev_ptrs) == len(self.ctxs)
+        arr = (L.vp * len(dev_ptrs))(*[L.vp(p) for p in dev_ptrs])
+        L.check(L.lib.gaast_comm_allreduce_sum(self._h, arr, int(count)))
+
+    def close(self):
+        h, self._h = self._h, None
+        if h:
+            L.lib.gaast_comm_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _is_broadcast(b: DeviceBatch) -> bool:
     return False if b.length != 1 else True
 

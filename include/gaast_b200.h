@@ -240,6 +240,29 @@ gaast_status gaast_eval_host(gaast_plan* plan, const double* const* host_in, con
                              const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
                              double* host_out, int engine, int arith);
 
+/* ------------------------------------------------------------------ comm --
+ * Multi-GPU: batch elements are independent, so a batch is sharded into
+ * contiguous slices, one per device, and every device evaluates its slice with its own ctx /
+ * plan / batches -- no communication.  The ONE collective of the path is the all-reduce of the
+ * batch-sum vector gaast_eval_sum leaves on each device (66 doubles for the G(8,4) workload).
+ * NCCL (over NVLink / NVSwitch) is loaded with dlopen("libnccl.so.2"): GAAST_ERR_UNSUPPORTED if
+ * it is not installed.  gaast has no counterpart (it is single-threaded and batch-less). */
+typedef struct gaast_comm gaast_comm;
+#define GAAST_COMM_ID_BYTES 128u
+/* One process driving n devices of one node: ctxs[i] is rank i (ncclCommInitAll). */
+gaast_status gaast_comm_create(gaast_ctx* const* ctxs, uint32_t n, gaast_comm** out);
+/* One process per device: rank 0 draws an id (GAAST_COMM_ID_BYTES bytes), the caller ships it to
+ * the other processes by its own means, every process then joins with its ctx and rank. */
+gaast_status gaast_comm_unique_id(unsigned char* id);
+gaast_status gaast_comm_create_rank(gaast_ctx* ctx, uint32_t n_ranks, uint32_t rank, const unsigned char* id,
+                                    gaast_comm** out);
+uint32_t gaast_comm_size(const gaast_comm* comm);
+/* In place: dev_sums[i] addresses `count` doubles on the i-th LOCAL device of the communicator (all
+ * of them after gaast_comm_create, exactly one after gaast_comm_create_rank); afterwards every
+ * device holds the element-wise total over all ranks.  Ordered on each ctx's stream, asynchronous. */
+gaast_status gaast_comm_allreduce_sum(gaast_comm* comm, double* const* dev_sums, size_t count);
+gaast_status gaast_comm_destroy(gaast_comm* comm);
+
 /* Name and launch shape of the kernel the last gaast_eval on this plan used. */
 const char* gaast_plan_last_kernel(const gaast_plan* plan);
 

@@ -1,0 +1,68 @@
+"""gaast_comm (include/gaast_b200.h): the batch-sum all-reduce behind the C ABI (NCCL found with
+dlopen).  The single-GPU cases run everywhere; the sharded evaluation over two devices runs when
+the box has two (gpurun --gpus 2)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import gaast_b200 as g  # noqa: E402
+from gaast_b200 import _lib as L  # noqa: E402
+from gaast_b200 import workloads as W  # noqa: E402
+from gaast_b200.dist import shard_range  # noqa: E402
+from tests.helpers import oracle_eval  # noqa: E402
+
+
+def test_comm_single_rank_is_identity():
+    import torch
+    ctx = g.Ctx.on_torch_stream(0)
+    for comm in (g.Comm([ctx]), g.Comm.join(ctx, 1, 0, g.Comm.unique_id())):
+        assert comm.size == 1
+        x = torch.arange(66, dtype=torch.float64, device="cuda:0") * 0.5
+        torch.cuda.synchronize()
+        comm.allreduce_sum([x.data_ptr()], 66)
+        ctx.sync()
+        assert torch.equal(x.cpu(), torch.arange(66, dtype=torch.float64) * 0.5)
+        comm.close()
+    with pytest.raises(g.GaastError):
+        g.Comm([ctx, ctx])  # the same device twice
+
+
+def test_comm_sharded_batch_sum_two_devices():
+    """cfg5 (G(8,4) versor sandwich + batch-sum) sharded over two GPUs driven by ONE process: each
+    device evaluates its contiguous slice, the 66-double sums meet in gaast_comm_allreduce_sum."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w = W.WORKLOADS["cfg5"]
+    batch = 6000 + 38
+    host = W.host_inputs(w, batch)
+    bcs = [bc for _, bc in w.inputs]
+    want = oracle_eval(w.build, w.metric, host, bcs, batch)[2]
+    ctxs = [g.Ctx(d) for d in range(2)]
+    comm = g.Comm(ctxs)
+    assert comm.size == 2
+    sums, outs = [], []
+    for r, ctx in enumerate(ctxs):
+        b0, b1 = shard_range(batch, r, 2)
+        plan = g.Plan(ctx, W.specialize(w))
+        dev = [g.DeviceBatch.from_host(ctx, w.n, {k: (v if bc else v[:, b0:b1]) for k, v in host[s].items()}, broadcast=bc)
+               for s, bc in enumerate(bcs)]
+        out = plan.alloc_output(b1 - b0)
+        s = torch.zeros(66, dtype=torch.float64, device=f"cuda:{r}")
+        torch.cuda.synchronize(r)  # the fill runs on torch's stream, the evaluation on the ctx's
+        plan.eval_sum(dev, s.data_ptr(), out=out)
+        sums.append(s)
+        outs.append((plan, dev, out, b0, b1))
+    comm.allreduce_sum([s.data_ptr() for s in sums], 66)
+    for ctx in ctxs:
+        ctx.sync()
+    ref = want.sum(axis=1)
+    mag = np.abs(want).sum(axis=1)
+    for r in range(2):
+        got = sums[r].cpu().numpy()
+        assert np.all(np.abs(got - ref) <= 1e-12 * mag), f"rank {r}"
+    assert torch.equal(sums[0].cpu(), sums[1].cpu())  # every rank holds the same total
+    for plan, dev, out, b0, b1 in outs:  # and the per-element results are the slices of the whole
+        np.testing.assert_allclose(out.to_host()[2], want[:, b0:b1], rtol=0, atol=1e-12 * np.abs(want).max())
+    comm.close()
