@@ -2,7 +2,8 @@
  * Python, no torch, no C++.  Builds the reference's README expression
  * D = <A + B*C>_2 in G(3,0), lowers it, evaluates a batch on the GPU with both
  * engines and checks the result against a direct C evaluation of the same plan
- * description (the reference's term loop, eval.rs:77-83).
+ * description (the reference's term loop, eval.rs:77-83); then the f32 variant (bit-exact
+ * against the same loop in float), the batch-sum and the communicator.
  *
  *   gcc -std=c11 -O1 -Iinclude tests/c_abi_smoke.c -Lgaast_b200 -lgaast_b200 -Wl,-rpath,$PWD/gaast_b200 -lm -o /tmp/c_abi_smoke
  *
@@ -130,6 +131,101 @@ int main(void) {
             fprintf(stderr, "engine %d disagrees with the plan evaluated in C\n", engines[e]);
             return 1;
         }
+    }
+    /* the f32 variant of the same plan: binary32 batches in, binary32 out (strict arithmetic = the
+     * reference's operation sequence in float, replayed here in C) */
+    {
+        static float host32[3][8][N], got32[3][N], want32[3][N];
+        gaast_batch* in32[3];
+        gaast_batch* out32 = NULL;
+        for (int s = 0; s < 3; ++s) {
+            for (int r = 0; r < 8; ++r)
+                for (int i = 0; i < N; ++i) host32[s][r][i] = (float)host[s][r][i];
+            CHECK(gaast_batch_alloc_typed(ctx, DIM, 0xF, N, 0, GAAST_F32, &in32[s]));
+            uint32_t row = 0;
+            for (uint32_t k = 0; k <= DIM; ++k) {
+                CHECK(gaast_batch_upload_f32(in32[s], k, &host32[s][row][0], N));
+                row += kRows[k];
+            }
+        }
+        CHECK(gaast_batch_alloc_typed(ctx, DIM, 1u << 2, N, 0, GAAST_F32, &out32));
+        if (gaast_batch_dtype(out32) != GAAST_F32) return 1;
+        for (int i = 0; i < N; ++i) {
+            float buf[8][8];
+            memset(buf, 0, sizeof buf);
+            for (uint32_t o = 0; o < desc->n_ops; ++o) {
+                const gaast_op* op = &desc->ops[o];
+                if (op->kind == GAAST_OP_ADD_INPUT) {
+                    const gaast_input_desc* id = &desc->inputs[op->a];
+                    uint32_t src = 0, dst = 0;
+                    for (uint32_t k = 0; k <= DIM; ++k) {
+                        const int in_dst = (desc->buffer_masks[op->dst] >> k) & 1, in_src = (id->grade_mask >> k) & 1;
+                        if (((op->mask >> k) & 1) && in_dst && in_src)
+                            for (uint32_t r = 0; r < kRows[k]; ++r) buf[op->dst][dst + r] += host32[id->slot][src + r][i];
+                        if (in_src) src += kRows[k];
+                        if (in_dst) dst += kRows[k];
+                    }
+                } else {
+                    for (uint32_t t = op->term_begin; t < op->term_begin + op->term_count; ++t) {
+                        const gaast_term* tm = &desc->terms[t];
+                        volatile float prod = buf[op->a][tm->a] * buf[op->b][tm->b]; /* no contraction */
+                        volatile float scaled = prod * (float)tm->coeff;
+                        buf[op->dst][tm->out] = buf[op->dst][tm->out] + scaled;
+                    }
+                }
+            }
+            for (int r = 0; r < 3; ++r) want32[r][i] = buf[0][r];
+        }
+        for (int e = 0; e < 2; ++e) {
+            CHECK(gaast_eval(plan, in32, 3, out32, engines[e], GAAST_ARITH_STRICT));
+            CHECK(gaast_batch_download_f32(out32, 2, &got32[0][0], N));
+            CHECK(gaast_ctx_sync(ctx));
+            if (memcmp(got32, want32, sizeof got32) != 0) {
+                fprintf(stderr, "f32 engine %d is not bit-identical to the plan replayed in float\n", engines[e]);
+                return 1;
+            }
+        }
+        /* mixing scalar types in one call is refused */
+        gaast_batch* mixed[3] = {in32[0], in32[1], in[2]};
+        if (gaast_eval(plan, mixed, 3, out32, GAAST_ENGINE_AUTO, GAAST_ARITH_FMA) != GAAST_ERR_SHAPE) {
+            fprintf(stderr, "mixed f32 / f64 batches were not refused\n");
+            return 1;
+        }
+        printf("f32 variant: both engines bit-identical to the float replay\n");
+        gaast_batch_free(out32);
+        for (int s = 0; s < 3; ++s) gaast_batch_free(in32[s]);
+    }
+
+    /* batch-sum + the communicator (one rank here: the all-reduce leaves the sum unchanged) */
+    {
+        gaast_batch* sum_batch = NULL; /* 3 contiguous doubles of device memory: a grade-0 batch of length 3 */
+        CHECK(gaast_batch_alloc(ctx, DIM, 1u << 0, 3, 0, &sum_batch));
+        double* dev_sum = (double*)gaast_batch_grade_ptr(sum_batch, 0);
+        CHECK(gaast_eval_sum(plan, in, 3, out, dev_sum, GAAST_ENGINE_AUTO, GAAST_ARITH_FMA));
+        gaast_comm* comm = NULL;
+        gaast_status cst = gaast_comm_create(&ctx, 1, &comm);
+        if (cst == GAAST_OK) {
+            double* ptrs[1] = {dev_sum};
+            CHECK(gaast_comm_allreduce_sum(comm, ptrs, 3));
+            if (gaast_comm_size(comm) != 1) return 1;
+        } else if (cst != GAAST_ERR_UNSUPPORTED) { /* UNSUPPORTED = NCCL is not installed */
+            fprintf(stderr, "gaast_comm_create: %s\n", gaast_last_error());
+            return 1;
+        }
+        double sums[3] = {0};
+        CHECK(gaast_batch_download(sum_batch, 0, sums, 3));
+        CHECK(gaast_ctx_sync(ctx));
+        for (int r = 0; r < 3; ++r) {
+            double ref = 0.0, mag = 0.0;
+            for (int i = 0; i < N; ++i) { ref += want[r][i]; mag += fabs(want[r][i]); }
+            if (!(fabs(sums[r] - ref) <= 1e-11 * mag)) {
+                fprintf(stderr, "batch-sum component %d: %.17g vs %.17g\n", r, sums[r], ref);
+                return 1;
+            }
+        }
+        printf("batch-sum%s ok\n", comm ? " + gaast_comm all-reduce (1 rank)" : "");
+        if (comm) gaast_comm_destroy(comm);
+        gaast_batch_free(sum_batch);
     }
     printf("launches: %llu\n", (unsigned long long)gaast_ctx_launch_count(ctx));
 
