@@ -387,6 +387,9 @@ def run_gpu(args):
             line["e2e"] = {"value": n / (e["ms_per_step"] / 1e3) * w.products * world, "unit": UNIT,
                            "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
                            "ms_per_step": e["ms_per_step"], "matches_resident": e["matches_resident"],
+                           # PCIe is the bound of this leg: tools/pcie_peak.py measured 55.6 (H2D alone), 55.0 (D2H alone)
+                           # and 47.1 GB/s each way at the same time on this pool (profiles/r1_pcie_peak.txt)
+                           "gbs_each_way": max(e["h2d"], e["d2h"]) / (e["ms_per_step"] * 1e6),
                            "note": "gaast_eval_host: pinned host arrays, chunked H2D/kernel/D2H pipeline"
                            + ("; measured on rank 0 and scaled by the rank count" if world > 1 else "")}
         except Exception as ex:  # keep the headline line even if the host leg fails
