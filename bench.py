@@ -292,9 +292,11 @@ def measure_e2e(ctx, w, res, steps, torch):
     plan = res["plan"]
     host_in, grades, bcs = [], [], []
     h2d = 0
+    dt = next(iter(res["tin"][0].values())).dtype  # float64, or float32 for the f32 variant
+    es = 4 if dt == torch.float32 else 8
     for t, (gr, bc) in zip(res["tin"], w.inputs):
         rows = sum(comb(w.n, k) for k in gr)
-        h = torch.empty((rows, 1 if bc else n), dtype=torch.float64, pin_memory=True)
+        h = torch.empty((rows, 1 if bc else n), dtype=dt, pin_memory=True)
         r = 0
         for k in gr:
             c = comb(w.n, k)
@@ -303,9 +305,9 @@ def measure_e2e(ctx, w, res, steps, torch):
         host_in.append(h)
         grades.append(gr)
         bcs.append(bc)
-        h2d += rows * 8 * (1 if bc else n)
+        h2d += rows * es * (1 if bc else n)
     out_rows = _root_cols(plan, w)
-    host_out = torch.empty((out_rows, n), dtype=torch.float64, pin_memory=True)
+    host_out = torch.empty((out_rows, n), dtype=dt, pin_memory=True)
     torch.cuda.synchronize()
     plan.eval_host(host_in, grades, bcs, n, host_out)  # warm-up: allocates the device buffer sets
     t0 = time.perf_counter()
@@ -321,7 +323,7 @@ def measure_e2e(ctx, w, res, steps, torch):
     ref = res["out"].download(plan.root_grades()[0])[:, :1000]
     got = host_out[:ref.shape[0], :1000].numpy()
     ok = bool((ref == got).all())
-    return {"ms_per_step": ms / steps, "h2d": h2d, "d2h": out_rows * 8 * n, "matches_resident": ok}
+    return {"ms_per_step": ms / steps, "h2d": h2d, "d2h": out_rows * es * n, "matches_resident": ok}
 
 
 def run_gpu(args):
@@ -375,8 +377,8 @@ def run_gpu(args):
     if clocks is not None:
         line["clocks"] = clocks
 
-    if args.dtype == "f32":  # the f32 variant is a device-resident API; its FMA-pipe peak is not the f64 one
-        args.no_e2e = args.no_cpu = True
+    if args.dtype == "f32":  # no CPU leg for the f32 variant (the reference is f64-only); its FMA-pipe peak is not the f64 one
+        args.no_cpu = True
         args.all = False
         for key in ("fp64_tflops", "fp64_peak_tflops", "fp64_frac"):
             line["roofline"].pop(key)
@@ -390,7 +392,8 @@ def run_gpu(args):
                            # PCIe is the bound of this leg: tools/pcie_peak.py measured 55.6 (H2D alone), 55.0 (D2H alone)
                            # and 47.1 GB/s each way at the same time on this pool (profiles/r1_pcie_peak.txt)
                            "gbs_each_way": max(e["h2d"], e["d2h"]) / (e["ms_per_step"] * 1e6),
-                           "note": "gaast_eval_host: pinned host arrays, chunked H2D/kernel/D2H pipeline"
+                           "note": ("gaast_eval_host_f32" if args.dtype == "f32" else "gaast_eval_host")
+                           + ": pinned host arrays, chunked H2D/kernel/D2H pipeline"
                            + ("; measured on rank 0 and scaled by the rank count" if world > 1 else "")}
         except Exception as ex:  # keep the headline line even if the host leg fails
             line["e2e"] = {"error": f"{type(ex).__name__}: {ex}"}

@@ -126,6 +126,8 @@ PROTOTYPES = {
     "gaast_eval_sum": (C.c_int, vp, C.POINTER(vp), u32, vp, vp, C.c_int, C.c_int),
     "gaast_eval_host": (C.c_int, vp, C.POINTER(vp), C.POINTER(u32), C.POINTER(C.c_int), u32, u64, u64, vp,
                         C.c_int, C.c_int),
+    "gaast_eval_host_f32": (C.c_int, vp, C.POINTER(vp), C.POINTER(u32), C.POINTER(C.c_int), u32, u64, u64, vp,
+                            C.c_int, C.c_int),
     "gaast_comm_create": (C.c_int, C.POINTER(vp), u32, C.POINTER(vp)),
     "gaast_comm_unique_id": (C.c_int, C.c_char_p),
     "gaast_comm_create_rank": (C.c_int, vp, u32, u32, C.c_char_p, C.POINTER(vp)),

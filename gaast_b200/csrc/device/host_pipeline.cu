@@ -16,6 +16,7 @@ struct HostPipe {
     static constexpr int kSets = 3;
     gaast_ctx* ctx = nullptr;
     uint64_t chunk = 0;
+    int dtype = GAAST_F64;
     std::vector<uint32_t> masks;
     std::vector<int> bcast;
     std::vector<gaast_batch*> in[kSets];
@@ -55,10 +56,14 @@ uint32_t rows_of(uint32_t n, uint32_t mask) {
 
 }  // namespace
 
-extern "C" gaast_status gaast_eval_host(gaast_plan* plan, const double* const* host_in, const uint32_t* in_masks,
-                                        const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
-                                        double* host_out, int engine, int arith) {
+static gaast_status eval_host_impl(gaast_plan* plan, const void* const* host_in_v, const uint32_t* in_masks,
+                                   const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
+                                   void* host_out_v, int dtype, int engine, int arith) {
     try {
+        if (dtype != GAAST_F64 && dtype != GAAST_F32) throw Error(GAAST_ERR_INVALID, "eval_host: unknown dtype");
+        const size_t es = dtype == GAAST_F32 ? 4 : 8;
+        const char* const* host_in = reinterpret_cast<const char* const*>(host_in_v);
+        char* host_out = static_cast<char*>(host_out_v);
         if (!plan || !plan->ctx) throw Error(GAAST_ERR_INVALID, "eval_host: null or offline plan");
         gaast_ctx* ctx = plan->ctx;
         const auto& h = plan->h;
@@ -78,13 +83,13 @@ extern "C" gaast_status gaast_eval_host(gaast_plan* plan, const double* const* h
         const uint32_t wide = std::max<uint32_t>(1, std::max(in_rows, out_rows));
         uint64_t chunk_mib = 32;
         if (const char* e = std::getenv("GAAST_HOST_CHUNK_MIB")) chunk_mib = std::max(1, std::atoi(e));
-        uint64_t chunk = (chunk_mib << 20) / (8ull * wide);
+        uint64_t chunk = (chunk_mib << 20) / (uint64_t(es) * wide);
         chunk = std::max<uint64_t>(4096, chunk / 4096 * 4096);
         chunk = std::min<uint64_t>(chunk, (len + 4095) / 4096 * 4096);
         if (chunk == 0) chunk = 4096;
 
         gaast::HostPipe* p = plan->pipe;
-        bool rebuild = !p || p->chunk != chunk || p->masks.size() != n_inputs;
+        bool rebuild = !p || p->chunk != chunk || p->masks.size() != n_inputs || p->dtype != dtype;
         if (p && !rebuild)
             for (uint32_t s = 0; s < n_inputs; ++s)
                 if (p->masks[s] != in_masks[s] || p->bcast[s] != (in_broadcast[s] != 0)) rebuild = true;
@@ -94,14 +99,16 @@ extern "C" gaast_status gaast_eval_host(gaast_plan* plan, const double* const* h
             auto np = std::make_unique<gaast::HostPipe>();
             np->ctx = ctx;
             np->chunk = chunk;
+            np->dtype = dtype;
             np->masks.assign(in_masks, in_masks + n_inputs);
             np->bcast.resize(n_inputs);
             for (uint32_t s = 0; s < n_inputs; ++s) np->bcast[s] = in_broadcast[s] != 0;
             for (int set = 0; set < gaast::HostPipe::kSets; ++set) {
                 np->in[set].assign(n_inputs, nullptr);
                 for (uint32_t s = 0; s < n_inputs; ++s)
-                    ckg(gaast_batch_alloc(ctx, h.n, in_masks[s], np->bcast[s] ? 1 : chunk, np->bcast[s], &np->in[set][s]));
-                ckg(gaast_batch_alloc(ctx, h.n, h.buffer_masks[0], chunk, 0, &np->out[set]));
+                    ckg(gaast_batch_alloc_typed(ctx, h.n, in_masks[s], np->bcast[s] ? 1 : chunk, np->bcast[s], dtype,
+                                                &np->in[set][s]));
+                ckg(gaast_batch_alloc_typed(ctx, h.n, h.buffer_masks[0], chunk, 0, dtype, &np->out[set]));
                 ck(cudaEventCreateWithFlags(&np->h2d_done[set], cudaEventDisableTiming), "event");
                 ck(cudaEventCreateWithFlags(&np->comp_done[set], cudaEventDisableTiming), "event");
                 ck(cudaEventCreateWithFlags(&np->d2h_done[set], cudaEventDisableTiming), "event");
@@ -109,14 +116,14 @@ extern "C" gaast_status gaast_eval_host(gaast_plan* plan, const double* const* h
             plan->pipe = p = np.release();
         }
 
-        auto copy_rows = [&](double* dev, uint64_t dev_stride, const double* host, uint64_t hstride, uint64_t width,
+        auto copy_rows = [&](double* dev, uint64_t dev_stride, const char* host, uint64_t hstride, uint64_t width,
                              uint32_t rows, bool to_dev, cudaStream_t st) {
             if (!rows || !width) return;
             if (to_dev)
-                ck(cudaMemcpy2DAsync(dev, dev_stride * 8, host, hstride * 8, width * 8, rows, cudaMemcpyHostToDevice, st),
+                ck(cudaMemcpy2DAsync(dev, dev_stride * es, host, hstride * es, width * es, rows, cudaMemcpyHostToDevice, st),
                    "H2D");
             else
-                ck(cudaMemcpy2DAsync(const_cast<double*>(host), hstride * 8, dev, dev_stride * 8, width * 8, rows,
+                ck(cudaMemcpy2DAsync(const_cast<char*>(host), hstride * es, dev, dev_stride * es, width * es, rows,
                                      cudaMemcpyDeviceToHost, st),
                    "D2H");
         };
@@ -136,7 +143,7 @@ extern "C" gaast_status gaast_eval_host(gaast_plan* plan, const double* const* h
                     // a shared operand: the host array is [rows] contiguous, one value per component
                     copy_rows(b->base, b->stride, host_in[s], 1, 1, rows, true, ctx->h2d);
                 } else {
-                    copy_rows(b->base, b->stride, host_in[s] + off, host_stride, w, rows, true, ctx->h2d);
+                    copy_rows(b->base, b->stride, host_in[s] + off * es, host_stride, w, rows, true, ctx->h2d);
                 }
                 b->len = p->bcast[s] ? 1 : w;
             }
@@ -149,7 +156,7 @@ extern "C" gaast_status gaast_eval_host(gaast_plan* plan, const double* const* h
             ck(cudaEventRecord(p->comp_done[set], ctx->stream), "record");
             // D2H
             ck(cudaStreamWaitEvent(ctx->d2h, p->comp_done[set], 0), "wait");
-            copy_rows(p->out[set]->base, p->out[set]->stride, host_out + off, host_stride, w, out_rows, false, ctx->d2h);
+            copy_rows(p->out[set]->base, p->out[set]->stride, host_out + off * es, host_stride, w, out_rows, false, ctx->d2h);
             ck(cudaEventRecord(p->d2h_done[set], ctx->d2h), "record");
         }
         ck(cudaStreamSynchronize(ctx->d2h), "sync");
@@ -166,4 +173,18 @@ extern "C" gaast_status gaast_eval_host(gaast_plan* plan, const double* const* h
         gaast::set_last_error(e.what());
         return GAAST_ERR_INVALID;
     }
+}
+
+extern "C" gaast_status gaast_eval_host(gaast_plan* plan, const double* const* host_in, const uint32_t* in_masks,
+                                        const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
+                                        double* host_out, int engine, int arith) {
+    return eval_host_impl(plan, reinterpret_cast<const void* const*>(host_in), in_masks, in_broadcast, n_inputs, len,
+                          host_stride, host_out, GAAST_F64, engine, arith);
+}
+
+extern "C" gaast_status gaast_eval_host_f32(gaast_plan* plan, const float* const* host_in, const uint32_t* in_masks,
+                                            const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
+                                            float* host_out, int engine, int arith) {
+    return eval_host_impl(plan, reinterpret_cast<const void* const*>(host_in), in_masks, in_broadcast, n_inputs, len,
+                          host_stride, host_out, GAAST_F32, engine, arith);
 }

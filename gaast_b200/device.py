@@ -254,14 +254,16 @@ class Plan:
     def eval_host(self, host_in: Sequence[np.ndarray], in_grades: Sequence[Iterable[int]],
                   in_broadcast: Sequence[bool], length: int, host_out: np.ndarray, host_stride: Optional[int] = None,
                   engine: int = L.ENGINE_AUTO, arith: int = L.ARITH_FMA):
-        """Host arrays in / out (see gaast_eval_host).  Arrays are [rows][host_stride] float64."""
+        """Host arrays in / out (see gaast_eval_host).  Arrays are [rows][host_stride] float64, or all
+        float32 (gaast_eval_host_f32)."""
         n_in = len(host_in)
         ptrs = (L.vp * max(1, n_in))(*[_host_ptr(a) for a in host_in])
         masks = (L.u32 * max(1, n_in))(*[grade_mask(g) for g in in_grades])
         bc = (C.c_int * max(1, n_in))(*[int(bool(x)) for x in in_broadcast])
         stride = int(host_stride if host_stride is not None else length)
-        L.check(L.lib.gaast_eval_host(self._h, ptrs, masks, bc, n_in, int(length), stride, L.vp(_host_ptr(host_out)),
-                                      engine, arith))
+        f32 = str(getattr(host_out, "dtype", "")).endswith("float32")  # numpy or torch, all arrays of one type
+        fn = L.lib.gaast_eval_host_f32 if f32 else L.lib.gaast_eval_host
+        L.check(fn(self._h, ptrs, masks, bc, n_in, int(length), stride, L.vp(_host_ptr(host_out)), engine, arith))
 
     def free(self):
         h, self._h = self._h, None

@@ -240,6 +240,11 @@ gaast_status gaast_eval_host(gaast_plan* plan, const double* const* host_in, con
                              const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
                              double* host_out, int engine, int arith);
 
+/* The same pipeline for binary32 host arrays (the f32 variant; half the PCIe traffic). */
+gaast_status gaast_eval_host_f32(gaast_plan* plan, const float* const* host_in, const uint32_t* in_masks,
+                                 const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
+                                 float* host_out, int engine, int arith);
+
 /* ------------------------------------------------------------------ comm --
  * Multi-GPU: batch elements are independent, so a batch is sharded into
  * contiguous slices, one per device, and every device evaluates its slice with its own ctx /

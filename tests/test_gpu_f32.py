@@ -142,3 +142,34 @@ def test_f32_wide_plan_table_engine_global_workspace(ctx):
     ctx.sync()
     assert "engine=table" in plan.last_kernel() and "ws=global" in plan.last_kernel()
     assert_bit_exact(out.to_host(), want, "G(10) full product in f32, table engine, global workspace")
+
+
+def test_f32_eval_host_matches_resident(ctx):
+    """gaast_eval_host_f32: binary32 host arrays through the chunked H2D / kernel / D2H pipeline give the
+    bits of the device-resident evaluation (several chunks: GAAST_HOST_CHUNK_MIB=1)."""
+    import os
+    w = W.WORKLOADS["cfg2"]
+    batch = 300_000 + 6
+    host = _f32_inputs(w, batch)
+    bcs = [bc for _, bc in w.inputs]
+    plan = g.Plan(ctx, W.specialize(w))
+    dev = [g.DeviceBatch.from_host(ctx, w.n, host[s], broadcast=bc, dtype=L.F32) for s, bc in enumerate(bcs)]
+    want = plan.eval(dev).to_host()
+    ctx.sync()
+    from math import comb
+    flat_in, grades = [], []
+    for (gr, bc), d in zip(w.inputs, host):
+        flat_in.append(np.ascontiguousarray(np.concatenate([d[k] for k in gr], axis=0)))
+        grades.append(gr)
+    rows = sum(comb(w.n, k) for k in plan.root_grades())
+    out = np.zeros((rows, batch), dtype=np.float32)
+    os.environ["GAAST_HOST_CHUNK_MIB"] = "1"
+    try:
+        plan.eval_host(flat_in, grades, bcs, batch, out)
+    finally:
+        del os.environ["GAAST_HOST_CHUNK_MIB"]
+    r = 0
+    for k in plan.root_grades():
+        c = comb(w.n, k)
+        assert np.array_equal(out[r:r + c], want[k]), f"grade {k}"
+        r += c
