@@ -25,7 +25,7 @@ vp = C.c_void_p
  ERR_SHAPE) = range(9)
 STATUS_NAMES = ["OK", "INVALID", "UNSUPPORTED", "PANIC", "NO_DEVICE", "CUDA", "OOM", "JIT", "SHAPE"]
 
-ENGINE_AUTO, ENGINE_TABLE, ENGINE_SPECIALIZED = 0, 1, 2
+ENGINE_AUTO, ENGINE_TABLE, ENGINE_SPECIALIZED, ENGINE_DENSE_WARP = 0, 1, 2, 3
 ARITH_FMA, ARITH_STRICT = 0, 1
 F64, F32 = 0, 1  # gaast_dtype
 

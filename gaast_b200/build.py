@@ -34,6 +34,7 @@ SOURCES = [
     "device/jit.cpp",
     "device/comm.cpp",
     "device/table_engine.cu",
+    "device/dense_warp.cu",
     "device/runtime.cu",
     "device/host_pipeline.cu",
 ]

@@ -1,0 +1,229 @@
+// Dense-warp engine: full geometric products in high dimension (n = 7..10), ONE WARP PER MULTIVECTOR.
+//
+// The specialised engine keeps one batch element per thread, which is what reaches the HBM roofline
+// on the grade-restricted BASELINE workloads.  A FULL product in G(n), n >= 7, does not fit that
+// mapping: 2 x 2^n operand components per element (2-16 KB) exceed a thread's registers and
+// shared-memory share, 4^n straight-line terms (16 K - 1 M) exceed any sensible kernel, and the table
+// engine needs 5 shared-memory wavefronts per 32 element-terms.  Here a warp owns one element:
+//
+//   out[k] = sum_a  c(a, a^k) * A[a] * B[a^k]                       (eval.rs:77-83 for a full table)
+//
+//   * both operands of a tile of T elements are staged in shared memory, TRANSPOSED to
+//     [element][blade bitmask] (global arrays are batch-innermost: the tile is read in coalesced
+//     rows and written with an odd row pitch, conflict free);
+//   * lane l owns the outputs k with (k & 31) == l, 2^n / 32 accumulators in registers;
+//   * for a given left blade a the lane reads B[(g << 5) | ((a & 31) ^ l)] for every 32-blade group g:
+//     the 32 lanes touch the 32 members of one group in a permuted order -- a conflict-free LDS --
+//     and A[a] is one broadcast read; no shuffles, no reduction across lanes are needed at all;
+//   * the coefficients are +-1 (non-degenerate diagonal metric): one bit per (a, b), read as
+//     warp-uniform 128-bit words [a][b >> 5], bit (b & 31); the bits are taken from the plan's own
+//     term table, nothing is re-derived.
+//
+// Arithmetic: one DFMA per term, terms of an output summed in ascending left-blade order (not the
+// reference's order): FMA arithmetic only, like the other dense lowerings; GAAST_ARITH_STRICT keeps
+// using the table engine.  Only plans that ARE a full product of two batch inputs qualify
+// (dense_warp_analyse); everything else is untouched.
+#include <algorithm>
+#include <cstring>
+
+#include "../runtime.hpp"
+
+namespace gaast {
+
+namespace {
+
+
+struct DenseWarpArgs {
+    const uint16_t* blade_of_slot;  // [2^n] blade bitmask of every slot (grades ascending, masks ascending)
+    const uint32_t* sign_words;     // [2^n][J]: bit (b & 31) of word [a][b >> 5] set = coefficient of (a, b) is -1
+    int n, T, LD;                   // tile: T elements, row pitch LD = 2^n + 1 doubles
+    int gstart[GAAST_MAX_DIM + 2];  // first slot of grade k
+    int streamL[GAAST_MAX_DIM + 1], streamR[GAAST_MAX_DIM + 1], streamO[GAAST_MAX_DIM + 1];
+};
+
+__device__ __forceinline__ double flip_if(double v, unsigned bit) {  // bit in {0, 1}
+    return __hiloint2double(__double2hiint(v) ^ int(bit << 31), __double2loint(v));
+}
+
+template <int J>
+__global__ void __launch_bounds__(512) dense_warp_kernel(const __grid_constant__ EvalArgs a,
+                                                         const __grid_constant__ DenseWarpArgs d) {
+    extern __shared__ double sm[];
+    constexpr int NB = 32 * J;  // 2^n blades
+    const int T = d.T, LD = d.LD;
+    double* const A = sm;
+    double* const B = sm + size_t(T) * LD;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    // tile traffic: `per` rows of T consecutive elements per warp instruction
+    const int per = 32 / T, te = lane % T, tr = lane / T;
+    const long long n_tiles = (a.n + T - 1) / T;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long e0 = tile * T;
+        const int cnt = int(a.n - e0 < T ? a.n - e0 : T);
+        // ---- stage both operands: coalesced rows in, [element][blade] out (graded.rs:46 per grade) ----
+        for (int r = warp * per + tr; r < NB; r += n_warps * per) {
+            const int blade = d.blade_of_slot[r];
+            const int k = __popc(blade), row = r - d.gstart[k];
+            if (te < cnt) {
+                A[te * LD + blade] = __ldg(a.sptr[d.streamL[k]] + (long long)row * a.srow[d.streamL[k]] + e0 + te);
+                B[te * LD + blade] = __ldg(a.sptr[d.streamR[k]] + (long long)row * a.srow[d.streamR[k]] + e0 + te);
+            }
+        }
+        __syncthreads();
+        // ---- one warp per multivector ----
+        for (int e = warp; e < cnt; e += n_warps) {
+            double* const Ae = A + e * LD;
+            const double* const Be = B + e * LD;
+            double acc[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[j] = 0.0;
+#pragma unroll
+            for (int ahi = 0; ahi < J; ++ahi) {
+#pragma unroll 1
+                for (int alo = 0; alo < 32; ++alo) {
+                    const int ab = ahi * 32 + alo;
+                    const double xa = Ae[ab];       // broadcast
+                    const unsigned bl = alo ^ lane;  // this lane's member of every group
+                    const uint4* const wp = reinterpret_cast<const uint4*>(d.sign_words + size_t(ab) * J);
+#pragma unroll
+                    for (int q = 0; q < J / 4; ++q) {
+                        const uint4 w4 = __ldg(wp + q);  // warp-uniform
+                        const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int g = q * 4 + c;  // group of b; output group = ahi ^ g
+                            const double yb = Be[g * 32 + bl];
+                            acc[ahi ^ g] = fma(flip_if(xa, (w[c] >> bl) & 1u), yb, acc[ahi ^ g]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();  // every lane has read all of Ae: the element's results replace its left operand
+#pragma unroll
+            for (int j = 0; j < J; ++j) Ae[j * 32 + lane] = acc[j];
+        }
+        __syncthreads();
+        // ---- results out: [element][blade] -> coalesced rows of the root's grade arrays ----
+        if (a.store_out)
+            for (int r = warp * per + tr; r < NB; r += n_warps * per) {
+                const int blade = d.blade_of_slot[r];
+                const int k = __popc(blade), row = r - d.gstart[k];
+                if (te < cnt) a.sptr[d.streamO[k]][(long long)row * a.srow[d.streamO[k]] + e0 + te] = A[te * LD + blade];
+            }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+// Does the plan consist of exactly  root = L * R  with L and R two full-grade batch inputs and a
+// complete +-1 coefficient table?  Fills the host tables on success.
+bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
+    const uint32_t n = h.n;
+    if (n < 7 || n > 10) return false;
+    const uint32_t full = (2u << n) - 1, NB = 1u << n;
+    if (h.buffer_masks.size() != 3 || h.ops.size() != 3) return false;
+    for (uint32_t m : h.buffer_masks)
+        if (m != full) return false;
+    const gaast_op &o0 = h.ops[0], &o1 = h.ops[1], &mul = h.ops[2];
+    if (o0.kind != GAAST_OP_ADD_INPUT || o1.kind != GAAST_OP_ADD_INPUT || mul.kind != GAAST_OP_MUL_TERMS) return false;
+    if (mul.dst != 0 || mul.a == 0 || mul.b == 0 || mul.a == mul.b || mul.term_count != uint64_t(NB) * NB) return false;
+    auto input_of = [&](uint32_t buf, uint32_t* slot) {
+        const gaast_op* src = o0.dst == buf ? &o0 : (o1.dst == buf ? &o1 : nullptr);
+        if (!src || src->mask != full) return false;
+        const gaast_input_desc& in = h.inputs[src->a];
+        if (in.kind != GAAST_INPUT_BATCH || in.grade_mask != full) return false;
+        *slot = in.slot;
+        return true;
+    };
+    if (o0.dst == o1.dst) return false;
+    uint32_t slotL = 0, slotR = 0;
+    if (!input_of(mul.a, &slotL) || !input_of(mul.b, &slotR)) return false;
+    // slot <-> blade (algebra.rs:221-246): grades ascending, masks of a grade in ascending numeric order
+    std::vector<uint16_t> blade_of(NB);
+    std::vector<int> gstart(n + 2, 0);
+    {
+        uint32_t s = 0;
+        for (uint32_t k = 0; k <= n; ++k) {
+            gstart[k] = int(s);
+            for (uint32_t b = 0; b < NB; ++b)
+                if (uint32_t(__builtin_popcount(b)) == k) blade_of[s++] = uint16_t(b);
+        }
+        gstart[n + 1] = int(s);
+    }
+    std::vector<uint16_t> slot_of(NB);
+    for (uint32_t s = 0; s < NB; ++s) slot_of[blade_of[s]] = uint16_t(s);
+    const uint32_t J = NB / 32;
+    std::vector<uint32_t> words(size_t(NB) * J, 0);
+    std::vector<uint8_t> seen(size_t(NB) * NB / 8, 0);
+    for (uint32_t t = mul.term_begin; t < mul.term_begin + mul.term_count; ++t) {
+        const gaast_term& tm = h.terms[t];
+        if (tm.a >= NB || tm.b >= NB || tm.out >= NB) return false;
+        const uint32_t ab = blade_of[tm.a], bb = blade_of[tm.b];
+        if (slot_of[ab ^ bb] != tm.out) return false;
+        if (tm.coeff != 1.0 && tm.coeff != -1.0) return false;  // degenerate or scaled metric: table engine
+        const size_t bit = size_t(ab) * NB + bb;
+        if (seen[bit >> 3] >> (bit & 7) & 1) return false;
+        seen[bit >> 3] |= uint8_t(1u << (bit & 7));
+        if (tm.coeff < 0) words[size_t(ab) * J + (bb >> 5)] |= 1u << (bb & 31);
+    }
+    if (out) {
+        out->n = n;
+        out->slotL = slotL;
+        out->slotR = slotR;
+        out->blade_of_slot = std::move(blade_of);
+        out->sign_words = std::move(words);
+        out->gstart = std::move(gstart);
+    }
+    return true;
+}
+
+DenseWarpLaunch dense_warp_shape(const gaast_ctx& ctx, uint32_t n, long long batch) {
+    DenseWarpLaunch s;
+    const int NB = 1 << n, LD = NB + 1;
+    int T = 32;
+    while (T > 1 && size_t(2) * T * LD * sizeof(double) > size_t(ctx.smem_optin) - 1024) T /= 2;
+    s.T = T;
+    s.LD = LD;
+    s.smem = size_t(2) * T * LD * sizeof(double);
+    const int per_sm = std::max<int>(1, int((size_t(ctx.smem_optin)) / (s.smem + 1024)));
+    // one element per warp and pass where a single block owns the SM; 8 warps otherwise
+    s.threads = per_sm == 1 ? std::min(512, std::max(256, 32 * T)) : 256;
+    const long long tiles = (batch + T - 1) / T;
+    const long long cap = (long long)ctx.sm_count * std::min(per_sm, 2048 / s.threads);
+    s.grid = int(std::max<long long>(1, std::min(tiles, cap)));
+    return s;
+}
+
+cudaError_t dense_warp_launch(const EvalArgs& args, const DenseWarpHost& hplan, const DevicePlanHost& h,
+                              const uint16_t* d_blade_of_slot, const uint32_t* d_sign_words, const DenseWarpLaunch& shape,
+                              cudaStream_t stream) {
+    DenseWarpArgs d;
+    std::memset(&d, 0, sizeof d);
+    d.blade_of_slot = d_blade_of_slot;
+    d.sign_words = d_sign_words;
+    d.n = int(hplan.n);
+    d.T = shape.T;
+    d.LD = shape.LD;
+    for (uint32_t k = 0; k <= hplan.n + 1; ++k) d.gstart[k] = hplan.gstart[k];
+    for (uint32_t k = 0; k <= hplan.n; ++k) {
+        d.streamL[k] = h.stream_of(hplan.slotL, k);
+        d.streamR[k] = h.stream_of(hplan.slotR, k);
+        d.streamO[k] = int(h.n_in_streams + k);  // the root holds every grade, ascending
+    }
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shape.smem));
+        if (e != cudaSuccess) return e;
+        kernel<<<shape.grid, shape.threads, shape.smem, stream>>>(args, d);
+        return cudaGetLastError();
+    };
+    switch (hplan.n) {
+        case 7: return go(dense_warp_kernel<4>);
+        case 8: return go(dense_warp_kernel<8>);
+        case 9: return go(dense_warp_kernel<16>);
+        case 10: return go(dense_warp_kernel<32>);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace gaast

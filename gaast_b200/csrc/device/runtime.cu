@@ -239,6 +239,8 @@ gaast_status gaast_plan_destroy(gaast_plan* plan) {
             cudaFree(plan->d_partials);
             cudaFree(plan->d_ws);
             cudaFree(plan->d_uniform);
+            cudaFree(plan->d_dw_blades);
+            cudaFree(plan->d_dw_signs);
         }
         delete plan;
     });
@@ -503,12 +505,35 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         return;
     }
 
+    // dense-warp engine: usable for this call?  (full product plan, f64, FMA arithmetic, per-element operands)
+    auto dense_warp_ready = [&]() {
+        if (with_sum || f32 || arith != GAAST_ARITH_FMA || bslots != 0 || !out) return false;
+        if (plan->dense_warp_state == 0) {
+            plan->dense_warp_state = gaast::dense_warp_analyse(h, &plan->dense_warp) ? 1 : -1;
+            if (plan->dense_warp_state == 1) {
+                upload(plan->d_dw_blades, plan->dense_warp.blade_of_slot, ctx->stream);
+                upload(plan->d_dw_signs, plan->dense_warp.sign_words, ctx->stream);
+            }
+        }
+        return plan->dense_warp_state == 1;
+    };
+    bool use_dense_warp = false;
+    if (engine == GAAST_ENGINE_DENSE_WARP) {
+        if (!dense_warp_ready())
+            throw Error(GAAST_ERR_UNSUPPORTED,
+                        "dense-warp engine: the plan is not a full product of two per-element f64 batch inputs in G(n), "
+                        "7 <= n <= 10, with a +-1 metric, evaluated in FMA arithmetic without batch-sum");
+        use_dense_warp = true;
+    }
+
     std::shared_ptr<gaast::JitKernel> jk;
     // AUTO: a handful of elements of a plan never specialised before is not worth generating and
     // compiling a kernel for (0.3-3 s): the table engine evaluates it at once.
     const bool tiny = engine == GAAST_ENGINE_AUTO && plan->jit.empty() &&
                       double(n) * double(h.total_terms > 0 ? h.total_terms : 1) < 2e6;
-    if ((engine == GAAST_ENGINE_AUTO && !tiny) || engine == GAAST_ENGINE_SPECIALIZED) {
+    if (use_dense_warp) {
+        // chosen explicitly
+    } else if ((engine == GAAST_ENGINE_AUTO && !tiny) || engine == GAAST_ENGINE_SPECIALIZED) {
         if (plan->jit_error.empty() || engine == GAAST_ENGINE_SPECIALIZED) {
             try {
                 gaast::CodegenOptions opt;
@@ -538,12 +563,24 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
             }
         }
         if (!jk && engine == GAAST_ENGINE_SPECIALIZED) throw Error(GAAST_ERR_JIT, plan->jit_error);
+        // too large / too wide to specialise: a full high-dimensional product still has a fast engine
+        if (!jk && engine == GAAST_ENGINE_AUTO && dense_warp_ready()) use_dense_warp = true;
     } else if (engine != GAAST_ENGINE_TABLE && engine != GAAST_ENGINE_AUTO) {
         throw Error(GAAST_ERR_INVALID, "unknown engine");
     }
 
     int grid = 0;
-    if (jk) {
+    if (use_dense_warp) {
+        const gaast::DenseWarpLaunch shape = gaast::dense_warp_shape(*ctx, h.n, n);
+        grid = shape.grid;
+        cuda_check(gaast::dense_warp_launch(a, plan->dense_warp, h, plan->d_dw_blades, plan->d_dw_signs, shape, ctx->stream),
+                   "launch dense-warp engine");
+        ctx->launches++;
+        char desc[256];
+        std::snprintf(desc, sizeof desc, "dense_warp_kernel engine=dense_warp grid=%d block=%d smem=%zu tile=%d elements",
+                      grid, shape.threads, shape.smem, shape.T);
+        plan->last_kernel = desc;
+    } else if (jk) {
         const long long per_block = (long long)jk->threads * jk->elems_per_thread;
         const long long blocks = (n + per_block - 1) / per_block;
         if (blocks > 0x7fffffffLL) throw Error(GAAST_ERR_SHAPE, "batch too long for one launch");

@@ -96,6 +96,23 @@ cudaError_t reduce_partials_launch(const double* partials, int n_blocks, int n_c
                                    cudaStream_t stream);
 const char* table_engine_arch();
 
+// dense_warp.cu: full geometric products in G(n), n = 7..10, one warp per multivector
+struct DenseWarpHost {
+    uint32_t n = 0, slotL = 0, slotR = 0;
+    std::vector<uint16_t> blade_of_slot;  // [2^n]
+    std::vector<uint32_t> sign_words;     // [2^n][2^n / 32]
+    std::vector<int> gstart;              // first slot of grade k
+};
+struct DenseWarpLaunch {
+    int T = 0, LD = 0, threads = 0, grid = 0;
+    size_t smem = 0;
+};
+bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out);
+DenseWarpLaunch dense_warp_shape(const gaast_ctx& ctx, uint32_t n, long long batch);
+cudaError_t dense_warp_launch(const EvalArgs& args, const DenseWarpHost& hplan, const DevicePlanHost& h,
+                              const uint16_t* d_blade_of_slot, const uint32_t* d_sign_words, const DenseWarpLaunch& shape,
+                              cudaStream_t stream);
+
 // host_pipeline.cu
 struct HostPipe;
 void host_pipe_destroy(HostPipe* p);
@@ -144,4 +161,9 @@ struct gaast_plan {
     int variant = 0;
     int force_ept = 0;
     gaast::HostPipe* pipe = nullptr;  // device buffer sets of gaast_eval_host
+    // dense-warp engine: analysed on first use (0 = not yet, 1 = eligible, -1 = not a full product)
+    int dense_warp_state = 0;
+    gaast::DenseWarpHost dense_warp;
+    uint16_t* d_dw_blades = nullptr;
+    uint32_t* d_dw_signs = nullptr;
 };

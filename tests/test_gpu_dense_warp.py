@@ -1,0 +1,85 @@
+"""The dense-warp engine (csrc/device/dense_warp.cu): full geometric products in G(n), n = 7..10,
+one warp per multivector.  FMA arithmetic, so the bar is 1e-12 x max(|oracle|, sum |terms|); the
+strict arithmetic of the same plans keeps running on the table engine, bit-exact."""
+from math import comb
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import gaast_b200 as g  # noqa: E402
+from gaast_b200 import _lib as L  # noqa: E402
+from gaast_b200.expr import Input, mv as pmv  # noqa: E402
+from tests.helpers import assert_bit_exact, assert_close, oracle_abs_scale, oracle_eval  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = g.Ctx(0)
+    yield c
+    c.close()
+
+
+def _case(n, metric, batch, seed):
+    full = tuple(range(n + 1))
+    rng = np.random.default_rng(seed)
+    host = [{k: rng.uniform(-1, 1, (comb(n, k), batch)) for k in full} for _ in range(2)]
+    build = lambda a, b: a * b  # noqa: E731
+    ast = build(pmv(Input(0, full)), pmv(Input(1, full))).specialize(metric)
+    return full, host, build, ast
+
+
+@pytest.mark.parametrize("n,metric,batch", [
+    (7, [1.0] * 7, 1), (7, [1.0] * 5 + [-1.0] * 2, 33), (7, [1.0] * 7, 200),
+    (8, [1.0] * 8, 2), (8, [-1.0, 1.0] * 4, 70),
+    (9, [1.0] * 8 + [-1.0], 19), (10, [1.0] * 10, 9),
+])
+def test_dense_warp_parity(ctx, n, metric, batch):
+    full, host, build, ast = _case(n, metric, batch, 100 * n + batch)
+    want = oracle_eval(build, metric, host, [False, False], batch)
+    scale = oracle_abs_scale(build, metric, host, [False, False], batch)
+    plan = g.Plan(ctx, ast)
+    dev = [g.DeviceBatch.from_host(ctx, n, h) for h in host]
+    out = plan.eval(dev, engine=L.ENGINE_DENSE_WARP)
+    ctx.sync()
+    assert "engine=dense_warp" in plan.last_kernel()
+    assert_close(out.to_host(), want, scale, what=f"G({n}) dense-warp")
+    # AUTO reaches the same engine once the plan turns out too large / too wide to specialise
+    # (a handful of elements of a never-seen plan goes to the table engine: not worth a decision)
+    if batch * 4 ** n >= 2e6:
+        out2 = plan.eval(dev, engine=L.ENGINE_AUTO)
+        ctx.sync()
+        assert "engine=dense_warp" in plan.last_kernel(), plan.last_kernel()
+        assert_bit_exact(out2.to_host(), out.to_host(), "AUTO == explicit dense-warp")
+    # strict arithmetic stays on the table engine, bit-identical to the reference order
+    if n <= 8:
+        out3 = plan.eval(dev, engine=L.ENGINE_AUTO, arith=L.ARITH_STRICT)
+        ctx.sync()
+        assert "engine=table" in plan.last_kernel()
+        assert_bit_exact(out3.to_host(), want, f"G({n}) strict on the table engine")
+
+
+def test_dense_warp_refuses_other_plans(ctx):
+    n = 7
+    full = tuple(range(n + 1))
+    a, b = pmv(Input(0, full)), pmv(Input(1, full))
+    dev = [g.DeviceBatch.alloc(ctx, n, full, 64) for _ in range(2)]
+    for ast in ((a ^ b).specialize([1.0] * n),                      # not a full product
+                (a * b).specialize([1.0] * 6 + [0.0]),               # degenerate metric: zero coefficients
+                (a * b).specialize([1.0] * 6 + [2.0])):              # scaled metric: |coefficient| != 1
+        plan = g.Plan(ctx, ast)
+        with pytest.raises(g.GaastError) as ei:
+            plan.eval(dev, engine=L.ENGINE_DENSE_WARP)
+        assert ei.value.status == L.ERR_UNSUPPORTED
+        plan.eval(dev, engine=L.ENGINE_AUTO)  # still evaluates, on another engine
+        ctx.sync()
+        assert "dense_warp" not in plan.last_kernel()
+    # a plan of the right shape, but a broadcast operand or f32 batches: refused as well
+    plan = g.Plan(ctx, (a * b).specialize([1.0] * n))
+    shared = g.DeviceBatch.alloc(ctx, n, full, 1, broadcast=True)
+    with pytest.raises(g.GaastError):
+        plan.eval([shared, dev[1]], engine=L.ENGINE_DENSE_WARP)
+    d32 = [g.DeviceBatch.alloc(ctx, n, full, 64, dtype=L.F32) for _ in range(2)]
+    with pytest.raises(g.GaastError):
+        plan.eval(d32, engine=L.ENGINE_DENSE_WARP)
