@@ -15,14 +15,22 @@
 //   * for a given left blade a the lane reads B[(g << 5) | ((a & 31) ^ l)] for every 32-blade group g:
 //     the 32 lanes touch the 32 members of one group in a permuted order -- a conflict-free LDS --
 //     and A[a] is one broadcast read; no shuffles, no reduction across lanes are needed at all;
-//   * the coefficients are +-1 (non-degenerate diagonal metric): one bit per (a, b), read as
-//     warp-uniform 128-bit words [a][b >> 5], bit (b & 31); the bits are taken from the plan's own
-//     term table, nothing is re-derived.
+//   * loop order: for every low part alo of the left blade (32 iterations) the warp reads the J = 2^n / 32
+//     left values A[(ahi, alo)] (broadcasts, kept in registers) and every lane ITS member of each right
+//     group, B[(g << 5) | (alo ^ l)], once: 2 J shared-memory reads feed J^2 terms;
+//   * the coefficients are +-1 (non-degenerate diagonal metric) and factorise over G(n) = G(hi) (x) G(lo5):
+//         c(a, b) = sigma(ahi, bhi) * (-1)^(|ahi| |blo|) * lambda(alo, blo)
+//     (pairs (i in a, j in b, i > j): hi-hi, hi-lo = all of them, lo-hi = none, lo-lo; the metric factor
+//     splits the same way).  lambda and the parity factor depend on the lane: they are folded into the
+//     left value once per (ahi, alo).  sigma is warp-uniform: it is applied by toggling the sign bit of
+//     the right value with a mask that sits in the kernel parameters (a constant-bank operand), so a
+//     term costs one LOP3 and one DFMA.  sigma and lambda are READ FROM THE PLAN's term table and the
+//     factorisation is verified against every one of its 4^n coefficients before the engine is used.
 //
-// Arithmetic: one DFMA per term, terms of an output summed in ascending left-blade order (not the
-// reference's order): FMA arithmetic only, like the other dense lowerings; GAAST_ARITH_STRICT keeps
-// using the table engine.  Only plans that ARE a full product of two batch inputs qualify
-// (dense_warp_analyse); everything else is untouched.
+// Arithmetic: one DFMA per term, terms of an output summed in (alo, ahi) order (not the reference's
+// order): FMA arithmetic only, like the other dense lowerings; GAAST_ARITH_STRICT keeps using the
+// table engine.  Only plans that ARE a full product of two batch inputs qualify (dense_warp_analyse);
+// everything else is untouched.
 #include <algorithm>
 #include <cstring>
 
@@ -33,12 +41,15 @@ namespace gaast {
 namespace {
 
 
+constexpr int kMaxJ = 32;  // n = 10
+
 struct DenseWarpArgs {
     const uint16_t* blade_of_slot;  // [2^n] blade bitmask of every slot (grades ascending, masks ascending)
-    const uint32_t* sign_words;     // [2^n][J]: bit (b & 31) of word [a][b >> 5] set = coefficient of (a, b) is -1
     int n, T, LD;                   // tile: T elements, row pitch LD = 2^n + 1 doubles
     int gstart[GAAST_MAX_DIM + 2];  // first slot of grade k
     int streamL[GAAST_MAX_DIM + 1], streamR[GAAST_MAX_DIM + 1], streamO[GAAST_MAX_DIM + 1];
+    unsigned lambda_words[32];      // bit blo of word alo set: lambda(alo, blo) = -1
+    unsigned toggle[kMaxJ * kMaxJ]; // [ahi * J + g]: 0x80000000 where sigma(ahi, g) != sigma(ahi - 1, g)  (sigma(-1, .) = +1)
 };
 
 __device__ __forceinline__ double flip_if(double v, unsigned bit) {  // bit in {0, 1}
@@ -46,8 +57,8 @@ __device__ __forceinline__ double flip_if(double v, unsigned bit) {  // bit in {
 }
 
 template <int J>
-__global__ void __launch_bounds__(512) dense_warp_kernel(const __grid_constant__ EvalArgs a,
-                                                         const __grid_constant__ DenseWarpArgs d) {
+__global__ void __launch_bounds__(J >= 32 ? 256 : 512) dense_warp_kernel(const __grid_constant__ EvalArgs a,
+                                                                         const __grid_constant__ DenseWarpArgs d) {
     extern __shared__ double sm[];
     constexpr int NB = 32 * J;  // 2^n blades
     const int T = d.T, LD = d.LD;
@@ -77,24 +88,25 @@ __global__ void __launch_bounds__(512) dense_warp_kernel(const __grid_constant__
             double acc[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) acc[j] = 0.0;
-#pragma unroll
-            for (int ahi = 0; ahi < J; ++ahi) {
 #pragma unroll 1
-                for (int alo = 0; alo < 32; ++alo) {
-                    const int ab = ahi * 32 + alo;
-                    const double xa = Ae[ab];       // broadcast
-                    const unsigned bl = alo ^ lane;  // this lane's member of every group
-                    const uint4* const wp = reinterpret_cast<const uint4*>(d.sign_words + size_t(ab) * J);
+            for (int alo = 0; alo < 32; ++alo) {
+                const unsigned bl = alo ^ lane;                        // this lane's member of every right group
+                const unsigned lam = (d.lambda_words[alo] >> bl) & 1u;  // lambda(alo, blo)
+                const unsigned par = __popc(bl) & 1u;                   // |blo| odd
+                // the J left values of this alo, lane-dependent signs folded in (once per left blade)
+                double xe[J];
 #pragma unroll
-                    for (int q = 0; q < J / 4; ++q) {
-                        const uint4 w4 = __ldg(wp + q);  // warp-uniform
-                        const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
+                for (int ahi = 0; ahi < J; ++ahi)
+                    xe[ahi] = flip_if(Ae[ahi * 32 + alo], (__builtin_popcount(ahi) & 1) ? (lam ^ par) : lam);  // broadcast reads
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int g = q * 4 + c;  // group of b; output group = ahi ^ g
-                            const double yb = Be[g * 32 + bl];
-                            acc[ahi ^ g] = fma(flip_if(xa, (w[c] >> bl) & 1u), yb, acc[ahi ^ g]);
-                        }
+                for (int g = 0; g < J; ++g) {
+                    double yb = Be[g * 32 + bl];  // conflict free: the 32 lanes read a permutation of one group
+#pragma unroll
+                    for (int ahi = 0; ahi < J; ++ahi) {
+                        // warp-uniform sign sigma(ahi, g): toggle the right value's sign bit in place (the mask is a
+                        // constant-bank operand; toggles accumulate from one ahi to the next)
+                        yb = __hiloint2double(__double2hiint(yb) ^ int(d.toggle[ahi * J + g]), __double2loint(yb));
+                        acc[ahi ^ g] = fma(xe[ahi], yb, acc[ahi ^ g]);
                     }
                 }
             }
@@ -154,8 +166,8 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
     std::vector<uint16_t> slot_of(NB);
     for (uint32_t s = 0; s < NB; ++s) slot_of[blade_of[s]] = uint16_t(s);
     const uint32_t J = NB / 32;
-    std::vector<uint32_t> words(size_t(NB) * J, 0);
-    std::vector<uint8_t> seen(size_t(NB) * NB / 8, 0);
+    // the whole coefficient table as sign bits [a][b] (it must be complete and +-1) ...
+    std::vector<uint8_t> seen(size_t(NB) * NB / 8, 0), neg(size_t(NB) * NB / 8, 0);
     for (uint32_t t = mul.term_begin; t < mul.term_begin + mul.term_count; ++t) {
         const gaast_term& tm = h.terms[t];
         if (tm.a >= NB || tm.b >= NB || tm.out >= NB) return false;
@@ -165,14 +177,39 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
         const size_t bit = size_t(ab) * NB + bb;
         if (seen[bit >> 3] >> (bit & 7) & 1) return false;
         seen[bit >> 3] |= uint8_t(1u << (bit & 7));
-        if (tm.coeff < 0) words[size_t(ab) * J + (bb >> 5)] |= 1u << (bb & 31);
+        if (tm.coeff < 0) neg[bit >> 3] |= uint8_t(1u << (bit & 7));
     }
+    auto is_neg = [&](uint32_t ab, uint32_t bb) {
+        const size_t bit = size_t(ab) * NB + bb;
+        return (neg[bit >> 3] >> (bit & 7) & 1) != 0;
+    };
+    // ... and its factorisation  c(a, b) = sigma(ahi, bhi) * (-1)^(|ahi| |blo|) * lambda(alo, blo),  verified term by term
+    std::vector<uint8_t> sigma(size_t(J) * J);
+    std::vector<uint32_t> lambda_words(32, 0);
+    for (uint32_t ah = 0; ah < J; ++ah)
+        for (uint32_t bh = 0; bh < J; ++bh) sigma[ah * J + bh] = is_neg(ah << 5, bh << 5);
+    for (uint32_t al = 0; al < 32; ++al)
+        for (uint32_t bl = 0; bl < 32; ++bl)
+            if (is_neg(al, bl)) lambda_words[al] |= 1u << bl;
+    for (uint32_t ab = 0; ab < NB; ++ab)
+        for (uint32_t bb = 0; bb < NB; ++bb) {
+            const uint32_t ah = ab >> 5, al = ab & 31, bh = bb >> 5, bl = bb & 31;
+            const bool chi = (__builtin_popcount(ah) & __builtin_popcount(bl) & 1) != 0;
+            const bool want = bool(sigma[ah * J + bh]) ^ chi ^ bool(lambda_words[al] >> bl & 1);
+            if (want != is_neg(ab, bb)) return false;
+        }
     if (out) {
         out->n = n;
         out->slotL = slotL;
         out->slotR = slotR;
         out->blade_of_slot = std::move(blade_of);
-        out->sign_words = std::move(words);
+        out->lambda_words = std::move(lambda_words);
+        out->toggle.assign(size_t(J) * J, 0);
+        for (uint32_t ah = 0; ah < J; ++ah)
+            for (uint32_t g = 0; g < J; ++g) {
+                const bool prev = ah ? bool(sigma[(ah - 1) * J + g]) : false;
+                out->toggle[ah * J + g] = (bool(sigma[ah * J + g]) != prev) ? 0x80000000u : 0u;
+            }
         out->gstart = std::move(gstart);
     }
     return true;
@@ -196,12 +233,12 @@ DenseWarpLaunch dense_warp_shape(const gaast_ctx& ctx, uint32_t n, long long bat
 }
 
 cudaError_t dense_warp_launch(const EvalArgs& args, const DenseWarpHost& hplan, const DevicePlanHost& h,
-                              const uint16_t* d_blade_of_slot, const uint32_t* d_sign_words, const DenseWarpLaunch& shape,
-                              cudaStream_t stream) {
+                              const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaStream_t stream) {
     DenseWarpArgs d;
     std::memset(&d, 0, sizeof d);
     d.blade_of_slot = d_blade_of_slot;
-    d.sign_words = d_sign_words;
+    for (int i = 0; i < 32; ++i) d.lambda_words[i] = hplan.lambda_words[size_t(i)];
+    for (size_t i = 0; i < hplan.toggle.size(); ++i) d.toggle[i] = hplan.toggle[i];
     d.n = int(hplan.n);
     d.T = shape.T;
     d.LD = shape.LD;

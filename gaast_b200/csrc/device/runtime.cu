@@ -240,7 +240,6 @@ gaast_status gaast_plan_destroy(gaast_plan* plan) {
             cudaFree(plan->d_ws);
             cudaFree(plan->d_uniform);
             cudaFree(plan->d_dw_blades);
-            cudaFree(plan->d_dw_signs);
         }
         delete plan;
     });
@@ -512,7 +511,6 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
             plan->dense_warp_state = gaast::dense_warp_analyse(h, &plan->dense_warp) ? 1 : -1;
             if (plan->dense_warp_state == 1) {
                 upload(plan->d_dw_blades, plan->dense_warp.blade_of_slot, ctx->stream);
-                upload(plan->d_dw_signs, plan->dense_warp.sign_words, ctx->stream);
             }
         }
         return plan->dense_warp_state == 1;
@@ -573,7 +571,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     if (use_dense_warp) {
         const gaast::DenseWarpLaunch shape = gaast::dense_warp_shape(*ctx, h.n, n);
         grid = shape.grid;
-        cuda_check(gaast::dense_warp_launch(a, plan->dense_warp, h, plan->d_dw_blades, plan->d_dw_signs, shape, ctx->stream),
+        cuda_check(gaast::dense_warp_launch(a, plan->dense_warp, h, plan->d_dw_blades, shape, ctx->stream),
                    "launch dense-warp engine");
         ctx->launches++;
         char desc[256];

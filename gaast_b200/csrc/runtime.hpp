@@ -100,7 +100,8 @@ const char* table_engine_arch();
 struct DenseWarpHost {
     uint32_t n = 0, slotL = 0, slotR = 0;
     std::vector<uint16_t> blade_of_slot;  // [2^n]
-    std::vector<uint32_t> sign_words;     // [2^n][2^n / 32]
+    std::vector<uint32_t> lambda_words;   // [32]: bit blo of word alo = lambda(alo, blo) is -1
+    std::vector<uint32_t> toggle;         // [J][J], J = 2^n / 32: sign-bit masks that step sigma(ahi - 1, g) to sigma(ahi, g)
     std::vector<int> gstart;              // first slot of grade k
 };
 struct DenseWarpLaunch {
@@ -110,8 +111,7 @@ struct DenseWarpLaunch {
 bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out);
 DenseWarpLaunch dense_warp_shape(const gaast_ctx& ctx, uint32_t n, long long batch);
 cudaError_t dense_warp_launch(const EvalArgs& args, const DenseWarpHost& hplan, const DevicePlanHost& h,
-                              const uint16_t* d_blade_of_slot, const uint32_t* d_sign_words, const DenseWarpLaunch& shape,
-                              cudaStream_t stream);
+                              const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaStream_t stream);
 
 // host_pipeline.cu
 struct HostPipe;
@@ -165,5 +165,4 @@ struct gaast_plan {
     int dense_warp_state = 0;
     gaast::DenseWarpHost dense_warp;
     uint16_t* d_dw_blades = nullptr;
-    uint32_t* d_dw_signs = nullptr;
 };
