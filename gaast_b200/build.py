@@ -38,7 +38,7 @@ SOURCES = [
     "device/runtime.cu",
     "device/host_pipeline.cu",
 ]
-HEADERS = ["common.hpp", "device_plan.hpp", "runtime.hpp", "eval_args.h", "host/host.hpp",
+HEADERS = ["common.hpp", "device_plan.hpp", "runtime.hpp", "eval_args.h", "host/host.hpp", "device/dense_warp_kernel.h",
            "../../include/gaast_b200.h", "../../include/gaast_b200_host.h"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -51,6 +51,13 @@ def _write_args_text():
     src = os.path.join(CSRC, "eval_args.h")
     dst = os.path.join(CSRC, "eval_args_text.inc")
     text = 'R"GAASTARGS(' + open(src).read() + ')GAASTARGS"\n'
+    if not os.path.exists(dst) or open(dst).read() != text:
+        with open(dst, "w") as f:
+            f.write(text)
+    # the dense-warp device code, pasted into the per-plan source NVRTC compiles
+    src = os.path.join(CSRC, "device", "dense_warp_kernel.h")
+    dst = os.path.join(CSRC, "device", "dense_warp_kernel_text.inc")
+    text = 'R"GAASTDW(' + open(src).read() + ')GAASTDW"\n'
     if not os.path.exists(dst) or open(dst).read() != text:
         with open(dst, "w") as f:
             f.write(text)

@@ -41,90 +41,21 @@ namespace gaast {
 namespace {
 
 
-constexpr int kMaxJ = 32;  // n = 10
-
-struct DenseWarpArgs {
-    const uint16_t* blade_of_slot;  // [2^n] blade bitmask of every slot (grades ascending, masks ascending)
-    int n, T, LD;                   // tile: T elements, row pitch LD = 2^n + 1 doubles
-    int gstart[GAAST_MAX_DIM + 2];  // first slot of grade k
-    int streamL[GAAST_MAX_DIM + 1], streamR[GAAST_MAX_DIM + 1], streamO[GAAST_MAX_DIM + 1];
-    unsigned lambda_words[32];      // bit blo of word alo set: lambda(alo, blo) = -1
-    unsigned toggle[kMaxJ * kMaxJ]; // [ahi * J + g]: 0x80000000 where sigma(ahi, g) != sigma(ahi - 1, g)  (sigma(-1, .) = +1)
-};
-
-__device__ __forceinline__ double flip_if(double v, unsigned bit) {  // bit in {0, 1}
-    return __hiloint2double(__double2hiint(v) ^ int(bit << 31), __double2loint(v));
-}
+#include "dense_warp_kernel.h"
 
 template <int J>
 __global__ void __launch_bounds__(J >= 32 ? 256 : 512) dense_warp_kernel(const __grid_constant__ EvalArgs a,
                                                                          const __grid_constant__ DenseWarpArgs d) {
-    extern __shared__ double sm[];
-    constexpr int NB = 32 * J;  // 2^n blades
-    const int T = d.T, LD = d.LD;
-    double* const A = sm;
-    double* const B = sm + size_t(T) * LD;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    // tile traffic: `per` rows of T consecutive elements per warp instruction
-    const int per = 32 / T, te = lane % T, tr = lane / T;
-    const long long n_tiles = (a.n + T - 1) / T;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long e0 = tile * T;
-        const int cnt = int(a.n - e0 < T ? a.n - e0 : T);
-        // ---- stage both operands: coalesced rows in, [element][blade] out (graded.rs:46 per grade) ----
-        for (int r = warp * per + tr; r < NB; r += n_warps * per) {
-            const int blade = d.blade_of_slot[r];
-            const int k = __popc(blade), row = r - d.gstart[k];
-            if (te < cnt) {
-                A[te * LD + blade] = __ldg(a.sptr[d.streamL[k]] + (long long)row * a.srow[d.streamL[k]] + e0 + te);
-                B[te * LD + blade] = __ldg(a.sptr[d.streamR[k]] + (long long)row * a.srow[d.streamR[k]] + e0 + te);
-            }
-        }
-        __syncthreads();
-        // ---- one warp per multivector ----
-        for (int e = warp; e < cnt; e += n_warps) {
-            double* const Ae = A + e * LD;
-            const double* const Be = B + e * LD;
-            double acc[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) acc[j] = 0.0;
-#pragma unroll 1
-            for (int alo = 0; alo < 32; ++alo) {
-                const unsigned bl = alo ^ lane;                        // this lane's member of every right group
-                const unsigned lam = (d.lambda_words[alo] >> bl) & 1u;  // lambda(alo, blo)
-                const unsigned par = __popc(bl) & 1u;                   // |blo| odd
-                // the J left values of this alo, lane-dependent signs folded in (once per left blade)
-                double xe[J];
-#pragma unroll
-                for (int ahi = 0; ahi < J; ++ahi)
-                    xe[ahi] = flip_if(Ae[ahi * 32 + alo], (__builtin_popcount(ahi) & 1) ? (lam ^ par) : lam);  // broadcast reads
-#pragma unroll
-                for (int g = 0; g < J; ++g) {
-                    double yb = Be[g * 32 + bl];  // conflict free: the 32 lanes read a permutation of one group
-#pragma unroll
-                    for (int ahi = 0; ahi < J; ++ahi) {
-                        // warp-uniform sign sigma(ahi, g): toggle the right value's sign bit in place (the mask is a
-                        // constant-bank operand; toggles accumulate from one ahi to the next)
-                        yb = __hiloint2double(__double2hiint(yb) ^ int(d.toggle[ahi * J + g]), __double2loint(yb));
-                        acc[ahi ^ g] = fma(xe[ahi], yb, acc[ahi ^ g]);
-                    }
-                }
-            }
-            __syncwarp();  // every lane has read all of Ae: the element's results replace its left operand
-#pragma unroll
-            for (int j = 0; j < J; ++j) Ae[j * 32 + lane] = acc[j];
-        }
-        __syncthreads();
-        // ---- results out: [element][blade] -> coalesced rows of the root's grade arrays ----
-        if (a.store_out)
-            for (int r = warp * per + tr; r < NB; r += n_warps * per) {
-                const int blade = d.blade_of_slot[r];
-                const int k = __popc(blade), row = r - d.gstart[k];
-                if (te < cnt) a.sptr[d.streamO[k]][(long long)row * a.srow[d.streamO[k]] + e0 + te] = A[te * LD + blade];
-            }
-        __syncthreads();
-    }
+    dense_warp_body<J>(a, d);
 }
+
+// the same device code as text, for the per-plan kernels NVRTC builds (sigma folded at compile time)
+const char kDenseWarpKernelText[] =
+#include "dense_warp_kernel_text.inc"
+    ;
+const char kEvalArgsTextDw[] =
+#include "../eval_args_text.inc"
+    ;
 
 }  // namespace
 
@@ -204,6 +135,7 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
         out->slotR = slotR;
         out->blade_of_slot = std::move(blade_of);
         out->lambda_words = std::move(lambda_words);
+        out->sigma = sigma;
         out->toggle.assign(size_t(J) * J, 0);
         for (uint32_t ah = 0; ah < J; ++ah)
             for (uint32_t g = 0; g < J; ++g) {
@@ -232,8 +164,33 @@ DenseWarpLaunch dense_warp_shape(const gaast_ctx& ctx, uint32_t n, long long bat
     return s;
 }
 
+// CUDA source of the per-plan kernel: the shared device code with sigma as a compile-time table.
+CodegenResult dense_warp_codegen(const DenseWarpHost& hp, const DenseWarpLaunch& shape) {
+    const uint32_t J = (1u << hp.n) / 32;
+    std::string src = "// generated by gaast_b200: dense-warp kernel for a full product in G(n), n=" + std::to_string(hp.n) +
+                      ", sigma folded at compile time\n";
+    src += kEvalArgsTextDw;
+    src += "\nusing gaast::EvalArgs;\n#define GAAST_DW_J " + std::to_string(J) + "\n";
+    src += "__device__ constexpr unsigned char kDwSigma[" + std::to_string(J * J) + "] = {";
+    for (size_t i = 0; i < hp.sigma.size(); ++i) src += (i ? "," : "") + std::to_string(int(hp.sigma[i]));
+    src += "};\n#define GAAST_DW_SIGMA_NEG(ahi, g) (kDwSigma[(ahi) * GAAST_DW_J + (g)] != 0)\n";
+    src += kDenseWarpKernelText;
+    src += "\nextern \"C\" __global__ void __launch_bounds__(" + std::to_string(shape.threads) +
+           ") gaast_dense_warp(const __grid_constant__ EvalArgs a, const __grid_constant__ DenseWarpArgs d) {\n"
+           "  dense_warp_body<GAAST_DW_J>(a, d);\n}\n";
+    CodegenResult cg;
+    cg.source = std::move(src);
+    cg.kernel_name = "gaast_dense_warp";
+    cg.threads = shape.threads;
+    cg.smem_bytes = shape.smem;
+    cg.notes = "dense-warp(n=" + std::to_string(hp.n) + ")";
+    return cg;
+}
+
+// `jit_kernel`: the per-plan kernel (sigma compile-time), or null for the generic kernel of this library.
 cudaError_t dense_warp_launch(const EvalArgs& args, const DenseWarpHost& hplan, const DevicePlanHost& h,
-                              const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaStream_t stream) {
+                              const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaKernel_t jit_kernel,
+                              cudaStream_t stream) {
     DenseWarpArgs d;
     std::memset(&d, 0, sizeof d);
     d.blade_of_slot = d_blade_of_slot;
@@ -247,6 +204,11 @@ cudaError_t dense_warp_launch(const EvalArgs& args, const DenseWarpHost& hplan, 
         d.streamL[k] = h.stream_of(hplan.slotL, k);
         d.streamR[k] = h.stream_of(hplan.slotR, k);
         d.streamO[k] = int(h.n_in_streams + k);  // the root holds every grade, ascending
+    }
+    if (jit_kernel) {
+        void* params[] = {const_cast<EvalArgs*>(&args), &d};
+        return cudaLaunchKernel(reinterpret_cast<const void*>(jit_kernel), dim3(shape.grid), dim3(shape.threads), params,
+                                shape.smem, stream);
     }
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shape.smem));

@@ -240,6 +240,7 @@ gaast_status gaast_plan_destroy(gaast_plan* plan) {
             cudaFree(plan->d_ws);
             cudaFree(plan->d_uniform);
             cudaFree(plan->d_dw_blades);
+            plan->dw_jit.clear();
         }
         delete plan;
     });
@@ -318,7 +319,20 @@ gaast_status gaast_plan_precompile_typed(gaast_plan* plan, uint64_t broadcast_sl
         opt.f32 = dtype == GAAST_F32;
         gaast::CodegenResult cg;
         std::string key, origin;
-        gaast::build_specialized(plan->h, opt, &cg, &key, &origin);
+        try {
+            gaast::build_specialized(plan->h, opt, &cg, &key, &origin);
+        } catch (const Error&) {
+            // too large / too wide to specialise: a full high-dimensional product gets its dense-warp kernel instead
+            gaast::DenseWarpHost dw;
+            if (opt.f32 || opt.with_sum || arith != GAAST_ARITH_FMA || !gaast::dense_warp_analyse(plan->h, &dw)) throw;
+            gaast_ctx fake;  // offline: the launch shape of a B200 (227 KB of shared memory per block, 148 SMs)
+            fake.sm_count = 148;
+            fake.smem_optin = 232448;
+            const gaast::DenseWarpLaunch shape = gaast::dense_warp_shape(fake, plan->h.n, 1 << 20);
+            cg = gaast::dense_warp_codegen(dw, shape);
+            std::string log;
+            gaast::jit_cubin(cg, &key, &origin, &log);
+        }
         plan->last_kernel = cg.kernel_name + " key=" + key + " origin=" + origin + " " + cg.notes;
     });
 }
@@ -571,12 +585,35 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     if (use_dense_warp) {
         const gaast::DenseWarpLaunch shape = gaast::dense_warp_shape(*ctx, h.n, n);
         grid = shape.grid;
-        cuda_check(gaast::dense_warp_launch(a, plan->dense_warp, h, plan->d_dw_blades, shape, ctx->stream),
+        // per-plan kernel (the warp-uniform signs folded at compile time) when NVRTC or the cache has it,
+        // else the generic kernel compiled into the library
+        std::shared_ptr<gaast::JitKernel> dwk;
+        if (!plan->dw_jit_failed && !std::getenv("GAAST_DENSE_WARP_GENERIC")) {
+            auto it = plan->dw_jit.find(shape.threads);
+            if (it != plan->dw_jit.end()) {
+                dwk = it->second;
+            } else {
+                try {
+                    gaast::CodegenResult cg = gaast::dense_warp_codegen(plan->dense_warp, shape);
+                    std::string key, origin, log;
+                    std::vector<char> cubin = gaast::jit_cubin(cg, &key, &origin, &log);
+                    dwk = gaast::jit_load(cg, cubin);
+                    dwk->key = key;
+                    dwk->origin = origin;
+                    plan->dw_jit.emplace(shape.threads, dwk);
+                } catch (const Error&) {
+                    plan->dw_jit_failed = true;
+                }
+            }
+        }
+        cuda_check(gaast::dense_warp_launch(a, plan->dense_warp, h, plan->d_dw_blades, shape, dwk ? dwk->kernel : nullptr,
+                                            ctx->stream),
                    "launch dense-warp engine");
         ctx->launches++;
-        char desc[256];
-        std::snprintf(desc, sizeof desc, "dense_warp_kernel engine=dense_warp grid=%d block=%d smem=%zu tile=%d elements",
-                      grid, shape.threads, shape.smem, shape.T);
+        char desc[320];
+        std::snprintf(desc, sizeof desc, "%s engine=dense_warp origin=%s grid=%d block=%d smem=%zu tile=%d elements regs=%d",
+                      dwk ? "gaast_dense_warp" : "dense_warp_kernel", dwk ? dwk->origin.c_str() : "library", grid, shape.threads,
+                      shape.smem, shape.T, dwk ? dwk->regs : 0);
         plan->last_kernel = desc;
     } else if (jk) {
         const long long per_block = (long long)jk->threads * jk->elems_per_thread;

@@ -102,6 +102,7 @@ struct DenseWarpHost {
     std::vector<uint16_t> blade_of_slot;  // [2^n]
     std::vector<uint32_t> lambda_words;   // [32]: bit blo of word alo = lambda(alo, blo) is -1
     std::vector<uint32_t> toggle;         // [J][J], J = 2^n / 32: sign-bit masks that step sigma(ahi - 1, g) to sigma(ahi, g)
+    std::vector<uint8_t> sigma;           // [J][J]: 1 = sigma(ahi, bhi) is -1
     std::vector<int> gstart;              // first slot of grade k
 };
 struct DenseWarpLaunch {
@@ -111,7 +112,9 @@ struct DenseWarpLaunch {
 bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out);
 DenseWarpLaunch dense_warp_shape(const gaast_ctx& ctx, uint32_t n, long long batch);
 cudaError_t dense_warp_launch(const EvalArgs& args, const DenseWarpHost& hplan, const DevicePlanHost& h,
-                              const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaStream_t stream);
+                              const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaKernel_t jit_kernel,
+                              cudaStream_t stream);
+CodegenResult dense_warp_codegen(const DenseWarpHost& hp, const DenseWarpLaunch& shape);
 
 // host_pipeline.cu
 struct HostPipe;
@@ -165,4 +168,6 @@ struct gaast_plan {
     int dense_warp_state = 0;
     gaast::DenseWarpHost dense_warp;
     uint16_t* d_dw_blades = nullptr;
+    std::map<int, std::shared_ptr<gaast::JitKernel>> dw_jit;  // per block size: the kernel with sigma folded in
+    bool dw_jit_failed = false;  // NVRTC unavailable: keep using the generic kernel
 };
