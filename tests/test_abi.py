@@ -89,3 +89,20 @@ def test_huge_plans_are_left_to_the_table_engine():
     with pytest.raises(g.GaastError) as ei:
         plan.kernel_source()
     assert ei.value.status == L.ERR_JIT and "table engine" in str(ei.value)
+
+
+def test_offline_precompile_of_a_dense_warp_plan():
+    """A full product in G(7): too wide for the specialised engine, so the build-time precompile step
+    analyses it for the dense-warp engine (term table complete, +-1, factorisation verified) and compiles
+    that kernel with NVRTC -- all without a device.  A degenerate metric does not qualify."""
+    from gaast_b200.device import Plan
+    from gaast_b200.expr import Input, mv as pmv
+    full = tuple(range(8))
+    a, b = pmv(Input(0, full)), pmv(Input(1, full))
+    plan = Plan(None, (a * b).specialize([1.0, 1.0, 1.0, 1.0, -1.0, -1.0, 1.0]))
+    info = plan.precompile(0, L.ARITH_FMA, False, True)
+    assert "gaast_dense_warp" in info and "dense-warp(n=7)" in info
+    bad = Plan(None, (a * b).specialize([1.0] * 6 + [0.0]))
+    with pytest.raises(L.GaastError) as ei:
+        bad.precompile(0, L.ARITH_FMA, False, True)
+    assert ei.value.status == L.ERR_JIT
