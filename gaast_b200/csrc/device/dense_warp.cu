@@ -70,7 +70,9 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
         if (m != full) return false;
     const gaast_op &o0 = h.ops[0], &o1 = h.ops[1], &mul = h.ops[2];
     if (o0.kind != GAAST_OP_ADD_INPUT || o1.kind != GAAST_OP_ADD_INPUT || mul.kind != GAAST_OP_MUL_TERMS) return false;
-    if (mul.dst != 0 || mul.a == 0 || mul.b == 0 || mul.a == mul.b || mul.term_count != uint64_t(NB) * NB) return false;
+    if (mul.dst != 0 || mul.a == 0 || mul.b == 0 || mul.a == mul.b || mul.term_count > uint64_t(NB) * NB ||
+        mul.term_count < uint64_t(NB))
+        return false;
     auto input_of = [&](uint32_t buf, uint32_t* slot) {
         const gaast_op* src = o0.dst == buf ? &o0 : (o1.dst == buf ? &o1 : nullptr);
         if (!src || src->mask != full) return false;
@@ -110,23 +112,41 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
         seen[bit >> 3] |= uint8_t(1u << (bit & 7));
         if (tm.coeff < 0) neg[bit >> 3] |= uint8_t(1u << (bit & 7));
     }
-    auto is_neg = [&](uint32_t ab, uint32_t bb) {
+    auto bit_of = [&](const std::vector<uint8_t>& v, uint32_t ab, uint32_t bb) {
         const size_t bit = size_t(ab) * NB + bb;
-        return (neg[bit >> 3] >> (bit & 7) & 1) != 0;
+        return (v[bit >> 3] >> (bit & 7) & 1) != 0;
     };
-    // ... and its factorisation  c(a, b) = sigma(ahi, bhi) * (-1)^(|ahi| |blo|) * lambda(alo, blo),  verified term by term
-    std::vector<uint8_t> sigma(size_t(J) * J);
-    std::vector<uint32_t> lambda_words(32, 0);
+    auto is_neg = [&](uint32_t ab, uint32_t bb) { return bit_of(neg, ab, bb); };
+    auto present = [&](uint32_t ab, uint32_t bb) { return bit_of(seen, ab, bb); };
+    // Which pairs does the product keep?  A geometric product keeps all of them; outer products and
+    // contractions keep (a, b) iff a rule on the HIGH parts and the same rule on the LOW parts both hold
+    // (a & b == 0, a subset of b, ...).  That is the shape this engine can use:
+    //     present(a, b) = keep_hi(ahi, bhi) & keep_lo(alo, blo)
+    // and, on the kept pairs,   c(a, b) = sigma(ahi, bhi) * (-1)^(|ahi| |blo|) * lambda(alo, blo).
+    // Both are read from the plan's term table and verified pair by pair.
+    if (!present(0, 0)) return false;
+    std::vector<uint8_t> sigma(size_t(J) * J);  // 0 = +1, 1 = -1, 2 = pair of high parts dropped
+    std::vector<uint32_t> lambda_words(32, 0), present_words(32, 0);
+    bool complete = true;
     for (uint32_t ah = 0; ah < J; ++ah)
-        for (uint32_t bh = 0; bh < J; ++bh) sigma[ah * J + bh] = is_neg(ah << 5, bh << 5);
+        for (uint32_t bh = 0; bh < J; ++bh)
+            sigma[ah * J + bh] = present(ah << 5, bh << 5) ? uint8_t(is_neg(ah << 5, bh << 5)) : uint8_t(2);
     for (uint32_t al = 0; al < 32; ++al)
-        for (uint32_t bl = 0; bl < 32; ++bl)
-            if (is_neg(al, bl)) lambda_words[al] |= 1u << bl;
+        for (uint32_t bl = 0; bl < 32; ++bl) {
+            if (present(al, bl)) present_words[al] |= 1u << bl;
+            if (present(al, bl) && is_neg(al, bl)) lambda_words[al] |= 1u << bl;
+        }
     for (uint32_t ab = 0; ab < NB; ++ab)
         for (uint32_t bb = 0; bb < NB; ++bb) {
             const uint32_t ah = ab >> 5, al = ab & 31, bh = bb >> 5, bl = bb & 31;
+            const bool keep = sigma[ah * J + bh] != 2 && (present_words[al] >> bl & 1);
+            if (keep != present(ab, bb)) return false;
+            if (!keep) {
+                complete = false;
+                continue;
+            }
             const bool chi = (__builtin_popcount(ah) & __builtin_popcount(bl) & 1) != 0;
-            const bool want = bool(sigma[ah * J + bh]) ^ chi ^ bool(lambda_words[al] >> bl & 1);
+            const bool want = bool(sigma[ah * J + bh] == 1) ^ chi ^ bool(lambda_words[al] >> bl & 1);
             if (want != is_neg(ab, bb)) return false;
         }
     if (out) {
@@ -135,12 +155,14 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
         out->slotR = slotR;
         out->blade_of_slot = std::move(blade_of);
         out->lambda_words = std::move(lambda_words);
+        out->present_words = std::move(present_words);
         out->sigma = sigma;
+        out->complete = complete;  // the library's generic kernel handles complete tables only
         out->toggle.assign(size_t(J) * J, 0);
         for (uint32_t ah = 0; ah < J; ++ah)
             for (uint32_t g = 0; g < J; ++g) {
-                const bool prev = ah ? bool(sigma[(ah - 1) * J + g]) : false;
-                out->toggle[ah * J + g] = (bool(sigma[ah * J + g]) != prev) ? 0x80000000u : 0u;
+                const bool prev = ah ? sigma[(ah - 1) * J + g] == 1 : false;
+                out->toggle[ah * J + g] = ((sigma[ah * J + g] == 1) != prev) ? 0x80000000u : 0u;
             }
         out->gstart = std::move(gstart);
     }
@@ -173,7 +195,8 @@ CodegenResult dense_warp_codegen(const DenseWarpHost& hp, const DenseWarpLaunch&
     src += "\nusing gaast::EvalArgs;\n#define GAAST_DW_J " + std::to_string(J) + "\n";
     src += "__device__ constexpr unsigned char kDwSigma[" + std::to_string(J * J) + "] = {";
     for (size_t i = 0; i < hp.sigma.size(); ++i) src += (i ? "," : "") + std::to_string(int(hp.sigma[i]));
-    src += "};\n#define GAAST_DW_SIGMA_NEG(ahi, g) (kDwSigma[(ahi) * GAAST_DW_J + (g)] != 0)\n";
+    src += "};\n#define GAAST_DW_SIGMA_NEG(ahi, g) (kDwSigma[(ahi) * GAAST_DW_J + (g)] == 1)\n"
+           "#define GAAST_DW_SIGMA_ABSENT(ahi, g) (kDwSigma[(ahi) * GAAST_DW_J + (g)] == 2)\n";
     src += kDenseWarpKernelText;
     src += "\nextern \"C\" __global__ void __launch_bounds__(" + std::to_string(shape.threads) +
            ") gaast_dense_warp(const __grid_constant__ EvalArgs a, const __grid_constant__ DenseWarpArgs d) {\n"
@@ -195,6 +218,8 @@ cudaError_t dense_warp_launch(const EvalArgs& args, const DenseWarpHost& hplan, 
     std::memset(&d, 0, sizeof d);
     d.blade_of_slot = d_blade_of_slot;
     for (int i = 0; i < 32; ++i) d.lambda_words[i] = hplan.lambda_words[size_t(i)];
+    for (int i = 0; i < 32; ++i) d.present_words[i] = hplan.present_words[size_t(i)];
+    if (!jit_kernel && !hplan.complete) return cudaErrorNotSupported;  // (the caller checks: see runtime.cu)
     for (size_t i = 0; i < hplan.toggle.size(); ++i) d.toggle[i] = hplan.toggle[i];
     d.n = int(hplan.n);
     d.T = shape.T;

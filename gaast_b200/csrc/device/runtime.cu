@@ -518,23 +518,45 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         return;
     }
 
-    // dense-warp engine: usable for this call?  (full product plan, f64, FMA arithmetic, per-element operands)
+    // dense-warp engine: the per-plan kernel (warp-uniform signs folded at compile time) when NVRTC or the
+    // cache has it, else null = the generic kernel compiled into the library
+    auto dense_warp_kernel_for = [&](const gaast::DenseWarpLaunch& shape) -> std::shared_ptr<gaast::JitKernel> {
+        if (plan->dw_jit_failed || std::getenv("GAAST_DENSE_WARP_GENERIC")) return nullptr;
+        auto it = plan->dw_jit.find(shape.threads);
+        if (it != plan->dw_jit.end()) return it->second;
+        try {
+            gaast::CodegenResult cg = gaast::dense_warp_codegen(plan->dense_warp, shape);
+            std::string key, origin, log;
+            std::vector<char> cubin = gaast::jit_cubin(cg, &key, &origin, &log);
+            auto k = gaast::jit_load(cg, cubin);
+            k->key = key;
+            k->origin = origin;
+            plan->dw_jit.emplace(shape.threads, k);
+            return k;
+        } catch (const Error&) {
+            plan->dw_jit_failed = true;
+            return nullptr;
+        }
+    };
+    // usable for this call?  (a dense product plan, f64, FMA arithmetic, per-element operands)
     auto dense_warp_ready = [&]() {
         if (with_sum || f32 || arith != GAAST_ARITH_FMA || bslots != 0 || !out) return false;
         if (plan->dense_warp_state == 0) {
             plan->dense_warp_state = gaast::dense_warp_analyse(h, &plan->dense_warp) ? 1 : -1;
-            if (plan->dense_warp_state == 1) {
-                upload(plan->d_dw_blades, plan->dense_warp.blade_of_slot, ctx->stream);
-            }
+            if (plan->dense_warp_state == 1) upload(plan->d_dw_blades, plan->dense_warp.blade_of_slot, ctx->stream);
         }
-        return plan->dense_warp_state == 1;
+        if (plan->dense_warp_state != 1) return false;
+        // products that drop pairs (outer products, contractions) need the per-plan kernel
+        if (!plan->dense_warp.complete && !dense_warp_kernel_for(gaast::dense_warp_shape(*ctx, h.n, n))) return false;
+        return true;
     };
     bool use_dense_warp = false;
     if (engine == GAAST_ENGINE_DENSE_WARP) {
         if (!dense_warp_ready())
             throw Error(GAAST_ERR_UNSUPPORTED,
-                        "dense-warp engine: the plan is not a full product of two per-element f64 batch inputs in G(n), "
-                        "7 <= n <= 10, with a +-1 metric, evaluated in FMA arithmetic without batch-sum");
+                        "dense-warp engine: the plan is not ONE product (geometric, outer, contraction) of two full-grade "
+                        "per-element f64 batch inputs in G(n), 7 <= n <= 10, with a +-1 metric, evaluated in FMA "
+                        "arithmetic without batch-sum");
         use_dense_warp = true;
     }
 
@@ -585,27 +607,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     if (use_dense_warp) {
         const gaast::DenseWarpLaunch shape = gaast::dense_warp_shape(*ctx, h.n, n);
         grid = shape.grid;
-        // per-plan kernel (the warp-uniform signs folded at compile time) when NVRTC or the cache has it,
-        // else the generic kernel compiled into the library
-        std::shared_ptr<gaast::JitKernel> dwk;
-        if (!plan->dw_jit_failed && !std::getenv("GAAST_DENSE_WARP_GENERIC")) {
-            auto it = plan->dw_jit.find(shape.threads);
-            if (it != plan->dw_jit.end()) {
-                dwk = it->second;
-            } else {
-                try {
-                    gaast::CodegenResult cg = gaast::dense_warp_codegen(plan->dense_warp, shape);
-                    std::string key, origin, log;
-                    std::vector<char> cubin = gaast::jit_cubin(cg, &key, &origin, &log);
-                    dwk = gaast::jit_load(cg, cubin);
-                    dwk->key = key;
-                    dwk->origin = origin;
-                    plan->dw_jit.emplace(shape.threads, dwk);
-                } catch (const Error&) {
-                    plan->dw_jit_failed = true;
-                }
-            }
-        }
+        std::shared_ptr<gaast::JitKernel> dwk = dense_warp_kernel_for(shape);
         cuda_check(gaast::dense_warp_launch(a, plan->dense_warp, h, plan->d_dw_blades, shape, dwk ? dwk->kernel : nullptr,
                                             ctx->stream),
                    "launch dense-warp engine");

@@ -102,7 +102,9 @@ struct DenseWarpHost {
     std::vector<uint16_t> blade_of_slot;  // [2^n]
     std::vector<uint32_t> lambda_words;   // [32]: bit blo of word alo = lambda(alo, blo) is -1
     std::vector<uint32_t> toggle;         // [J][J], J = 2^n / 32: sign-bit masks that step sigma(ahi - 1, g) to sigma(ahi, g)
-    std::vector<uint8_t> sigma;           // [J][J]: 1 = sigma(ahi, bhi) is -1
+    std::vector<uint32_t> present_words;  // [32]: bit blo of word alo = the product keeps the pair (alo, blo)
+    std::vector<uint8_t> sigma;           // [J][J]: 0 = +1, 1 = -1, 2 = the product drops the pair of high parts
+    bool complete = true;                 // every pair kept (geometric product): the generic kernel can run it
     std::vector<int> gstart;              // first slot of grade k
 };
 struct DenseWarpLaunch {

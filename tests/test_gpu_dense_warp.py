@@ -65,7 +65,8 @@ def test_dense_warp_refuses_other_plans(ctx):
     full = tuple(range(n + 1))
     a, b = pmv(Input(0, full)), pmv(Input(1, full))
     dev = [g.DeviceBatch.alloc(ctx, n, full, 64) for _ in range(2)]
-    for ast in ((a ^ b).specialize([1.0] * n),                      # not a full product
+    for ast in (((a * b) + a).specialize([1.0] * n),                # more than one product of two inputs
+                (a * b).g(2).specialize([1.0] * n),                  # the root is not the full grade set
                 (a * b).specialize([1.0] * 6 + [0.0]),               # degenerate metric: zero coefficients
                 (a * b).specialize([1.0] * 6 + [2.0])):              # scaled metric: |coefficient| != 1
         plan = g.Plan(ctx, ast)
@@ -83,3 +84,26 @@ def test_dense_warp_refuses_other_plans(ctx):
     d32 = [g.DeviceBatch.alloc(ctx, n, full, 64, dtype=L.F32) for _ in range(2)]
     with pytest.raises(g.GaastError):
         plan.eval(d32, engine=L.ENGINE_DENSE_WARP)
+
+
+@pytest.mark.parametrize("kind", ["outer", "lcontract", "rcontract"])
+def test_dense_warp_products_that_drop_pairs(ctx, kind):
+    """Outer product and contractions of two full multivectors in G(10): 59 049 kept pairs out of 2^20 --
+    too many terms to specialise.  The kept pairs factorise over (high part, low part), so the per-plan
+    dense-warp kernel skips dropped high pairs at compile time and zeroes dropped low pairs per lane."""
+    n, batch = 10, 11
+    metric = [1.0] * 7 + [-1.0] * 3
+    full = tuple(range(n + 1))
+    rng = np.random.default_rng(77)
+    host = [{k: rng.uniform(-1, 1, (comb(n, k), batch)) for k in full} for _ in range(2)]
+    build = {"outer": lambda a, b: a ^ b, "lcontract": lambda a, b: a << b, "rcontract": lambda a, b: a >> b}[kind]
+    ast = build(pmv(Input(0, full)), pmv(Input(1, full))).specialize(metric)
+    want = oracle_eval(build, metric, host, [False, False], batch)
+    scale = oracle_abs_scale(build, metric, host, [False, False], batch)
+    plan = g.Plan(ctx, ast)
+    dev = [g.DeviceBatch.from_host(ctx, n, h) for h in host]
+    out = plan.eval(dev, engine=L.ENGINE_DENSE_WARP)
+    ctx.sync()
+    assert "gaast_dense_warp" in plan.last_kernel()  # the per-plan kernel: the generic one needs a complete table
+    assert_close(out.to_host(), want, scale, what=f"G(10) {kind} dense-warp")
+    assert sorted(out.to_host()) == plan.root_grades()
