@@ -61,8 +61,8 @@ FP64_PEAK_TFLOPS = float(os.environ.get("GAAST_FP64_PEAK_TFLOPS", "0") or 0) or 
 # `ncu --set full` captures (profiles/r1_*_ncu.txt; captures taken at batch 4M are scaled to the full batch)
 NCU_TRAFFIC_BYTES = {
     "cfg1": 727105280 // 4,        # profiles/r1_cfg1_final_ncu.txt, captured at 4M elements (BASELINE batch is 1M)
-    "cfg2": 5318542000,            # profiles/r1_cfg2_final_ncu.txt at the BASELINE batch (algorithmic 5368709120)
-    "cfg3": 6409480000 * 4,        # profiles/r1_cfg3_final_ncu.txt at 4M elements (algorithmic 6442450944 at 4M)
+    "cfg2": 5316607000,            # profiles/r1_cfg2_final_ncu.txt at the BASELINE batch (algorithmic 5368709120)
+    "cfg3": 6409913000 * 4,        # profiles/r1_cfg3_final_ncu.txt at 4M elements (algorithmic 6442450944 at 4M)
     "cfg4": 9169429000 * 2,        # profiles/r1_cfg4_final_ncu.txt at 4M elements (algorithmic 9227468800 at 4M)
     "cfg5": 4792209000 * 8,        # profiles/r1_cfg5_final_ncu.txt at 4M elements (algorithmic 4831838208 at 4M)
 }
