@@ -29,8 +29,13 @@
 //
 // Arithmetic: one DFMA per term, terms of an output summed in (alo, ahi) order (not the reference's
 // order): FMA arithmetic only, like the other dense lowerings; GAAST_ARITH_STRICT keeps using the
-// table engine.  Only plans that ARE a full product of two batch inputs qualify (dense_warp_analyse);
-// everything else is untouched.
+// table engine.
+//
+// A plan qualifies (dense_warp_analyse) when every buffer carries the full grade set and its ops are:
+// inputs copied into operand buffers, sign flips of whole grades (Negation / Reverse / GradeInvolution),
+// and products, each written to a fresh buffer -- R * X * ~R, (A ^ B) * C, -(A * B) ... -- every product a
+// dense one that factorises as above.  The products run one after the other, intermediate results in
+// scratch buffers of the plan, sign flips folded into the copies.  Everything else is untouched.
 #include <algorithm>
 #include <cstring>
 
@@ -40,66 +45,24 @@ namespace gaast {
 
 namespace {
 
-
 #include "dense_warp_kernel.h"
 
 template <int J>
-__global__ void __launch_bounds__(J >= 32 ? 256 : 512) dense_warp_kernel(const __grid_constant__ EvalArgs a,
-                                                                         const __grid_constant__ DenseWarpArgs d) {
-    dense_warp_body<J>(a, d);
+__global__ void __launch_bounds__(J >= 32 ? 256 : 512) dense_warp_kernel(const __grid_constant__ DenseWarpArgs d) {
+    dense_warp_body<J>(d);
 }
 
 // the same device code as text, for the per-plan kernels NVRTC builds (sigma folded at compile time)
 const char kDenseWarpKernelText[] =
 #include "dense_warp_kernel_text.inc"
     ;
-const char kEvalArgsTextDw[] =
-#include "../eval_args_text.inc"
-    ;
 
-}  // namespace
-
-// Does the plan consist of exactly  root = L * R  with L and R two full-grade batch inputs and a
-// complete +-1 coefficient table?  Fills the host tables on success.
-bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
-    const uint32_t n = h.n;
-    if (n < 7 || n > 10) return false;
-    const uint32_t full = (2u << n) - 1, NB = 1u << n;
-    if (h.buffer_masks.size() != 3 || h.ops.size() != 3) return false;
-    for (uint32_t m : h.buffer_masks)
-        if (m != full) return false;
-    const gaast_op &o0 = h.ops[0], &o1 = h.ops[1], &mul = h.ops[2];
-    if (o0.kind != GAAST_OP_ADD_INPUT || o1.kind != GAAST_OP_ADD_INPUT || mul.kind != GAAST_OP_MUL_TERMS) return false;
-    if (mul.dst != 0 || mul.a == 0 || mul.b == 0 || mul.a == mul.b || mul.term_count > uint64_t(NB) * NB ||
-        mul.term_count < uint64_t(NB))
-        return false;
-    auto input_of = [&](uint32_t buf, uint32_t* slot) {
-        const gaast_op* src = o0.dst == buf ? &o0 : (o1.dst == buf ? &o1 : nullptr);
-        if (!src || src->mask != full) return false;
-        const gaast_input_desc& in = h.inputs[src->a];
-        if (in.kind != GAAST_INPUT_BATCH || in.grade_mask != full) return false;
-        *slot = in.slot;
-        return true;
-    };
-    if (o0.dst == o1.dst) return false;
-    uint32_t slotL = 0, slotR = 0;
-    if (!input_of(mul.a, &slotL) || !input_of(mul.b, &slotR)) return false;
-    // slot <-> blade (algebra.rs:221-246): grades ascending, masks of a grade in ascending numeric order
-    std::vector<uint16_t> blade_of(NB);
-    std::vector<int> gstart(n + 2, 0);
-    {
-        uint32_t s = 0;
-        for (uint32_t k = 0; k <= n; ++k) {
-            gstart[k] = int(s);
-            for (uint32_t b = 0; b < NB; ++b)
-                if (uint32_t(__builtin_popcount(b)) == k) blade_of[s++] = uint16_t(b);
-        }
-        gstart[n + 1] = int(s);
-    }
-    std::vector<uint16_t> slot_of(NB);
-    for (uint32_t s = 0; s < NB; ++s) slot_of[blade_of[s]] = uint16_t(s);
-    const uint32_t J = NB / 32;
-    // the whole coefficient table as sign bits [a][b] (it must be complete and +-1) ...
+// Tables of ONE product op: which pairs it keeps and with which sign, factorised over (high, low) parts.
+bool analyse_product(const DevicePlanHost& h, const gaast_op& mul, const std::vector<uint16_t>& blade_of,
+                     const std::vector<uint16_t>& slot_of, DenseWarpProduct* out) {
+    const uint32_t NB = 1u << h.n, J = NB / 32;
+    if (mul.term_count > uint64_t(NB) * NB || mul.term_count < uint64_t(NB)) return false;
+    // the coefficient table as presence and sign bits [a][b] (+-1 only) ...
     std::vector<uint8_t> seen(size_t(NB) * NB / 8, 0), neg(size_t(NB) * NB / 8, 0);
     for (uint32_t t = mul.term_begin; t < mul.term_begin + mul.term_count; ++t) {
         const gaast_term& tm = h.terms[t];
@@ -149,23 +112,111 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
             const bool want = bool(sigma[ah * J + bh] == 1) ^ chi ^ bool(lambda_words[al] >> bl & 1);
             if (want != is_neg(ab, bb)) return false;
         }
-    if (out) {
-        out->n = n;
-        out->slotL = slotL;
-        out->slotR = slotR;
-        out->blade_of_slot = std::move(blade_of);
-        out->lambda_words = std::move(lambda_words);
-        out->present_words = std::move(present_words);
-        out->sigma = sigma;
-        out->complete = complete;  // the library's generic kernel handles complete tables only
-        out->toggle.assign(size_t(J) * J, 0);
-        for (uint32_t ah = 0; ah < J; ++ah)
-            for (uint32_t g = 0; g < J; ++g) {
-                const bool prev = ah ? sigma[(ah - 1) * J + g] == 1 : false;
-                out->toggle[ah * J + g] = ((sigma[ah * J + g] == 1) != prev) ? 0x80000000u : 0u;
-            }
-        out->gstart = std::move(gstart);
+    out->lambda_words = std::move(lambda_words);
+    out->present_words = std::move(present_words);
+    out->sigma = sigma;
+    out->complete = complete;  // the library's generic kernel handles complete tables only
+    out->toggle.assign(size_t(J) * J, 0);
+    for (uint32_t ah = 0; ah < J; ++ah)
+        for (uint32_t g = 0; g < J; ++g) {
+            const bool prev = ah ? sigma[(ah - 1) * J + g] == 1 : false;
+            out->toggle[ah * J + g] = ((sigma[ah * J + g] == 1) != prev) ? 0x80000000u : 0u;
+        }
+    return true;
+}
+
+}  // namespace
+
+// Is the plan a chain of dense products of full-grade buffers (see the head of this file)?  Fills the
+// program -- one step per product -- on success.
+bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
+    const uint32_t n = h.n;
+    if (n < 7 || n > 10) return false;
+    const uint32_t full = (2u << n) - 1, NB = 1u << n;
+    for (uint32_t m : h.buffer_masks)
+        if (m != full) return false;
+    // slot <-> blade (algebra.rs:221-246): grades ascending, masks of a grade in ascending numeric order
+    std::vector<uint16_t> blade_of(NB), slot_of(NB);
+    std::vector<int> gstart(n + 2, 0);
+    {
+        uint32_t s = 0;
+        for (uint32_t k = 0; k <= n; ++k) {
+            gstart[k] = int(s);
+            for (uint32_t b = 0; b < NB; ++b)
+                if (uint32_t(__builtin_popcount(b)) == k) blade_of[s++] = uint16_t(b);
+        }
+        gstart[n + 1] = int(s);
+        for (uint32_t i = 0; i < NB; ++i) slot_of[blade_of[i]] = uint16_t(i);
     }
+    // what every buffer holds as the ops go by (eval.rs fills a cache entry completely before it is read)
+    struct State {
+        int kind = 0;  // 0 empty, 1 a batch input, 2 a product
+        int slot = -1, step = -1;
+        uint32_t neg = 0;
+        bool frozen = false;  // read as an operand: must not change any more
+    };
+    std::vector<State> st(h.buffer_masks.size());
+    DenseWarpHost prog;
+    prog.n = n;
+    int n_scratch = 0;
+    for (const gaast_op& op : h.ops) {
+        if (op.dst >= st.size()) return false;
+        State& d = st[op.dst];
+        if (d.frozen) return false;
+        switch (op.kind) {
+            case GAAST_OP_ADD_INPUT: {
+                const gaast_input_desc& in = h.inputs[op.a];
+                if (d.kind != 0 || op.mask != full || in.kind != GAAST_INPUT_BATCH || in.grade_mask != full) return false;
+                d.kind = 1;
+                d.slot = int(in.slot);
+                d.neg = 0;  // sign flips of an empty buffer flipped zeros
+                break;
+            }
+            case GAAST_OP_NEG_GRADES:
+                if (d.kind == 2) prog.steps[size_t(d.step)].O.neg_mask ^= op.mask;
+                d.neg ^= op.mask;  // (an empty buffer: zeros stay zeros; the mask is reset when it is filled)
+                break;
+            case GAAST_OP_MUL_TERMS: {
+                if (d.kind != 0 || op.a >= st.size() || op.b >= st.size() || op.a == op.dst || op.b == op.dst) return false;
+                State &l = st[op.a], &r = st[op.b];
+                if (l.kind == 0 || r.kind == 0) return false;
+                l.frozen = r.frozen = true;
+                DenseWarpStep step;
+                if (!analyse_product(h, op, blade_of, slot_of, &step.prod)) return false;
+                auto source = [&](const State& s) {
+                    DenseWarpOperand o;
+                    if (s.kind == 1) {
+                        o.slot = s.slot;
+                        o.neg_mask = s.neg;
+                    } else {
+                        o.scratch = prog.steps[size_t(s.step)].O.scratch;  // its flips were applied when it was stored
+                    }
+                    return o;
+                };
+                step.L = source(l);
+                step.R = source(r);
+                if (step.L.slot < 0 && step.L.scratch < 0) return false;  // (the root is never an operand)
+                if (step.R.slot < 0 && step.R.scratch < 0) return false;
+                if (op.dst == 0) step.O.root = true;
+                else step.O.scratch = n_scratch++;
+                d.kind = 2;
+                d.step = int(prog.steps.size());
+                d.neg = 0;
+                prog.steps.push_back(std::move(step));
+                break;
+            }
+            default: return false;  // scalar 1/x, sqrt: not a dense product chain
+        }
+    }
+    if (prog.steps.empty() || st[0].kind != 2) return false;
+    for (size_t i = 0; i + 1 < prog.steps.size(); ++i)
+        if (prog.steps[i].O.root) return false;  // the root must be the last product
+    prog.n_scratch = n_scratch;
+    prog.complete = true;
+    for (const DenseWarpStep& s : prog.steps) prog.complete = prog.complete && s.prod.complete;
+    prog.blade_of_slot = std::move(blade_of);
+    prog.gstart = std::move(gstart);
+    if (out) *out = std::move(prog);
     return true;
 }
 
@@ -186,62 +237,69 @@ DenseWarpLaunch dense_warp_shape(const gaast_ctx& ctx, uint32_t n, long long bat
     return s;
 }
 
-// CUDA source of the per-plan kernel: the shared device code with sigma as a compile-time table.
-CodegenResult dense_warp_codegen(const DenseWarpHost& hp, const DenseWarpLaunch& shape) {
-    const uint32_t J = (1u << hp.n) / 32;
-    std::string src = "// generated by gaast_b200: dense-warp kernel for a full product in G(n), n=" + std::to_string(hp.n) +
+// CUDA source of the per-plan kernel of one product: the shared device code with sigma as a compile-time table.
+CodegenResult dense_warp_codegen(uint32_t n, const DenseWarpProduct& prod, const DenseWarpLaunch& shape) {
+    const uint32_t J = (1u << n) / 32;
+    std::string src = "// generated by gaast_b200: dense-warp kernel for a dense product in G(n), n=" + std::to_string(n) +
                       ", sigma folded at compile time\n";
-    src += kEvalArgsTextDw;
-    src += "\nusing gaast::EvalArgs;\n#define GAAST_DW_J " + std::to_string(J) + "\n";
+    src += "#define GAAST_DW_J " + std::to_string(J) + "\n";
     src += "__device__ constexpr unsigned char kDwSigma[" + std::to_string(J * J) + "] = {";
-    for (size_t i = 0; i < hp.sigma.size(); ++i) src += (i ? "," : "") + std::to_string(int(hp.sigma[i]));
+    for (size_t i = 0; i < prod.sigma.size(); ++i) src += (i ? "," : "") + std::to_string(int(prod.sigma[i]));
     src += "};\n#define GAAST_DW_SIGMA_NEG(ahi, g) (kDwSigma[(ahi) * GAAST_DW_J + (g)] == 1)\n"
            "#define GAAST_DW_SIGMA_ABSENT(ahi, g) (kDwSigma[(ahi) * GAAST_DW_J + (g)] == 2)\n";
     src += kDenseWarpKernelText;
     src += "\nextern \"C\" __global__ void __launch_bounds__(" + std::to_string(shape.threads) +
-           ") gaast_dense_warp(const __grid_constant__ EvalArgs a, const __grid_constant__ DenseWarpArgs d) {\n"
-           "  dense_warp_body<GAAST_DW_J>(a, d);\n}\n";
+           ") gaast_dense_warp(const __grid_constant__ DenseWarpArgs d) {\n  dense_warp_body<GAAST_DW_J>(d);\n}\n";
     CodegenResult cg;
     cg.source = std::move(src);
     cg.kernel_name = "gaast_dense_warp";
     cg.threads = shape.threads;
     cg.smem_bytes = shape.smem;
-    cg.notes = "dense-warp(n=" + std::to_string(hp.n) + ")";
+    cg.notes = "dense-warp(n=" + std::to_string(n) + ")";
     return cg;
 }
 
-// `jit_kernel`: the per-plan kernel (sigma compile-time), or null for the generic kernel of this library.
-cudaError_t dense_warp_launch(const EvalArgs& args, const DenseWarpHost& hplan, const DevicePlanHost& h,
+// One product of the program.  `jit_kernel`: its per-plan kernel (sigma compile-time), or null for the
+// generic kernel of this library (complete tables only).  L / R / O: per-grade arrays, see DenseWarpArgs.
+cudaError_t dense_warp_launch(const DenseWarpHost& prog, const DenseWarpStep& step, const DenseWarpBuffers& L,
+                              const DenseWarpBuffers& R, const DenseWarpBuffers& O, long long batch,
                               const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaKernel_t jit_kernel,
                               cudaStream_t stream) {
     DenseWarpArgs d;
     std::memset(&d, 0, sizeof d);
     d.blade_of_slot = d_blade_of_slot;
-    for (int i = 0; i < 32; ++i) d.lambda_words[i] = hplan.lambda_words[size_t(i)];
-    for (int i = 0; i < 32; ++i) d.present_words[i] = hplan.present_words[size_t(i)];
-    if (!jit_kernel && !hplan.complete) return cudaErrorNotSupported;  // (the caller checks: see runtime.cu)
-    for (size_t i = 0; i < hplan.toggle.size(); ++i) d.toggle[i] = hplan.toggle[i];
-    d.n = int(hplan.n);
+    d.batch = batch;
+    d.n = int(prog.n);
     d.T = shape.T;
     d.LD = shape.LD;
-    for (uint32_t k = 0; k <= hplan.n + 1; ++k) d.gstart[k] = hplan.gstart[k];
-    for (uint32_t k = 0; k <= hplan.n; ++k) {
-        d.streamL[k] = h.stream_of(hplan.slotL, k);
-        d.streamR[k] = h.stream_of(hplan.slotR, k);
-        d.streamO[k] = int(h.n_in_streams + k);  // the root holds every grade, ascending
+    for (uint32_t k = 0; k <= prog.n + 1; ++k) d.gstart[k] = prog.gstart[k];
+    for (uint32_t k = 0; k <= prog.n; ++k) {
+        d.Lp[k] = L.ptr[k];
+        d.Lrow[k] = L.row[k];
+        d.Rp[k] = R.ptr[k];
+        d.Rrow[k] = R.row[k];
+        d.Op[k] = O.ptr[k];
+        d.Orow[k] = O.row[k];
     }
+    d.Lneg = step.L.neg_mask;
+    d.Rneg = step.R.neg_mask;
+    d.Oneg = step.O.neg_mask;
+    for (int i = 0; i < 32; ++i) d.lambda_words[i] = step.prod.lambda_words[size_t(i)];
+    for (int i = 0; i < 32; ++i) d.present_words[i] = step.prod.present_words[size_t(i)];
+    for (size_t i = 0; i < step.prod.toggle.size(); ++i) d.toggle[i] = step.prod.toggle[i];
     if (jit_kernel) {
-        void* params[] = {const_cast<EvalArgs*>(&args), &d};
+        void* params[] = {&d};
         return cudaLaunchKernel(reinterpret_cast<const void*>(jit_kernel), dim3(shape.grid), dim3(shape.threads), params,
                                 shape.smem, stream);
     }
+    if (!step.prod.complete) return cudaErrorNotSupported;  // (the caller checks: see runtime.cu)
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shape.smem));
         if (e != cudaSuccess) return e;
-        kernel<<<shape.grid, shape.threads, shape.smem, stream>>>(args, d);
+        kernel<<<shape.grid, shape.threads, shape.smem, stream>>>(d);
         return cudaGetLastError();
     };
-    switch (hplan.n) {
+    switch (prog.n) {
         case 7: return go(dense_warp_kernel<4>);
         case 8: return go(dense_warp_kernel<8>);
         case 9: return go(dense_warp_kernel<16>);

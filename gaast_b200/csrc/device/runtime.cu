@@ -241,6 +241,7 @@ gaast_status gaast_plan_destroy(gaast_plan* plan) {
             cudaFree(plan->d_uniform);
             cudaFree(plan->d_dw_blades);
             plan->dw_jit.clear();
+            for (double* p : plan->d_dw_scratch) cudaFree(p);
         }
         delete plan;
     });
@@ -329,9 +330,12 @@ gaast_status gaast_plan_precompile_typed(gaast_plan* plan, uint64_t broadcast_sl
             fake.sm_count = 148;
             fake.smem_optin = 232448;
             const gaast::DenseWarpLaunch shape = gaast::dense_warp_shape(fake, plan->h.n, 1 << 20);
-            cg = gaast::dense_warp_codegen(dw, shape);
-            std::string log;
-            gaast::jit_cubin(cg, &key, &origin, &log);
+            for (const gaast::DenseWarpStep& step : dw.steps) {  // one kernel per product (equal tables share a cubin)
+                cg = gaast::dense_warp_codegen(plan->h.n, step.prod, shape);
+                std::string log;
+                gaast::jit_cubin(cg, &key, &origin, &log);
+            }
+            cg.notes += " x" + std::to_string(dw.steps.size()) + " product(s)";
         }
         plan->last_kernel = cg.kernel_name + " key=" + key + " origin=" + origin + " " + cg.notes;
     });
@@ -520,25 +524,26 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
 
     // dense-warp engine: the per-plan kernel (warp-uniform signs folded at compile time) when NVRTC or the
     // cache has it, else null = the generic kernel compiled into the library
-    auto dense_warp_kernel_for = [&](const gaast::DenseWarpLaunch& shape) -> std::shared_ptr<gaast::JitKernel> {
+    auto dense_warp_kernel_for = [&](int step, const gaast::DenseWarpLaunch& shape) -> std::shared_ptr<gaast::JitKernel> {
         if (plan->dw_jit_failed || std::getenv("GAAST_DENSE_WARP_GENERIC")) return nullptr;
-        auto it = plan->dw_jit.find(shape.threads);
+        const auto jkey = std::make_pair(step, shape.threads);
+        auto it = plan->dw_jit.find(jkey);
         if (it != plan->dw_jit.end()) return it->second;
         try {
-            gaast::CodegenResult cg = gaast::dense_warp_codegen(plan->dense_warp, shape);
+            gaast::CodegenResult cg = gaast::dense_warp_codegen(h.n, plan->dense_warp.steps[size_t(step)].prod, shape);
             std::string key, origin, log;
             std::vector<char> cubin = gaast::jit_cubin(cg, &key, &origin, &log);
             auto k = gaast::jit_load(cg, cubin);
             k->key = key;
             k->origin = origin;
-            plan->dw_jit.emplace(shape.threads, k);
+            plan->dw_jit.emplace(jkey, k);
             return k;
         } catch (const Error&) {
             plan->dw_jit_failed = true;
             return nullptr;
         }
     };
-    // usable for this call?  (a dense product plan, f64, FMA arithmetic, per-element operands)
+    // usable for this call?  (a chain of dense products, f64, FMA arithmetic, per-element operands)
     auto dense_warp_ready = [&]() {
         if (with_sum || f32 || arith != GAAST_ARITH_FMA || bslots != 0 || !out) return false;
         if (plan->dense_warp_state == 0) {
@@ -546,16 +551,20 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
             if (plan->dense_warp_state == 1) upload(plan->d_dw_blades, plan->dense_warp.blade_of_slot, ctx->stream);
         }
         if (plan->dense_warp_state != 1) return false;
-        // products that drop pairs (outer products, contractions) need the per-plan kernel
-        if (!plan->dense_warp.complete && !dense_warp_kernel_for(gaast::dense_warp_shape(*ctx, h.n, n))) return false;
+        // products that drop pairs (outer products, contractions) need their per-plan kernel
+        if (!plan->dense_warp.complete) {
+            const gaast::DenseWarpLaunch shape = gaast::dense_warp_shape(*ctx, h.n, n);
+            for (size_t i = 0; i < plan->dense_warp.steps.size(); ++i)
+                if (!plan->dense_warp.steps[i].prod.complete && !dense_warp_kernel_for(int(i), shape)) return false;
+        }
         return true;
     };
     bool use_dense_warp = false;
     if (engine == GAAST_ENGINE_DENSE_WARP) {
         if (!dense_warp_ready())
             throw Error(GAAST_ERR_UNSUPPORTED,
-                        "dense-warp engine: the plan is not ONE product (geometric, outer, contraction) of two full-grade "
-                        "per-element f64 batch inputs in G(n), 7 <= n <= 10, with a +-1 metric, evaluated in FMA "
+                        "dense-warp engine: the plan is not a chain of dense products (geometric, outer, contraction) of "
+                        "full-grade per-element f64 operands in G(n), 7 <= n <= 10, with a +-1 metric, evaluated in FMA "
                         "arithmetic without batch-sum");
         use_dense_warp = true;
     }
@@ -607,15 +616,48 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     if (use_dense_warp) {
         const gaast::DenseWarpLaunch shape = gaast::dense_warp_shape(*ctx, h.n, n);
         grid = shape.grid;
-        std::shared_ptr<gaast::JitKernel> dwk = dense_warp_kernel_for(shape);
-        cuda_check(gaast::dense_warp_launch(a, plan->dense_warp, h, plan->d_dw_blades, shape, dwk ? dwk->kernel : nullptr,
-                                            ctx->stream),
-                   "launch dense-warp engine");
-        ctx->launches++;
+        const gaast::DenseWarpHost& prog = plan->dense_warp;
+        // scratch buffers for the intermediate products: [2^n][stride], rows on 128-byte boundaries
+        const size_t stride = (size_t(n) + 15) / 16 * 16;
+        if (plan->d_dw_scratch.size() < size_t(prog.n_scratch) || plan->dw_scratch_stride < stride) {
+            for (double* p : plan->d_dw_scratch) cudaFree(p);
+            plan->d_dw_scratch.assign(size_t(prog.n_scratch), nullptr);
+            plan->dw_scratch_stride = 0;
+            for (double*& p : plan->d_dw_scratch)
+                cuda_check(cudaMalloc(&p, (size_t(1) << h.n) * stride * sizeof(double)), "cudaMalloc(dense-warp scratch)");
+            plan->dw_scratch_stride = stride;
+        }
+        auto buffers_of = [&](const gaast::DenseWarpOperand& o) {
+            gaast::DenseWarpBuffers b;
+            for (uint32_t k = 0; k <= h.n; ++k) {
+                if (o.slot >= 0) {
+                    const int si = h.stream_of(uint32_t(o.slot), k);
+                    b.ptr[k] = a.sptr[si];
+                    b.row[k] = a.srow[si];
+                } else if (o.root) {
+                    b.ptr[k] = a.sptr[h.n_in_streams + k];  // the root holds every grade, ascending
+                    b.row[k] = a.srow[h.n_in_streams + k];
+                } else {
+                    b.ptr[k] = plan->d_dw_scratch[size_t(o.scratch)] + size_t(prog.gstart[k]) * plan->dw_scratch_stride;
+                    b.row[k] = (long long)plan->dw_scratch_stride;
+                }
+            }
+            return b;
+        };
+        std::shared_ptr<gaast::JitKernel> dwk;
+        for (size_t i = 0; i < prog.steps.size(); ++i) {
+            const gaast::DenseWarpStep& step = prog.steps[i];
+            dwk = dense_warp_kernel_for(int(i), shape);
+            cuda_check(gaast::dense_warp_launch(prog, step, buffers_of(step.L), buffers_of(step.R), buffers_of(step.O), n,
+                                                plan->d_dw_blades, shape, dwk ? dwk->kernel : nullptr, ctx->stream),
+                       "launch dense-warp engine");
+            ctx->launches++;
+        }
         char desc[320];
-        std::snprintf(desc, sizeof desc, "%s engine=dense_warp origin=%s grid=%d block=%d smem=%zu tile=%d elements regs=%d",
-                      dwk ? "gaast_dense_warp" : "dense_warp_kernel", dwk ? dwk->origin.c_str() : "library", grid, shape.threads,
-                      shape.smem, shape.T, dwk ? dwk->regs : 0);
+        std::snprintf(desc, sizeof desc,
+                      "%s engine=dense_warp origin=%s products=%zu grid=%d block=%d smem=%zu tile=%d elements regs=%d",
+                      dwk ? "gaast_dense_warp" : "dense_warp_kernel", dwk ? dwk->origin.c_str() : "library", prog.steps.size(),
+                      grid, shape.threads, shape.smem, shape.T, dwk ? dwk->regs : 0);
         plan->last_kernel = desc;
     } else if (jk) {
         const long long per_block = (long long)jk->threads * jk->elems_per_thread;

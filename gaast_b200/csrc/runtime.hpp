@@ -96,16 +96,35 @@ cudaError_t reduce_partials_launch(const double* partials, int n_blocks, int n_c
                                    cudaStream_t stream);
 const char* table_engine_arch();
 
-// dense_warp.cu: full geometric products in G(n), n = 7..10, one warp per multivector
-struct DenseWarpHost {
-    uint32_t n = 0, slotL = 0, slotR = 0;
-    std::vector<uint16_t> blade_of_slot;  // [2^n]
+// dense_warp.cu: chains of dense products of full-grade buffers in G(n), n = 7..10, one warp per multivector
+struct DenseWarpProduct {                 // tables of one product op
     std::vector<uint32_t> lambda_words;   // [32]: bit blo of word alo = lambda(alo, blo) is -1
-    std::vector<uint32_t> toggle;         // [J][J], J = 2^n / 32: sign-bit masks that step sigma(ahi - 1, g) to sigma(ahi, g)
     std::vector<uint32_t> present_words;  // [32]: bit blo of word alo = the product keeps the pair (alo, blo)
+    std::vector<uint32_t> toggle;         // [J][J], J = 2^n / 32: sign-bit masks that step sigma(ahi - 1, g) to sigma(ahi, g)
     std::vector<uint8_t> sigma;           // [J][J]: 0 = +1, 1 = -1, 2 = the product drops the pair of high parts
     bool complete = true;                 // every pair kept (geometric product): the generic kernel can run it
+};
+struct DenseWarpOperand {   // where a full-grade buffer lives when a product reads or writes it
+    int slot = -1;          // >= 0: a batch input (read only)
+    int scratch = -1;       // >= 0: a scratch buffer of the plan (an earlier product)
+    bool root = false;      // the root's grade arrays (written by the last product)
+    uint32_t neg_mask = 0;  // grades whose sign flips on the way (Negation / Reverse / GradeInvolution)
+};
+struct DenseWarpStep {
+    DenseWarpProduct prod;
+    DenseWarpOperand L, R, O;
+};
+struct DenseWarpHost {
+    uint32_t n = 0;
+    std::vector<uint16_t> blade_of_slot;  // [2^n]
     std::vector<int> gstart;              // first slot of grade k
+    std::vector<DenseWarpStep> steps;     // one per product, in the plan's order
+    int n_scratch = 0;
+    bool complete = true;                 // every product keeps every pair
+};
+struct DenseWarpBuffers {  // per-grade arrays of one operand / result at launch time
+    double* ptr[GAAST_MAX_DIM + 2] = {};
+    long long row[GAAST_MAX_DIM + 2] = {};
 };
 struct DenseWarpLaunch {
     int T = 0, LD = 0, threads = 0, grid = 0;
@@ -113,10 +132,11 @@ struct DenseWarpLaunch {
 };
 bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out);
 DenseWarpLaunch dense_warp_shape(const gaast_ctx& ctx, uint32_t n, long long batch);
-cudaError_t dense_warp_launch(const EvalArgs& args, const DenseWarpHost& hplan, const DevicePlanHost& h,
+cudaError_t dense_warp_launch(const DenseWarpHost& prog, const DenseWarpStep& step, const DenseWarpBuffers& L,
+                              const DenseWarpBuffers& R, const DenseWarpBuffers& O, long long batch,
                               const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaKernel_t jit_kernel,
                               cudaStream_t stream);
-CodegenResult dense_warp_codegen(const DenseWarpHost& hp, const DenseWarpLaunch& shape);
+CodegenResult dense_warp_codegen(uint32_t n, const DenseWarpProduct& prod, const DenseWarpLaunch& shape);
 
 // host_pipeline.cu
 struct HostPipe;
@@ -170,6 +190,8 @@ struct gaast_plan {
     int dense_warp_state = 0;
     gaast::DenseWarpHost dense_warp;
     uint16_t* d_dw_blades = nullptr;
-    std::map<int, std::shared_ptr<gaast::JitKernel>> dw_jit;  // per block size: the kernel with sigma folded in
+    std::map<std::pair<int, int>, std::shared_ptr<gaast::JitKernel>> dw_jit;  // (step, block size): kernel with sigma folded in
+    std::vector<double*> d_dw_scratch;  // intermediate products: [2^n][stride] each
+    size_t dw_scratch_stride = 0;
     bool dw_jit_failed = false;  // NVRTC unavailable: keep using the generic kernel
 };

@@ -65,7 +65,7 @@ def test_dense_warp_refuses_other_plans(ctx):
     full = tuple(range(n + 1))
     a, b = pmv(Input(0, full)), pmv(Input(1, full))
     dev = [g.DeviceBatch.alloc(ctx, n, full, 64) for _ in range(2)]
-    for ast in (((a * b) + a).specialize([1.0] * n),                # more than one product of two inputs
+    for ast in (((a * b) + a).specialize([1.0] * n),                # a sum lands in the product's buffer
                 (a * b).g(2).specialize([1.0] * n),                  # the root is not the full grade set
                 (a * b).specialize([1.0] * 6 + [0.0]),               # degenerate metric: zero coefficients
                 (a * b).specialize([1.0] * 6 + [2.0])):              # scaled metric: |coefficient| != 1
@@ -107,3 +107,41 @@ def test_dense_warp_products_that_drop_pairs(ctx, kind):
     assert "gaast_dense_warp" in plan.last_kernel()  # the per-plan kernel: the generic one needs a complete table
     assert_close(out.to_host(), want, scale, what=f"G(10) {kind} dense-warp")
     assert sorted(out.to_host()) == plan.root_grades()
+
+
+CHAINS = {
+    "sandwich": lambda a, b, c: a * b * a.rev(),          # two products, the second operand a reversed input
+    "outer_then_geometric": lambda a, b, c: (a ^ b) * c,  # products of different kinds
+    "negated": lambda a, b, c: -(a * b),                  # sign flip of the root after the product
+    "involuted_operand": lambda a, b, c: (a * b).ginvol() * c.conj(),
+    "reused_product": lambda a, b, c: (lambda p: p * p.clone())(a * b),  # one cached product, both operands
+    "three_deep": lambda a, b, c: ((a * b) * c) * (b << a),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CHAINS))
+def test_dense_warp_product_chains(ctx, name):
+    """Several dense products in one plan (R X ~R with full multivectors, ...): the products run one after
+    the other, intermediate results in scratch buffers, sign flips folded into the copies.  Such a plan is
+    far too large to specialise (2+ x 16 384 terms), so AUTO lands here instead of on the table engine."""
+    n, batch = 7, 150
+    metric = [1.0] * 5 + [-1.0] * 2
+    full = tuple(range(n + 1))
+    rng = np.random.default_rng(len(name))
+    host = [{k: rng.uniform(-1, 1, (comb(n, k), batch)) for k in full} for _ in range(3)]
+    build = CHAINS[name]
+    ast = build(*[pmv(Input(s, full)) for s in range(3)]).specialize(metric)
+    plan = g.Plan(ctx, ast)
+    ns = plan.num_slots()
+    want = oracle_eval(build, metric, host, [False] * 3, batch)
+    scale = oracle_abs_scale(build, metric, host, [False] * 3, batch)
+    dev = [g.DeviceBatch.from_host(ctx, n, h) for h in host][:ns]
+    out = plan.eval(dev, engine=L.ENGINE_AUTO)
+    ctx.sync()
+    assert "engine=dense_warp" in plan.last_kernel(), plan.last_kernel()
+    assert_close(out.to_host(), want, scale, what=f"chain {name}")
+    # a second batch length reuses (and regrows) the scratch buffers
+    out2 = plan.eval([g.DeviceBatch.from_host(ctx, n, {k: v[:, :37] for k, v in h.items()}) for h in host][:ns])
+    ctx.sync()
+    assert_close(out2.to_host(), {k: v[:, :37] for k, v in want.items()}, {k: v[:, :37] for k, v in scale.items()},
+                 what=f"chain {name}, shorter batch")
