@@ -281,6 +281,8 @@ cudaError_t dense_warp_launch(const DenseWarpHost& prog, const DenseWarpStep& st
         d.Op[k] = O.ptr[k];
         d.Orow[k] = O.row[k];
     }
+    d.Lstep = L.shared ? 0 : 1;
+    d.Rstep = R.shared ? 0 : 1;
     d.Lneg = step.L.neg_mask;
     d.Rneg = step.R.neg_mask;
     d.Oneg = step.O.neg_mask;

@@ -545,7 +545,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     };
     // usable for this call?  (a chain of dense products, f64, FMA arithmetic, per-element operands)
     auto dense_warp_ready = [&]() {
-        if (with_sum || f32 || arith != GAAST_ARITH_FMA || bslots != 0 || !out) return false;
+        if (with_sum || f32 || arith != GAAST_ARITH_FMA || !out) return false;
         if (plan->dense_warp_state == 0) {
             plan->dense_warp_state = gaast::dense_warp_analyse(h, &plan->dense_warp) ? 1 : -1;
             if (plan->dense_warp_state == 1) upload(plan->d_dw_blades, plan->dense_warp.blade_of_slot, ctx->stream);
@@ -634,6 +634,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                     const int si = h.stream_of(uint32_t(o.slot), k);
                     b.ptr[k] = a.sptr[si];
                     b.row[k] = a.srow[si];
+                    b.shared = (bslots >> o.slot) & 1;  // a fixed operand (the rotor of R X ~R): stride 0
                 } else if (o.root) {
                     b.ptr[k] = a.sptr[h.n_in_streams + k];  // the root holds every grade, ascending
                     b.row[k] = a.srow[h.n_in_streams + k];

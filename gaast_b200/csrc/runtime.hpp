@@ -125,6 +125,7 @@ struct DenseWarpHost {
 struct DenseWarpBuffers {  // per-grade arrays of one operand / result at launch time
     double* ptr[GAAST_MAX_DIM + 2] = {};
     long long row[GAAST_MAX_DIM + 2] = {};
+    bool shared = false;  // a broadcast input: one element for the whole batch
 };
 struct DenseWarpLaunch {
     int T = 0, LD = 0, threads = 0, grid = 0;

@@ -76,11 +76,8 @@ def test_dense_warp_refuses_other_plans(ctx):
         plan.eval(dev, engine=L.ENGINE_AUTO)  # still evaluates, on another engine
         ctx.sync()
         assert "dense_warp" not in plan.last_kernel()
-    # a plan of the right shape, but a broadcast operand or f32 batches: refused as well
+    # a plan of the right shape, but f32 batches: refused as well
     plan = g.Plan(ctx, (a * b).specialize([1.0] * n))
-    shared = g.DeviceBatch.alloc(ctx, n, full, 1, broadcast=True)
-    with pytest.raises(g.GaastError):
-        plan.eval([shared, dev[1]], engine=L.ENGINE_DENSE_WARP)
     d32 = [g.DeviceBatch.alloc(ctx, n, full, 64, dtype=L.F32) for _ in range(2)]
     with pytest.raises(g.GaastError):
         plan.eval(d32, engine=L.ENGINE_DENSE_WARP)
@@ -145,3 +142,23 @@ def test_dense_warp_product_chains(ctx, name):
     ctx.sync()
     assert_close(out2.to_host(), {k: v[:, :37] for k, v in want.items()}, {k: v[:, :37] for k, v in scale.items()},
                  what=f"chain {name}, shorter batch")
+
+
+def test_dense_warp_shared_operand(ctx):
+    """A fixed versor applied to a batch of full multivectors, R X ~R in G(8): R is a broadcast batch (one
+    element, stride 0) read by both products."""
+    n, batch = 8, 90
+    metric = [1.0] * 7 + [-1.0]
+    full = tuple(range(n + 1))
+    rng = np.random.default_rng(5)
+    host = [{k: rng.uniform(-1, 1, (comb(n, k), 1 if s == 0 else batch)) for k in full} for s in range(2)]
+    build = lambda r, x: r * x * r.rev()  # noqa: E731
+    ast = build(pmv(Input(0, full)), pmv(Input(1, full))).specialize(metric)
+    want = oracle_eval(build, metric, host, [True, False], batch)
+    scale = oracle_abs_scale(build, metric, host, [True, False], batch)
+    plan = g.Plan(ctx, ast)
+    dev = [g.DeviceBatch.from_host(ctx, n, host[0], broadcast=True), g.DeviceBatch.from_host(ctx, n, host[1])]
+    out = plan.eval(dev, engine=L.ENGINE_DENSE_WARP)
+    ctx.sync()
+    assert "products=2" in plan.last_kernel()
+    assert_close(out.to_host(), want, scale, what="fixed versor sandwich, G(8)")
