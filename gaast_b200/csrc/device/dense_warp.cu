@@ -31,10 +31,11 @@
 // order): FMA arithmetic only, like the other dense lowerings; GAAST_ARITH_STRICT keeps using the
 // table engine.
 //
-// A plan qualifies (dense_warp_analyse) when every buffer carries the full grade set and its ops are:
-// inputs copied into operand buffers, sign flips of whole grades (Negation / Reverse / GradeInvolution),
+// A plan qualifies (dense_warp_analyse) when its ops are: inputs copied into operand buffers, sign flips of whole grades (Negation / Reverse / GradeInvolution),
 // and products, each written to a fresh buffer -- R * X * ~R, (A ^ B) * C, -(A * B) ... -- every product a
-// dense one that factorises as above.  The products run one after the other, intermediate results in
+// dense one that factorises as above.  Buffers need not carry every grade (rotors hold the even ones): the
+// kernel pads operands with zeros, runs the complete product and stores the destination's grades, provided
+// the pairs the plan lacks are exactly those the grade sets explain.  The products run one after the other, intermediate results in
 // scratch buffers of the plan, sign flips folded into the copies.  Everything else is untouched.
 #include <algorithm>
 #include <cstring>
@@ -57,18 +58,31 @@ const char kDenseWarpKernelText[] =
 #include "dense_warp_kernel_text.inc"
     ;
 
+// slot -> blade of a buffer with grade set `mask` (algebra.rs:221-246): grades ascending, masks of a grade in
+// ascending numeric order
+std::vector<uint16_t> blades_of_mask(uint32_t n, uint32_t mask) {
+    std::vector<uint16_t> v;
+    for (uint32_t k = 0; k <= n; ++k)
+        if (mask >> k & 1)
+            for (uint32_t b = 0; b < (1u << n); ++b)
+                if (uint32_t(__builtin_popcount(b)) == k) v.push_back(uint16_t(b));
+    return v;
+}
+
 // Tables of ONE product op: which pairs it keeps and with which sign, factorised over (high, low) parts.
-bool analyse_product(const DevicePlanHost& h, const gaast_op& mul, const std::vector<uint16_t>& blade_of,
-                     const std::vector<uint16_t>& slot_of, DenseWarpProduct* out) {
-    const uint32_t NB = 1u << h.n, J = NB / 32;
-    if (mul.term_count > uint64_t(NB) * NB || mul.term_count < uint64_t(NB)) return false;
-    // the coefficient table as presence and sign bits [a][b] (+-1 only) ...
+// maskL / maskR / maskO: grade sets of the operand buffers and of the destination buffer.
+bool analyse_product(const DevicePlanHost& h, const gaast_op& mul, uint32_t maskL, uint32_t maskR, uint32_t maskO,
+                     DenseWarpProduct* out) {
+    const uint32_t n = h.n, NB = 1u << n, J = NB / 32, full = (2u << n) - 1;
+    if (mul.term_count > uint64_t(NB) * NB || mul.term_count < 1) return false;
+    const std::vector<uint16_t> bl_of = blades_of_mask(n, maskL), br_of = blades_of_mask(n, maskR), bo_of = blades_of_mask(n, maskO);
+    // the coefficient table as presence and sign bits [a][b] over ALL blades (+-1 only) ...
     std::vector<uint8_t> seen(size_t(NB) * NB / 8, 0), neg(size_t(NB) * NB / 8, 0);
     for (uint32_t t = mul.term_begin; t < mul.term_begin + mul.term_count; ++t) {
         const gaast_term& tm = h.terms[t];
-        if (tm.a >= NB || tm.b >= NB || tm.out >= NB) return false;
-        const uint32_t ab = blade_of[tm.a], bb = blade_of[tm.b];
-        if (slot_of[ab ^ bb] != tm.out) return false;
+        if (tm.a >= bl_of.size() || tm.b >= br_of.size() || tm.out >= bo_of.size()) return false;
+        const uint32_t ab = bl_of[tm.a], bb = br_of[tm.b];
+        if (bo_of[tm.out] != (ab ^ bb)) return false;
         if (tm.coeff != 1.0 && tm.coeff != -1.0) return false;  // degenerate or scaled metric: table engine
         const size_t bit = size_t(ab) * NB + bb;
         if (seen[bit >> 3] >> (bit & 7) & 1) return false;
@@ -81,37 +95,102 @@ bool analyse_product(const DevicePlanHost& h, const gaast_op& mul, const std::ve
     };
     auto is_neg = [&](uint32_t ab, uint32_t bb) { return bit_of(neg, ab, bb); };
     auto present = [&](uint32_t ab, uint32_t bb) { return bit_of(seen, ab, bb); };
-    // Which pairs does the product keep?  A geometric product keeps all of them; outer products and
-    // contractions keep (a, b) iff a rule on the HIGH parts and the same rule on the LOW parts both hold
-    // (a & b == 0, a subset of b, ...).  That is the shape this engine can use:
-    //     present(a, b) = keep_hi(ahi, bhi) & keep_lo(alo, blo)
-    // and, on the kept pairs,   c(a, b) = sigma(ahi, bhi) * (-1)^(|ahi| |blo|) * lambda(alo, blo).
-    // Both are read from the plan's term table and verified pair by pair.
-    if (!present(0, 0)) return false;
+    auto chi = [](uint32_t ah, uint32_t bl) { return (__builtin_popcount(ah) & __builtin_popcount(bl) & 1) != 0; };
     std::vector<uint8_t> sigma(size_t(J) * J);  // 0 = +1, 1 = -1, 2 = pair of high parts dropped
     std::vector<uint32_t> lambda_words(32, 0), present_words(32, 0);
     bool complete = true;
-    for (uint32_t ah = 0; ah < J; ++ah)
-        for (uint32_t bh = 0; bh < J; ++bh)
-            sigma[ah * J + bh] = present(ah << 5, bh << 5) ? uint8_t(is_neg(ah << 5, bh << 5)) : uint8_t(2);
-    for (uint32_t al = 0; al < 32; ++al)
-        for (uint32_t bl = 0; bl < 32; ++bl) {
-            if (present(al, bl)) present_words[al] |= 1u << bl;
-            if (present(al, bl) && is_neg(al, bl)) lambda_words[al] |= 1u << bl;
-        }
-    for (uint32_t ab = 0; ab < NB; ++ab)
-        for (uint32_t bb = 0; bb < NB; ++bb) {
-            const uint32_t ah = ab >> 5, al = ab & 31, bh = bb >> 5, bl = bb & 31;
-            const bool keep = sigma[ah * J + bh] != 2 && (present_words[al] >> bl & 1);
-            if (keep != present(ab, bb)) return false;
-            if (!keep) {
-                complete = false;
-                continue;
+    if (maskL == full && maskR == full && maskO == full) {
+        // Which pairs does the product keep?  A geometric product keeps all of them; outer products and
+        // contractions keep (a, b) iff a rule on the HIGH parts and the same rule on the LOW parts both hold
+        // (a & b == 0, a subset of b, ...).  That is the shape this engine can use:
+        //     present(a, b) = keep_hi(ahi, bhi) & keep_lo(alo, blo)
+        // and, on the kept pairs,   c(a, b) = sigma(ahi, bhi) * (-1)^(|ahi| |blo|) * lambda(alo, blo).
+        // Both are read from the plan's term table and verified pair by pair.
+        if (!present(0, 0)) return false;
+        for (uint32_t ah = 0; ah < J; ++ah)
+            for (uint32_t bh = 0; bh < J; ++bh)
+                sigma[ah * J + bh] = present(ah << 5, bh << 5) ? uint8_t(is_neg(ah << 5, bh << 5)) : uint8_t(2);
+        for (uint32_t al = 0; al < 32; ++al)
+            for (uint32_t bl = 0; bl < 32; ++bl) {
+                if (present(al, bl)) present_words[al] |= 1u << bl;
+                if (present(al, bl) && is_neg(al, bl)) lambda_words[al] |= 1u << bl;
             }
-            const bool chi = (__builtin_popcount(ah) & __builtin_popcount(bl) & 1) != 0;
-            const bool want = bool(sigma[ah * J + bh] == 1) ^ chi ^ bool(lambda_words[al] >> bl & 1);
-            if (want != is_neg(ab, bb)) return false;
+        for (uint32_t ab = 0; ab < NB; ++ab)
+            for (uint32_t bb = 0; bb < NB; ++bb) {
+                const uint32_t ah = ab >> 5, al = ab & 31, bh = bb >> 5, bl = bb & 31;
+                const bool keep = sigma[ah * J + bh] != 2 && (present_words[al] >> bl & 1);
+                if (keep != present(ab, bb)) return false;
+                if (!keep) {
+                    complete = false;
+                    continue;
+                }
+                const bool want = bool(sigma[ah * J + bh] == 1) ^ chi(ah, bl) ^ bool(lambda_words[al] >> bl & 1);
+                if (want != is_neg(ab, bb)) return false;
+            }
+    } else {
+        // Grade-restricted buffers (rotors: even grades only, ...).  The kernel runs the COMPLETE product on operands
+        // padded with zeros and stores the destination's grades only, so the pairs the plan lacks must be
+        // exactly those a grade set explains (a geometric product restricted by its buffers) ...
+        for (uint32_t ab = 0; ab < NB; ++ab)
+            for (uint32_t bb = 0; bb < NB; ++bb) {
+                const bool grades_ok = (maskL >> __builtin_popcount(ab) & 1) && (maskR >> __builtin_popcount(bb) & 1) &&
+                                       (maskO >> __builtin_popcount(ab ^ bb) & 1);
+                if (grades_ok != present(ab, bb)) return false;
+            }
+        // ... and sigma, lambda are recovered from the pairs that ARE there: every one of them is an equation
+        //     sigma(ahi, bhi) xor lambda(alo, blo) = sign(a, b) xor chi(ahi, blo)   over GF(2),
+        // solved by propagation from cell to cell (cells no pair mentions are free: 0), then verified.
+        std::vector<int8_t> sg(size_t(J) * J, -1), lm(1024, -1);
+        std::vector<uint32_t> queue;  // cell ids: sigma cells [0, J*J), lambda cells J*J + [0, 1024)
+        auto solve_from = [&](uint32_t start) {
+            queue.assign(1, start);
+            while (!queue.empty()) {
+                const uint32_t c = queue.back();
+                queue.pop_back();
+                if (c < J * J) {
+                    const uint32_t ah = c / J, bh = c % J;
+                    for (uint32_t al = 0; al < 32; ++al)
+                        for (uint32_t bl = 0; bl < 32; ++bl) {
+                            const uint32_t ab = ah << 5 | al, bb = bh << 5 | bl;
+                            if (!present(ab, bb) || lm[al * 32 + bl] >= 0) continue;
+                            lm[al * 32 + bl] = int8_t(sg[c] ^ int(is_neg(ab, bb)) ^ int(chi(ah, bl)));
+                            queue.push_back(J * J + al * 32 + bl);
+                        }
+                } else {
+                    const uint32_t al = (c - J * J) / 32, bl = (c - J * J) % 32;
+                    for (uint32_t ah = 0; ah < J; ++ah)
+                        for (uint32_t bh = 0; bh < J; ++bh) {
+                            const uint32_t ab = ah << 5 | al, bb = bh << 5 | bl;
+                            if (!present(ab, bb) || sg[ah * J + bh] >= 0) continue;
+                            sg[ah * J + bh] = int8_t(lm[al * 32 + bl] ^ int(is_neg(ab, bb)) ^ int(chi(ah, bl)));
+                            queue.push_back(ah * J + bh);
+                        }
+                }
+            }
+        };
+        for (uint32_t ab = 0; ab < NB; ++ab)
+            for (uint32_t bb = 0; bb < NB; ++bb) {
+                if (!present(ab, bb)) continue;
+                const uint32_t c = (ab >> 5) * J + (bb >> 5);
+                if (sg[c] >= 0) continue;
+                if (lm[(ab & 31) * 32 + (bb & 31)] >= 0) continue;  // reached through its lambda cell below
+                sg[c] = 0;
+                solve_from(c);
+            }
+        for (uint32_t ab = 0; ab < NB; ++ab)
+            for (uint32_t bb = 0; bb < NB; ++bb) {
+                if (!present(ab, bb)) continue;
+                const uint32_t ah = ab >> 5, al = ab & 31, bh = bb >> 5, bl = bb & 31;
+                if (sg[ah * J + bh] < 0 || lm[al * 32 + bl] < 0) return false;
+                if ((sg[ah * J + bh] ^ lm[al * 32 + bl]) != (int(is_neg(ab, bb)) ^ int(chi(ah, bl)))) return false;
+            }
+        for (size_t i = 0; i < sigma.size(); ++i) sigma[i] = uint8_t(sg[i] > 0);
+        for (uint32_t al = 0; al < 32; ++al) {
+            present_words[al] = 0xFFFFFFFFu;
+            for (uint32_t bl = 0; bl < 32; ++bl)
+                if (lm[al * 32 + bl] > 0) lambda_words[al] |= 1u << bl;
         }
+    }
     out->lambda_words = std::move(lambda_words);
     out->present_words = std::move(present_words);
     out->sigma = sigma;
@@ -127,33 +206,24 @@ bool analyse_product(const DevicePlanHost& h, const gaast_op& mul, const std::ve
 
 }  // namespace
 
-// Is the plan a chain of dense products of full-grade buffers (see the head of this file)?  Fills the
-// program -- one step per product -- on success.
+// Is the plan a chain of dense products (see the head of this file)?  Fills the program -- one step per
+// product -- on success.
 bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
     const uint32_t n = h.n;
     if (n < 7 || n > 10) return false;
-    const uint32_t full = (2u << n) - 1, NB = 1u << n;
-    for (uint32_t m : h.buffer_masks)
-        if (m != full) return false;
-    // slot <-> blade (algebra.rs:221-246): grades ascending, masks of a grade in ascending numeric order
-    std::vector<uint16_t> blade_of(NB), slot_of(NB);
+    const uint32_t NB = 1u << n;
+    std::vector<uint16_t> blade_of = blades_of_mask(n, (2u << n) - 1);
     std::vector<int> gstart(n + 2, 0);
-    {
-        uint32_t s = 0;
-        for (uint32_t k = 0; k <= n; ++k) {
-            gstart[k] = int(s);
-            for (uint32_t b = 0; b < NB; ++b)
-                if (uint32_t(__builtin_popcount(b)) == k) blade_of[s++] = uint16_t(b);
-        }
-        gstart[n + 1] = int(s);
-        for (uint32_t i = 0; i < NB; ++i) slot_of[blade_of[i]] = uint16_t(i);
+    for (uint32_t k = 0, s = 0; k <= n + 1; ++k) {
+        gstart[k] = int(s);
+        if (k <= n) s += uint32_t(binomial(n, k));
     }
     // what every buffer holds as the ops go by (eval.rs fills a cache entry completely before it is read)
     struct State {
         int kind = 0;  // 0 empty, 1 a batch input, 2 a product
         int slot = -1, step = -1;
-        uint32_t neg = 0;
-        bool frozen = false;  // read as an operand: must not change any more
+        uint32_t neg = 0, mask = 0;  // sign flips so far; grades that hold data
+        bool frozen = false;         // read as an operand: must not change any more
     };
     std::vector<State> st(h.buffer_masks.size());
     DenseWarpHost prog;
@@ -163,18 +233,20 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
         if (op.dst >= st.size()) return false;
         State& d = st[op.dst];
         if (d.frozen) return false;
+        const uint32_t bm = h.buffer_masks[op.dst];
         switch (op.kind) {
             case GAAST_OP_ADD_INPUT: {
                 const gaast_input_desc& in = h.inputs[op.a];
-                if (d.kind != 0 || op.mask != full || in.kind != GAAST_INPUT_BATCH || in.grade_mask != full) return false;
+                if (d.kind != 0 || in.kind != GAAST_INPUT_BATCH) return false;
                 d.kind = 1;
                 d.slot = int(in.slot);
-                d.neg = 0;  // sign flips of an empty buffer flipped zeros
+                d.mask = op.mask & in.grade_mask & bm;  // graded.rs:67-78: the grades both sides have
+                d.neg = 0;                              // sign flips of an empty buffer flipped zeros
                 break;
             }
             case GAAST_OP_NEG_GRADES:
-                if (d.kind == 2) prog.steps[size_t(d.step)].O.neg_mask ^= op.mask;
-                d.neg ^= op.mask;  // (an empty buffer: zeros stay zeros; the mask is reset when it is filled)
+                if (d.kind == 2) prog.steps[size_t(d.step)].O.neg_mask ^= op.mask & bm;
+                d.neg ^= op.mask & bm;  // (an empty buffer: zeros stay zeros; the mask is reset when it is filled)
                 break;
             case GAAST_OP_MUL_TERMS: {
                 if (d.kind != 0 || op.a >= st.size() || op.b >= st.size() || op.a == op.dst || op.b == op.dst) return false;
@@ -182,9 +254,11 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
                 if (l.kind == 0 || r.kind == 0) return false;
                 l.frozen = r.frozen = true;
                 DenseWarpStep step;
-                if (!analyse_product(h, op, blade_of, slot_of, &step.prod)) return false;
+                // (an input-backed buffer may hold fewer grades than it declares: the missing ones are zeros either way)
+                if (!analyse_product(h, op, h.buffer_masks[op.a], h.buffer_masks[op.b], bm, &step.prod)) return false;
                 auto source = [&](const State& s) {
                     DenseWarpOperand o;
+                    o.grade_mask = s.mask;
                     if (s.kind == 1) {
                         o.slot = s.slot;
                         o.neg_mask = s.neg;
@@ -199,9 +273,11 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
                 if (step.R.slot < 0 && step.R.scratch < 0) return false;
                 if (op.dst == 0) step.O.root = true;
                 else step.O.scratch = n_scratch++;
+                step.O.grade_mask = bm;
                 d.kind = 2;
                 d.step = int(prog.steps.size());
                 d.neg = 0;
+                d.mask = bm;
                 prog.steps.push_back(std::move(step));
                 break;
             }
@@ -216,6 +292,7 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
     for (const DenseWarpStep& s : prog.steps) prog.complete = prog.complete && s.prod.complete;
     prog.blade_of_slot = std::move(blade_of);
     prog.gstart = std::move(gstart);
+    (void)NB;
     if (out) *out = std::move(prog);
     return true;
 }
@@ -281,6 +358,9 @@ cudaError_t dense_warp_launch(const DenseWarpHost& prog, const DenseWarpStep& st
         d.Op[k] = O.ptr[k];
         d.Orow[k] = O.row[k];
     }
+    d.Lmask = step.L.grade_mask;
+    d.Rmask = step.R.grade_mask;
+    d.Omask = step.O.grade_mask;
     d.Lstep = L.shared ? 0 : 1;
     d.Rstep = R.shared ? 0 : 1;
     d.Lneg = step.L.neg_mask;

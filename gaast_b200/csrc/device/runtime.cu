@@ -1,5 +1,6 @@
 // C ABI of the device side (include/gaast_b200.h): ctx, batch, plan, eval.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -607,7 +608,11 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         }
         if (!jk && engine == GAAST_ENGINE_SPECIALIZED) throw Error(GAAST_ERR_JIT, plan->jit_error);
         // too large / too wide to specialise: a full high-dimensional product still has a fast engine
-        if (!jk && engine == GAAST_ENGINE_AUTO && dense_warp_ready()) use_dense_warp = true;
+        // (the engine always runs COMPLETE 4^n products: worth it while the plan keeps at least 1/16 of those
+        // pairs -- the table engine is 10-20x slower per term)
+        if (!jk && engine == GAAST_ENGINE_AUTO && dense_warp_ready() &&
+            double(h.total_terms) * 16.0 >= double(plan->dense_warp.steps.size()) * std::pow(4.0, double(h.n)))
+            use_dense_warp = true;
     } else if (engine != GAAST_ENGINE_TABLE && engine != GAAST_ENGINE_AUTO) {
         throw Error(GAAST_ERR_INVALID, "unknown engine");
     }
@@ -629,15 +634,19 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         }
         auto buffers_of = [&](const gaast::DenseWarpOperand& o) {
             gaast::DenseWarpBuffers b;
+            size_t root_stream = h.n_in_streams;  // the root's grade arrays follow the inputs, grades ascending
             for (uint32_t k = 0; k <= h.n; ++k) {
+                if (!(o.grade_mask >> k & 1)) continue;  // no data / not stored: the kernel never touches it
                 if (o.slot >= 0) {
                     const int si = h.stream_of(uint32_t(o.slot), k);
+                    if (si < 0) throw Error(GAAST_ERR_INVALID, "dense-warp engine: the plan has no stream for a grade it reads");
                     b.ptr[k] = a.sptr[si];
                     b.row[k] = a.srow[si];
                     b.shared = (bslots >> o.slot) & 1;  // a fixed operand (the rotor of R X ~R): stride 0
                 } else if (o.root) {
-                    b.ptr[k] = a.sptr[h.n_in_streams + k];  // the root holds every grade, ascending
-                    b.row[k] = a.srow[h.n_in_streams + k];
+                    b.ptr[k] = a.sptr[root_stream];
+                    b.row[k] = a.srow[root_stream];
+                    ++root_stream;
                 } else {
                     b.ptr[k] = plan->d_dw_scratch[size_t(o.scratch)] + size_t(prog.gstart[k]) * plan->dw_scratch_stride;
                     b.row[k] = (long long)plan->dw_scratch_stride;

@@ -109,6 +109,7 @@ struct DenseWarpOperand {   // where a full-grade buffer lives when a product re
     int scratch = -1;       // >= 0: a scratch buffer of the plan (an earlier product)
     bool root = false;      // the root's grade arrays (written by the last product)
     uint32_t neg_mask = 0;  // grades whose sign flips on the way (Negation / Reverse / GradeInvolution)
+    uint32_t grade_mask = 0;  // grades that hold data (operand) / that are stored (result)
 };
 struct DenseWarpStep {
     DenseWarpProduct prod;

@@ -125,7 +125,7 @@ typedef enum gaast_engine {
     GAAST_ENGINE_TABLE = 1,       /* generic table-driven kernels compiled into this library */
     GAAST_ENGINE_SPECIALIZED = 2, /* straight-line sm_100a kernel generated from the plan */
     GAAST_ENGINE_DENSE_WARP = 3   /* one warp per multivector: chains of dense products (geometric, outer,
-                                     contraction) of full-grade operands in G(n), n = 7..10, +-1 metric, FMA
+                                     contraction) of multivectors in G(n), n = 7..10, +-1 metric, FMA
                                      arithmetic (GAAST_ERR_UNSUPPORTED for any other plan).  AUTO picks it when
                                      such a plan is too large to specialise. */
 } gaast_engine;

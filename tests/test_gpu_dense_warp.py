@@ -66,7 +66,6 @@ def test_dense_warp_refuses_other_plans(ctx):
     a, b = pmv(Input(0, full)), pmv(Input(1, full))
     dev = [g.DeviceBatch.alloc(ctx, n, full, 64) for _ in range(2)]
     for ast in (((a * b) + a).specialize([1.0] * n),                # a sum lands in the product's buffer
-                (a * b).g(2).specialize([1.0] * n),                  # the root is not the full grade set
                 (a * b).specialize([1.0] * 6 + [0.0]),               # degenerate metric: zero coefficients
                 (a * b).specialize([1.0] * 6 + [2.0])):              # scaled metric: |coefficient| != 1
         plan = g.Plan(ctx, ast)
@@ -162,3 +161,34 @@ def test_dense_warp_shared_operand(ctx):
     ctx.sync()
     assert "products=2" in plan.last_kernel()
     assert_close(out.to_host(), want, scale, what="fixed versor sandwich, G(8)")
+
+
+@pytest.mark.parametrize("n,name", [(8, "rotor_product"), (8, "rotor_sandwich"), (9, "rotor_chain"), (8, "odd_times_even"),
+                                    (7, "projected_root")])
+def test_dense_warp_grade_restricted_buffers(ctx, n, name):
+    """Rotors hold the even grades only.  Their products in G(8) / G(9) are too wide to specialise; the
+    dense-warp kernel pads the operands with zeros, runs the complete product and stores the destination's
+    grades.  sigma and lambda are recovered from the pairs the plan does have."""
+    metric = [1.0] * (n - 2) + [-1.0] * 2
+    even, odd, full = tuple(range(0, n + 1, 2)), tuple(range(1, n + 1, 2)), tuple(range(n + 1))
+    slots, build = {
+        "rotor_product": ([even, even], lambda a, b: a * b),
+        "rotor_sandwich": ([even, full], lambda r, x: r * x * r.rev()),
+        "rotor_chain": ([even, even, even], lambda a, b, c: (a * b) * c.rev()),
+        "odd_times_even": ([odd, even], lambda a, b: (a * b).ginvol()),
+        "projected_root": ([full, full], lambda a, b: (a * b).g(2)),
+    }[name]
+    batch = 45
+    rng = np.random.default_rng(n + len(name))
+    host = [{k: rng.uniform(-1, 1, (comb(n, k), batch)) for k in gr} for gr in slots]
+    ast = build(*[pmv(Input(s, gr)) for s, gr in enumerate(slots)]).specialize(metric)
+    want = oracle_eval(build, metric, host, [False] * len(slots), batch)
+    scale = oracle_abs_scale(build, metric, host, [False] * len(slots), batch)
+    plan = g.Plan(ctx, ast)
+    dev = [g.DeviceBatch.from_host(ctx, n, h) for h in host]
+    out = plan.eval(dev, engine=L.ENGINE_DENSE_WARP)
+    ctx.sync()
+    assert "engine=dense_warp" in plan.last_kernel()
+    got = out.to_host()
+    assert sorted(got) == plan.root_grades() == sorted(want)
+    assert_close(got, want, scale, what=f"G({n}) {name}")
