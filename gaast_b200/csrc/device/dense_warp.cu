@@ -361,6 +361,9 @@ cudaError_t dense_warp_launch(const DenseWarpHost& prog, const DenseWarpStep& st
     d.Lmask = step.L.grade_mask;
     d.Rmask = step.R.grade_mask;
     d.Omask = step.O.grade_mask;
+    const unsigned full_mask = (2u << prog.n) - 1;
+    d.plain = step.L.grade_mask == full_mask && step.R.grade_mask == full_mask && !step.L.neg_mask && !step.R.neg_mask &&
+              !L.shared && !R.shared;
     d.Lstep = L.shared ? 0 : 1;
     d.Rstep = R.shared ? 0 : 1;
     d.Lneg = step.L.neg_mask;
