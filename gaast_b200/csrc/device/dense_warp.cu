@@ -324,6 +324,9 @@ CodegenResult dense_warp_codegen(uint32_t n, const DenseWarpProduct& prod, const
     for (size_t i = 0; i < prod.sigma.size(); ++i) src += (i ? "," : "") + std::to_string(int(prod.sigma[i]));
     src += "};\n#define GAAST_DW_SIGMA_NEG(ahi, g) (kDwSigma[(ahi) * GAAST_DW_J + (g)] == 1)\n"
            "#define GAAST_DW_SIGMA_ABSENT(ahi, g) (kDwSigma[(ahi) * GAAST_DW_J + (g)] == 2)\n";
+    bool all_kept = true;
+    for (uint32_t w : prod.present_words) all_kept = all_kept && w == 0xFFFFFFFFu;
+    if (all_kept) src += "#define GAAST_DW_ALL_KEPT 1\n";
     src += kDenseWarpKernelText;
     src += "\nextern \"C\" __global__ void __launch_bounds__(" + std::to_string(shape.threads) +
            ") gaast_dense_warp(const __grid_constant__ DenseWarpArgs d) {\n  dense_warp_body<GAAST_DW_J>(d);\n}\n";
