@@ -106,3 +106,20 @@ def test_offline_precompile_of_a_dense_warp_plan():
     with pytest.raises(L.GaastError) as ei:
         bad.precompile(0, L.ARITH_FMA, False, True)
     assert ei.value.status == L.ERR_JIT
+
+
+def test_offline_analysis_of_dense_warp_chains_and_grade_restricted_plans():
+    """The dense-warp analysis without a device: product chains, grade-restricted buffers (sigma / lambda
+    recovered by GF(2) propagation), outer products; and plans it must leave alone."""
+    from gaast_b200.device import Plan
+    from gaast_b200.expr import Input, mv as pmv
+    n = 8
+    metric = [1.0] * 6 + [-1.0] * 2
+    full, even = tuple(range(n + 1)), tuple(range(0, n + 1, 2))
+    a, b, r = pmv(Input(0, full)), pmv(Input(1, full)), pmv(Input(2, even))
+    for expr, products in ((a * b, 1), (r * a * r.rev(), 2), ((a ^ b) * r, 2), (-(a * b), 1)):
+        info = Plan(None, expr.specialize(metric)).precompile(0, L.ARITH_FMA, False, True)
+        assert "gaast_dense_warp" in info and f"x{products} product(s)" in info, info
+    for expr in (a * b + a, (a * b).norm_sq().sqrt() * a):  # a sum in the product's buffer; a scalar op
+        with pytest.raises(L.GaastError):
+            Plan(None, expr.specialize(metric)).precompile(0, L.ARITH_FMA, False, True)
