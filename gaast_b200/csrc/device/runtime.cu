@@ -608,10 +608,12 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         }
         if (!jk && engine == GAAST_ENGINE_SPECIALIZED) throw Error(GAAST_ERR_JIT, plan->jit_error);
         // too large / too wide to specialise: a full high-dimensional product still has a fast engine
-        // (the engine always runs COMPLETE 4^n products: worth it while the plan keeps at least 1/16 of those
-        // pairs -- the table engine is 10-20x slower per term)
+        // (the engine always runs COMPLETE 4^n products.  Measured per kept pair: 12-15 TFLOP/s against 1.2-2.1 on
+        // the table engine at n = 7, 8 -- worth it while the plan keeps at least 1/8 of the pairs; at n = 9, 10 the
+        // table engine's workspace is in global memory (0.09 TFLOP/s): 1/64.  exp/rotor_square.py, exp/big_products.py)
+        const double min_density = h.n <= 8 ? 1.0 / 8.0 : 1.0 / 64.0;
         if (!jk && engine == GAAST_ENGINE_AUTO && dense_warp_ready() &&
-            double(h.total_terms) * 16.0 >= double(plan->dense_warp.steps.size()) * std::pow(4.0, double(h.n)))
+            double(h.total_terms) >= min_density * double(plan->dense_warp.steps.size()) * std::pow(4.0, double(h.n)))
             use_dense_warp = true;
     } else if (engine != GAAST_ENGINE_TABLE && engine != GAAST_ENGINE_AUTO) {
         throw Error(GAAST_ERR_INVALID, "unknown engine");
