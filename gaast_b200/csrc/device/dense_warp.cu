@@ -220,8 +220,9 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
     }
     // what every buffer holds as the ops go by (eval.rs fills a cache entry completely before it is read)
     struct State {
-        int kind = 0;  // 0 empty, 1 a batch input, 2 a product
+        int kind = 0;  // 0 empty, 1 a batch input, 2 a product (or a sum of products)
         int slot = -1, step = -1;
+        std::vector<int> writers;  // products that landed in this buffer, in order
         uint32_t neg = 0, mask = 0;  // sign flips so far; grades that hold data
         bool frozen = false;         // read as an operand: must not change any more
     };
@@ -245,11 +246,13 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
                 break;
             }
             case GAAST_OP_NEG_GRADES:
-                if (d.kind == 2) prog.steps[size_t(d.step)].O.neg_mask ^= op.mask & bm;
+                // flips everything the buffer holds at this point (the in-place quirk included)
+                for (int w : d.writers) prog.steps[size_t(w)].O.neg_mask ^= op.mask & bm;
                 d.neg ^= op.mask & bm;  // (an empty buffer: zeros stay zeros; the mask is reset when it is filled)
                 break;
             case GAAST_OP_MUL_TERMS: {
-                if (d.kind != 0 || op.a >= st.size() || op.b >= st.size() || op.a == op.dst || op.b == op.dst) return false;
+                // the destination is fresh, or holds earlier products of the same sum (A*B + C*D, A*B - B*A)
+                if (d.kind == 1 || op.a >= st.size() || op.b >= st.size() || op.a == op.dst || op.b == op.dst) return false;
                 State &l = st[op.a], &r = st[op.b];
                 if (l.kind == 0 || r.kind == 0) return false;
                 l.frozen = r.frozen = true;
@@ -271,11 +274,18 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
                 step.R = source(r);
                 if (step.L.slot < 0 && step.L.scratch < 0) return false;  // (the root is never an operand)
                 if (step.R.slot < 0 && step.R.scratch < 0) return false;
-                if (op.dst == 0) step.O.root = true;
-                else step.O.scratch = n_scratch++;
-                step.O.grade_mask = bm;
+                if (d.kind == 2) {
+                    step.O = prog.steps[size_t(d.step)].O;  // same place as the first product of the sum ...
+                    step.O.neg_mask = 0;                    // ... flips from here on only
+                    step.accumulate = true;
+                } else {
+                    if (op.dst == 0) step.O.root = true;
+                    else step.O.scratch = n_scratch++;
+                    step.O.grade_mask = bm;
+                    d.step = int(prog.steps.size());
+                }
                 d.kind = 2;
-                d.step = int(prog.steps.size());
+                d.writers.push_back(int(prog.steps.size()));
                 d.neg = 0;
                 d.mask = bm;
                 prog.steps.push_back(std::move(step));
@@ -285,8 +295,7 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
         }
     }
     if (prog.steps.empty() || st[0].kind != 2) return false;
-    for (size_t i = 0; i + 1 < prog.steps.size(); ++i)
-        if (prog.steps[i].O.root) return false;  // the root must be the last product
+    // (products that write the root come last in eval.rs' order: nothing reads the root)
     prog.n_scratch = n_scratch;
     prog.complete = true;
     for (const DenseWarpStep& s : prog.steps) prog.complete = prog.complete && s.prod.complete;
@@ -367,6 +376,7 @@ cudaError_t dense_warp_launch(const DenseWarpHost& prog, const DenseWarpStep& st
     const unsigned full_mask = (2u << prog.n) - 1;
     d.plain = step.L.grade_mask == full_mask && step.R.grade_mask == full_mask && !step.L.neg_mask && !step.R.neg_mask &&
               !L.shared && !R.shared;
+    d.accumulate = step.accumulate ? 1 : 0;
     d.Lstep = L.shared ? 0 : 1;
     d.Rstep = R.shared ? 0 : 1;
     d.Lneg = step.L.neg_mask;

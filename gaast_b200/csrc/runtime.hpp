@@ -114,6 +114,7 @@ struct DenseWarpOperand {   // where a full-grade buffer lives when a product re
 struct DenseWarpStep {
     DenseWarpProduct prod;
     DenseWarpOperand L, R, O;
+    bool accumulate = false;  // O already holds an earlier product of the same sum: add to it
 };
 struct DenseWarpHost {
     uint32_t n = 0;

@@ -65,7 +65,7 @@ def test_dense_warp_refuses_other_plans(ctx):
     full = tuple(range(n + 1))
     a, b = pmv(Input(0, full)), pmv(Input(1, full))
     dev = [g.DeviceBatch.alloc(ctx, n, full, 64) for _ in range(2)]
-    for ast in (((a * b) + a).specialize([1.0] * n),                # a sum lands in the product's buffer
+    for ast in (((a * b) + a).specialize([1.0] * n),                # an input added into the product's buffer
                 (a * b).specialize([1.0] * 6 + [0.0]),               # degenerate metric: zero coefficients
                 (a * b).specialize([1.0] * 6 + [2.0])):              # scaled metric: |coefficient| != 1
         plan = g.Plan(ctx, ast)
@@ -112,6 +112,11 @@ CHAINS = {
     "involuted_operand": lambda a, b, c: (a * b).ginvol() * c.conj(),
     "reused_product": lambda a, b, c: (lambda p: p * p.clone())(a * b),  # one cached product, both operands
     "three_deep": lambda a, b, c: ((a * b) * c) * (b << a),
+    # sums of products land in one buffer (eval.rs:51-54); the subtraction carries the reference's in-place
+    # quirk (the negation flips what the buffer already holds), which the oracle reproduces
+    "commutator": lambda a, b, c: a * b - b * a,
+    "sum_of_products": lambda a, b, c: a * b + c * a,
+    "sum_then_product": lambda a, b, c: (a * b + (b ^ c)) * c,
 }
 
 
