@@ -223,6 +223,7 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
         int kind = 0;  // 0 empty, 1 a batch input, 2 a product (or a sum of products)
         int slot = -1, step = -1;
         std::vector<int> writers;  // products that landed in this buffer, in order
+        int addend_step = -1;      // the product whose store also adds a batch input into this buffer
         uint32_t neg = 0, mask = 0;  // sign flips so far; grades that hold data
         bool frozen = false;         // read as an operand: must not change any more
     };
@@ -238,7 +239,18 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
         switch (op.kind) {
             case GAAST_OP_ADD_INPUT: {
                 const gaast_input_desc& in = h.inputs[op.a];
-                if (d.kind != 0 || in.kind != GAAST_INPUT_BATCH) return false;
+                if (in.kind != GAAST_INPUT_BATCH) return false;
+                if (d.kind == 2) {
+                    // A*B + C: the input joins the store of the buffer's first product (one addend per buffer)
+                    if (d.addend_step >= 0) return false;
+                    DenseWarpStep& first = prog.steps[size_t(d.writers.front())];
+                    first.C.slot = int(in.slot);
+                    first.C.grade_mask = op.mask & in.grade_mask & bm;
+                    first.C.neg_mask = 0;
+                    d.addend_step = d.writers.front();
+                    break;
+                }
+                if (d.kind != 0) return false;
                 d.kind = 1;
                 d.slot = int(in.slot);
                 d.mask = op.mask & in.grade_mask & bm;  // graded.rs:67-78: the grades both sides have
@@ -248,11 +260,12 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
             case GAAST_OP_NEG_GRADES:
                 // flips everything the buffer holds at this point (the in-place quirk included)
                 for (int w : d.writers) prog.steps[size_t(w)].O.neg_mask ^= op.mask & bm;
+                if (d.addend_step >= 0) prog.steps[size_t(d.addend_step)].C.neg_mask ^= op.mask & bm;
                 d.neg ^= op.mask & bm;  // (an empty buffer: zeros stay zeros; the mask is reset when it is filled)
                 break;
             case GAAST_OP_MUL_TERMS: {
                 // the destination is fresh, or holds earlier products of the same sum (A*B + C*D, A*B - B*A)
-                if (d.kind == 1 || op.a >= st.size() || op.b >= st.size() || op.a == op.dst || op.b == op.dst) return false;
+                if (op.a >= st.size() || op.b >= st.size() || op.a == op.dst || op.b == op.dst) return false;
                 State &l = st[op.a], &r = st[op.b];
                 if (l.kind == 0 || r.kind == 0) return false;
                 l.frozen = r.frozen = true;
@@ -274,6 +287,14 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
                 step.R = source(r);
                 if (step.L.slot < 0 && step.L.scratch < 0) return false;  // (the root is never an operand)
                 if (step.R.slot < 0 && step.R.scratch < 0) return false;
+                if (d.kind == 1) {
+                    // C + A*B: the buffer holds an input so far; it becomes the addend of this product's store
+                    step.C.slot = d.slot;
+                    step.C.grade_mask = d.mask;
+                    step.C.neg_mask = d.neg;
+                    d.addend_step = int(prog.steps.size());
+                    d.kind = 0;
+                }
                 if (d.kind == 2) {
                     step.O = prog.steps[size_t(d.step)].O;  // same place as the first product of the sum ...
                     step.O.neg_mask = 0;                    // ... flips from here on only
@@ -351,7 +372,7 @@ CodegenResult dense_warp_codegen(uint32_t n, const DenseWarpProduct& prod, const
 // One product of the program.  `jit_kernel`: its per-plan kernel (sigma compile-time), or null for the
 // generic kernel of this library (complete tables only).  L / R / O: per-grade arrays, see DenseWarpArgs.
 cudaError_t dense_warp_launch(const DenseWarpHost& prog, const DenseWarpStep& step, const DenseWarpBuffers& L,
-                              const DenseWarpBuffers& R, const DenseWarpBuffers& O, long long batch,
+                              const DenseWarpBuffers& R, const DenseWarpBuffers& O, const DenseWarpBuffers& C, long long batch,
                               const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaKernel_t jit_kernel,
                               cudaStream_t stream) {
     DenseWarpArgs d;
@@ -377,6 +398,13 @@ cudaError_t dense_warp_launch(const DenseWarpHost& prog, const DenseWarpStep& st
     d.plain = step.L.grade_mask == full_mask && step.R.grade_mask == full_mask && !step.L.neg_mask && !step.R.neg_mask &&
               !L.shared && !R.shared;
     d.accumulate = step.accumulate ? 1 : 0;
+    d.Cmask = step.C.slot >= 0 ? step.C.grade_mask : 0u;
+    d.Cneg = step.C.neg_mask;
+    d.Cstep = C.shared ? 0 : 1;
+    for (uint32_t k = 0; k <= prog.n; ++k) {
+        d.Cp[k] = C.ptr[k];
+        d.Crow[k] = C.row[k];
+    }
     d.Lstep = L.shared ? 0 : 1;
     d.Rstep = R.shared ? 0 : 1;
     d.Lneg = step.L.neg_mask;

@@ -660,7 +660,8 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         for (size_t i = 0; i < prog.steps.size(); ++i) {
             const gaast::DenseWarpStep& step = prog.steps[i];
             dwk = dense_warp_kernel_for(int(i), shape);
-            cuda_check(gaast::dense_warp_launch(prog, step, buffers_of(step.L), buffers_of(step.R), buffers_of(step.O), n,
+            cuda_check(gaast::dense_warp_launch(prog, step, buffers_of(step.L), buffers_of(step.R), buffers_of(step.O),
+                                                step.C.slot >= 0 ? buffers_of(step.C) : gaast::DenseWarpBuffers(), n,
                                                 plan->d_dw_blades, shape, dwk ? dwk->kernel : nullptr, ctx->stream),
                        "launch dense-warp engine");
             ctx->launches++;

@@ -115,6 +115,7 @@ struct DenseWarpStep {
     DenseWarpProduct prod;
     DenseWarpOperand L, R, O;
     bool accumulate = false;  // O already holds an earlier product of the same sum: add to it
+    DenseWarpOperand C;       // optional addend (slot >= 0): a batch input summed into the same buffer
 };
 struct DenseWarpHost {
     uint32_t n = 0;
@@ -136,7 +137,7 @@ struct DenseWarpLaunch {
 bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out);
 DenseWarpLaunch dense_warp_shape(const gaast_ctx& ctx, uint32_t n, long long batch);
 cudaError_t dense_warp_launch(const DenseWarpHost& prog, const DenseWarpStep& step, const DenseWarpBuffers& L,
-                              const DenseWarpBuffers& R, const DenseWarpBuffers& O, long long batch,
+                              const DenseWarpBuffers& R, const DenseWarpBuffers& O, const DenseWarpBuffers& C, long long batch,
                               const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaKernel_t jit_kernel,
                               cudaStream_t stream);
 CodegenResult dense_warp_codegen(uint32_t n, const DenseWarpProduct& prod, const DenseWarpLaunch& shape);

@@ -120,6 +120,8 @@ def test_offline_analysis_of_dense_warp_chains_and_grade_restricted_plans():
     for expr, products in ((a * b, 1), (r * a * r.rev(), 2), ((a ^ b) * r, 2), (-(a * b), 1)):
         info = Plan(None, expr.specialize(metric)).precompile(0, L.ARITH_FMA, False, True)
         assert "gaast_dense_warp" in info and f"x{products} product(s)" in info, info
-    for expr in (a * b + a, (a * b).norm_sq().sqrt() * a):  # a sum in the product's buffer; a scalar op
+    info = Plan(None, (a * b + a).specialize(metric)).precompile(0, L.ARITH_FMA, False, True)
+    assert "gaast_dense_warp" in info  # an input added into the product's buffer joins the product's store
+    for expr in ((a * b).norm_sq().sqrt() * a, (a * b) * 2.5):  # a scalar op; a literal operand
         with pytest.raises(L.GaastError):
             Plan(None, expr.specialize(metric)).precompile(0, L.ARITH_FMA, False, True)

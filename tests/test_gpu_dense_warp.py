@@ -65,7 +65,7 @@ def test_dense_warp_refuses_other_plans(ctx):
     full = tuple(range(n + 1))
     a, b = pmv(Input(0, full)), pmv(Input(1, full))
     dev = [g.DeviceBatch.alloc(ctx, n, full, 64) for _ in range(2)]
-    for ast in (((a * b) + a).specialize([1.0] * n),                # an input added into the product's buffer
+    for ast in (((a * b).norm_sq().sqrt() * a).specialize([1.0] * n),  # a scalar op in the chain
                 (a * b).specialize([1.0] * 6 + [0.0]),               # degenerate metric: zero coefficients
                 (a * b).specialize([1.0] * 6 + [2.0])):              # scaled metric: |coefficient| != 1
         plan = g.Plan(ctx, ast)
@@ -117,6 +117,10 @@ CHAINS = {
     "commutator": lambda a, b, c: a * b - b * a,
     "sum_of_products": lambda a, b, c: a * b + c * a,
     "sum_then_product": lambda a, b, c: (a * b + (b ^ c)) * c,
+    # an input added into a product's buffer joins that product's store, whichever comes first
+    "product_plus_input": lambda a, b, c: a * b + c,
+    "input_plus_product": lambda a, b, c: c + a * b,
+    "negated_product_plus_input": lambda a, b, c: (-(a * b)) + c.rev(),
 }
 
 
