@@ -117,11 +117,12 @@ typedef struct gaast_plan_desc {
 /* ------------------------------------------------------------- handles ---- */
 typedef struct gaast_ctx gaast_ctx;     /* one device + one stream */
 typedef struct gaast_plan gaast_plan;   /* validated plan + its device tables + compiled kernels */
-typedef struct gaast_batch gaast_batch; /* device-resident SoA batch: one f64 array per grade */
+typedef struct gaast_batch gaast_batch; /* device-resident SoA batch: one f64 (or f32) array per grade */
 
 /* Evaluation engines (all run on the GPU; there is no host engine). */
 typedef enum gaast_engine {
-    GAAST_ENGINE_AUTO = 0,        /* specialised if NVRTC is usable, else table */
+    GAAST_ENGINE_AUTO = 0,        /* specialised when the plan can be specialised (NVRTC or the kernel cache),
+                                     dense-warp for large dense product chains in G(7..10), else table */
     GAAST_ENGINE_TABLE = 1,       /* generic table-driven kernels compiled into this library */
     GAAST_ENGINE_SPECIALIZED = 2, /* straight-line sm_100a kernel generated from the plan */
     GAAST_ENGINE_DENSE_WARP = 3   /* one warp per multivector: chains of dense products (geometric, outer,
