@@ -12,8 +12,10 @@ reference itself (tests/test_oracle_reference_kats.py): the 4 end-to-end
 `eval.rs` known-answer tests, the 5 `algebra.rs`, the 20 `grade_set.rs` and the
 1 `graded.rs` tests.  Those tests only cover G(3,0) and the degenerate metric
 [0,1,1]; coefficients under NEGATIVE signature, n > 3, contractions and
-`ginvol` are *parity-unpinned beyond source reading* of algebra.rs:73-83 and
-are covered here by algebraic-identity property tests instead.
+`ginvol` are *parity-unpinned by the reference's own vectors* (source reading of
+algebra.rs:73-83) and are covered here by algebraic-identity property tests and by
+an independent model of the same algebras as complex matrix algebras
+(tests/test_oracle_matrix_rep.py: G(4,1), G(2,2), G(6,0), G(4,3) ...) instead.
 
 Arithmetic: phase 4 is `f64` `*`, `+`, `1.0/x`, `sqrt` (eval.rs:82,107-108;
 graded.rs:63,74).  numpy float64 elementwise ops are IEEE-754 correctly rounded
