@@ -186,3 +186,98 @@ def test_reverse_involution_and_versor_sandwich(metric):
     ev = go.mv(go.GradeMapMV(v1)) * go.mv(go.GradeMapMV(v2))
     got = oracle_eval((ev.clone() * go.mv(go.GradeMapMV(x)) * ev.vinv()).g(1), metric)
     assert np.allclose(got[1], want[1], rtol=0, atol=1e-10), "versor sandwich"
+
+
+# ---- the BASELINE workloads themselves, evaluated with matrices --------------------------------
+class MatMV:
+    """A multivector as a matrix, with just the operators the workload expressions use.  Grade
+    selection goes through the trace readback, everything else is matrix algebra."""
+
+    def __init__(self, space, m):
+        self.s, self.m = space, m
+
+    def parts(self):
+        return {k: v for k, v in from_matrix(self.s["blades"], self.m, range(self.s["n"] + 1)).items()}
+
+    def part(self, k):
+        comps = from_matrix(self.s["blades"], self.m, [k])
+        return MatMV(self.s, to_matrix(self.s["blades"], comps))
+
+    def clone(self):
+        return self
+
+    def __add__(self, o):
+        return MatMV(self.s, self.m + o.m)
+
+    def __mul__(self, o):
+        return MatMV(self.s, self.m @ o.m)
+
+    def _select(self, o, target):
+        n = self.s["n"]
+        out = np.zeros_like(self.m)
+        for k in range(n + 1):
+            for l in range(n + 1):
+                t = target(k, l)
+                if 0 <= t <= n:
+                    out = out + (self.part(k) * o.part(l)).part(t).m
+        return MatMV(self.s, out)
+
+    def __xor__(self, o):  # outer product
+        return self._select(o, lambda k, l: k + l)
+
+    def __and__(self, o):  # inner product (expr.rs:180-197: nothing when either grade is 0)
+        return self._select(o, lambda k, l: abs(k - l) if k and l else -1)
+
+    def g(self, k):
+        return self.part(k)
+
+    def rev(self):
+        out = np.zeros_like(self.m)
+        for k in range(self.s["n"] + 1):
+            out = out + self.part(k).m * (-1.0 if (k * (k - 1) // 2) % 2 else 1.0)
+        return MatMV(self.s, out)
+
+    def vinv(self):  # versor inverse: the matrix inverse
+        return MatMV(self.s, np.linalg.inv(self.m))
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_full", "cfg3", "cfg4", "cfg5"])
+def test_baseline_workloads_against_matrix_algebra(name):
+    """The five BASELINE expressions -- G(3,0), G(4,1), G(6,0), G(10,0) and G(8,4) -- on the benchmark's own
+    synthetic inputs: oracle vs matrix algebra (128 x 128 complex matrices for G(8,4))."""
+    from gaast_b200 import workloads as W
+    from tests.helpers import oracle_eval as workload_oracle
+    w = W.WORKLOADS[name]
+    n, batch = w.n, 3
+    host = W.host_inputs(w, batch)
+    bcs = [bc for _, bc in w.inputs]
+    want = workload_oracle(w.build, w.metric, host, bcs, batch)
+    e = basis_vectors(w.metric)
+    dim = e[0].shape[0]
+
+    class LazyBlades(dict):  # only the grades that occur: G(8,4) has 4 096 blades, the workload touches a few hundred
+        def __missing__(self, k):
+            subsets = sorted(combinations(range(n), k), key=lambda s: sum(1 << i for i in s))
+            mats = []
+            for s in subsets:
+                m = np.eye(dim, dtype=complex)
+                for i in s:
+                    m = m @ e[i]
+                mats.append(m)
+            self[k] = mats
+            return mats
+
+    blades = LazyBlades()
+    # grade selection by readback only needs the grades the expression can produce: at most three factors
+    # of the inputs' highest grade
+    max_grade = min(n, 3 * max(k for gr, _ in w.inputs for k in gr))
+    for i in range(batch):
+        leaves = []
+        for d, bc in zip(host, bcs):
+            comps = {k: (v[:, 0] if bc else v[:, i]) for k, v in d.items()}
+            leaves.append(MatMV({"n": max_grade, "blades": blades}, to_matrix(blades, comps)))
+        res = w.build(*leaves)
+        got = from_matrix(blades, res.m, sorted(want))
+        for k in want:
+            scale = max(1.0, np.abs(want[k][:, i]).max())
+            assert np.allclose(got[k], want[k][:, i], rtol=0, atol=1e-9 * scale), f"{name}: element {i}, grade {k}"
