@@ -4,9 +4,25 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
 
 A "step" is one evaluation of the workload's expression over one full batch of
-synthetic random multivectors resident in HBM (one kernel launch).  Under
-torchrun every rank evaluates its own full batch (weak scaling, no data-path
-collective; cfg5's batch-sum adds one 66-double all-reduce per step).
+synthetic random multivectors resident in HBM (one kernel launch).  The line says only
+what THIS run measured:
+
+* headline (`value`, `roofline`): the workload of `--workload` (default cfg2 = BASELINE
+  configs[1]), weak scaling under torchrun (every rank a full BASELINE batch, no
+  collective in the step).  The K-step timed loop is repeated until at least 0.5 s of
+  device time has passed; `ms_per_step` is the median over the repetitions of
+  (max over ranks of the repetition's CUDA-event time) / K.
+* `e2e`: the same metric through gaast_eval_host (pinned HOST arrays in and out, H2D +
+  kernels + D2H in the timed region), run on EVERY rank at the same time between two
+  barriers; value = elements of all ranks / the slowest rank's time.
+* `cfg5_sharded`: BASELINE configs[4] as it is defined -- ONE 32 M batch sharded over the
+  N ranks (strong scaling), gaast_eval_sum + gaast_comm_allreduce_sum (NCCL, 66 doubles)
+  inside the timed step, with the single-GPU time of the same batch measured on rank 0 of
+  the same box in the same run, the step time without the all-reduce, and a check of the
+  all-reduced vector against torch.distributed.
+* `other_workloads` (N = 1): the other BASELINE configs, device-resident and (cfg3, cfg5)
+  end to end on a bounded sub-batch, plus one full G(8,0) product on the dense-warp engine.
+
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -25,6 +41,7 @@ if ROOT not in sys.path:
 
 METRIC = "multivector_products_per_sec"
 UNIT = "products/s"
+MIN_TIMED_SECONDS = 0.5  # the K-step loop is repeated until this much device time has passed
 
 # stdout carries exactly ONE line, the JSON record.  Libraries print there too (NCCL announces its
 # version on stdout when the process group starts): file descriptor 1 is pointed at stderr for the
@@ -54,18 +71,46 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# FP64 FMA-pipe peak measured with profiles/fp64_peak.cu on this pool; nominal 40 TFLOP/s
-FP64_PEAK_TFLOPS = float(os.environ.get("GAAST_FP64_PEAK_TFLOPS", "0") or 0) or 36.84  # profiles/r1_fp64_peak.txt
+# FP64 FMA-pipe peak.  MEASURED_PEAKS.json carries no f64 figure, so the denominator is this repo's own
+# microbenchmark (profiles/fp64_peak.cu -> profiles/r1_fp64_peak.txt, 36.84 TFLOP/s; 148 SMs x 64 DFMA/clk x
+# 1.965 GHz = 37.2 nominal); `roofline.fp64_peak_source` says so in the line.
+FP64_PEAK_TFLOPS = float(os.environ.get("GAAST_FP64_PEAK_TFLOPS", "0") or 0) or 36.84
+FP64_PEAK_SOURCE = "profiles/r1_fp64_peak.txt (this repo's DFMA microbenchmark; MEASURED_PEAKS.json has no f64 figure)"
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at the BASELINE batch, from the committed
-# `ncu --set full` captures (profiles/r1_*_ncu.txt; captures taken at batch 4M are scaled to the full batch)
-NCU_TRAFFIC_BYTES = {
-    "cfg1": 727105280 // 4,        # profiles/r1_cfg1_final_ncu.txt, captured at 4M elements (BASELINE batch is 1M)
-    "cfg2": 5316607000,            # profiles/r1_cfg2_final_ncu.txt at the BASELINE batch (algorithmic 5368709120)
-    "cfg3": 6409913000 * 4,        # profiles/r1_cfg3_final_ncu.txt at 4M elements (algorithmic 6442450944 at 4M)
-    "cfg4": 9169429000 * 2,        # profiles/r1_cfg4_final_ncu.txt at 4M elements (algorithmic 9227468800 at 4M)
-    "cfg5": 4792209000 * 8,        # profiles/r1_cfg5_final_ncu.txt at 4M elements (algorithmic 4831838208 at 4M)
-}
+
+def _ncu_traffic(kernel_desc: str, elements: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
+    the cubin that ran -- profiles/ncu_traffic.json is keyed by the cubin key `gaast_plan_last_kernel` reports.
+    A capture taken at another batch length is scaled by the element ratio (and says so); a kernel whose key
+    has no capture reports null and the reason."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception as ex:
+        return None, f"profiles/ncu_traffic.json unreadable: {ex}"
+    key = None
+    for tok in kernel_desc.split():
+        if tok.startswith("key="):
+            key = tok[4:]
+    if not key:
+        return None, "the kernel that ran has no cubin key (library kernel)"
+    ent = table.get(key)
+    if not ent:
+        return None, f"no ncu capture committed for cubin {key}"
+    scale = elements / float(ent["elements"])
+    note = ent["source"] + (f" (captured at {ent['elements']} elements, scaled x{scale:g})" if scale != 1.0 else "")
+    return int(ent["dram_bytes"] * scale), note
+
+
+def _executed_fma(kernel_desc: str):
+    """FMAs per element the generated kernel executes (the code generator counts them and reports
+    `fma/elem=` in gaast_plan_last_kernel); None for library kernels."""
+    for tok in kernel_desc.split():
+        if tok.startswith("fma/elem="):
+            try:
+                return int(tok[9:])
+            except ValueError:
+                return None
+    return None
 
 
 class ClockSampler:
@@ -78,7 +123,7 @@ class ClockSampler:
         self.gpu = gpu_index
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -86,7 +131,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -109,7 +154,8 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(power),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_under_load": len(busy), "reasons": sorted(reasons),
+                "covers": "the headline workload's warm-up and timed repetitions (sampled every 50 ms)"}
 
 
 def _dist():
@@ -151,7 +197,10 @@ def cpu_port_rate(w, target_seconds: float, threads: int, storage: int):
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (the oracle's C++ restatement of
-    eval.rs -- there is no rustc in this image, so not the Rust binary) on all host threads."""
+    eval.rs -- there is no rustc in this image, so not the Rust binary) on all host threads.
+    The timed arm uses the reference's own storage model (GradeMapMV: a hash map of vectors, fresh
+    cache per element); the same port with dense arrays and reused buffers is timed once beside it
+    (`cpu_baseline.dense_storage_value`) so that both ratios are on record."""
     rank, world, _ = _dist()
     if rank != 0:
         return
@@ -169,6 +218,7 @@ def run_reference(args):
         port.eval_port(ast, count, 1, threads)
     dt = time.perf_counter() - t0
     value = count * args.steps / dt * w.products
+    dense_rate, dense_count, dense_dt = cpu_port_rate(w, 4.0, threads, storage=0)
     sample = (f"{count} elements per step of {w.name} (full batch {w.batch}); GradeMapMV-like hash-map storage, "
               f"fresh cache per element, {threads} threads over batch ranges")
     line = {
@@ -176,131 +226,173 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{w.name}: {w.title}", "batch_per_gpu": w.batch, "sample_elements": count},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "dense_storage_value": dense_rate * w.products,
+                         "dense_storage_sample": f"{dense_count} elements, {dense_dt:.1f} s, the same port with dense per-grade "
+                                                 f"arrays and buffers reused across elements, {threads} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     _emit(line)
 
 
 # ------------------------------------------------------------------------ GPU arm ----
-def time_workload(ctx, w, steps, warmup, torch, dist, world, batch=None, engine=None, with_sum=None, tuning=None,
-                  f32=False):
-    """Device-resident timing of one workload: returns dict with ms_per_step etc.
-    f32: the reduced-precision variant (binary32 batches; half the algorithmic bytes)."""
-    import gaast_b200 as g
-    from gaast_b200 import _lib as L
-    from gaast_b200 import workloads as W
-    dev = torch.device("cuda", ctx.device)
-    n = batch or w.batch
-    plan = g.Plan(ctx, W.specialize(w))
-    if tuning:
-        plan.set_tuning(*tuning)
-    bytes_per_elem, _ = plan.cost(w.broadcast_mask())
-    if f32:
-        bytes_per_elem //= 2
-    # L2 hygiene: a step must not find its inputs in the 126 MB L2.  Large workloads are larger
-    # than L2 by themselves; small ones (cfg1: 185 MB) rotate over several input/output sets.
-    n_sets = max(1, min(8, -(-(1 << 30) // max(1, n * bytes_per_elem))))
-    if os.environ.get("GAAST_BENCH_NO_ROTATE"):
-        n_sets = 1  # diagnostic only: lets a small batch stay L2-resident
-    sets = []
-    for k in range(n_sets):
-        t = W.torch_inputs(w, n, dev, seed=None if k == 0 else W.seed_of(w) + 1000 * k)
-        if f32:
-            t = [{kk: v.float() for kk, v in x.items()} for x in t]
-        i = [g.DeviceBatch.wrap_torch(ctx, w.n, x, broadcast=bc) for x, (_, bc) in zip(t, w.inputs)]
-        sets.append((t, i, plan.alloc_output(n, L.F32 if f32 else L.F64)))
-    tin, ins, out = sets[0]
-    use_sum = w.sum_root if with_sum is None else with_sum
-    sums = torch.zeros(_root_cols(plan, w), dtype=torch.float64, device=dev)
-    eng = L.ENGINE_AUTO if engine is None else engine
-    counter = [0]
-    comm = None
-    if use_sum and world > 1:
-        # the path's one collective goes through the library's own communicator (gaast_comm, NCCL behind
-        # the C ABI); torch.distributed only ships the 128-byte id and provides the barrier
-        uid = [g.Comm.unique_id() if dist.get_rank() == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        comm = g.Comm.join(ctx, world, dist.get_rank(), uid[0])
-
-    def step():
-        _, s_in, s_out = sets[counter[0] % n_sets]
-        counter[0] += 1
-        if use_sum:
-            plan.eval_sum(s_in, sums.data_ptr(), out=s_out, engine=eng)
-            if comm is not None:
-                comm.allreduce_sum([sums.data_ptr()], sums.numel())  # the only collective of the path: 66 doubles
-        else:
-            plan.eval(s_in, out=s_out, engine=eng)
-
-    for _ in range(max(3, warmup)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # Launch-bound steps (cfg1: 185 MB, ~30 us per kernel) are captured once into a CUDA graph and
-    # replayed: the evaluation is stream-ordered and allocates nothing after its first call, so the
-    # C ABI is capturable as it is.  Everything else is launched directly.
-    expect_us = n * bytes_per_elem / 6.5e6
-    use_graph = world == 1 and not use_sum and expect_us < 200.0 and not os.environ.get("GAAST_BENCH_NO_GRAPH")
-    if use_graph:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=ctx.torch_stream):
-            for _ in range(steps):
-                step()
-        torch.cuda.synchronize()
-        e0.record()
-        graph.replay()
-        e1.record()
-    else:
-        e0.record()
-        for _ in range(steps):
-            step()
-        e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count - launches0  # this library's kernels only (NCCL's all-reduce kernel is not counted)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    bytes_per_elem, flops_per_elem = plan.cost(w.broadcast_mask())
-    if f32:
-        bytes_per_elem //= 2
-    res = {
-        "ms_per_step": ms / steps, "elements": n, "bytes_per_elem": bytes_per_elem, "flops_per_elem": flops_per_elem,
-        "launches": launches, "kernel": plan.last_kernel(), "plan": plan, "ins": ins, "out": out, "tin": tin,
-        "n_sets": n_sets, "cuda_graph": bool(use_graph), "comm": comm,
-    }
-    return res
-
-
 def _root_cols(plan, w):
     from math import comb
     return sum(comb(w.n, k) for k in plan.root_grades())
 
 
-def measure_e2e(ctx, w, res, steps, torch):
-    """Same metric through gaast_eval_host: pinned host arrays in and out, H2D + kernel + D2H in the timed region."""
+class Resident:
+    """One workload resident in HBM on this rank: plan, input/output sets, the step closure."""
+
+    def __init__(self, ctx, w, torch, batch=None, engine=None, tuning=None, f32=False, with_sum=None, seed_shift=0,
+                 torch_out=False):
+        import gaast_b200 as g
+        from gaast_b200 import _lib as L
+        from gaast_b200 import workloads as W
+        self.ctx, self.w, self.torch = ctx, w, torch
+        self.dev = torch.device("cuda", ctx.device)
+        self.n = n = batch or w.batch
+        self.f32 = f32
+        self.plan = g.Plan(ctx, W.specialize(w))
+        if tuning:
+            self.plan.set_tuning(*tuning)
+        self.bytes_per_elem, self.flops_per_elem = self.plan.cost(w.broadcast_mask())
+        if f32:
+            self.bytes_per_elem //= 2
+        # L2 hygiene: a step must not find its inputs in the 126 MB L2.  Large workloads are larger
+        # than L2 by themselves; small ones (cfg1: 185 MB) rotate over several input/output sets.
+        self.n_sets = max(1, min(8, -(-(1 << 30) // max(1, n * self.bytes_per_elem))))
+        if os.environ.get("GAAST_BENCH_NO_ROTATE"):
+            self.n_sets = 1  # diagnostic only: lets a small batch stay L2-resident
+        self.sets = []
+        for k in range(self.n_sets):
+            t = W.torch_inputs(w, n, self.dev, seed=(None if k == 0 and not seed_shift else W.seed_of(w) + 1000 * k + seed_shift))
+            if f32:
+                t = [{kk: v.float() for kk, v in x.items()} for x in t]
+            i = [g.DeviceBatch.wrap_torch(ctx, w.n, x, broadcast=bc) for x, (_, bc) in zip(t, w.inputs)]
+            if torch_out:  # the output as torch tensors, so that torch can check sums on the device
+                from math import comb
+                ot = {k2: torch.empty((comb(w.n, k2), n), dtype=torch.float32 if f32 else torch.float64, device=self.dev)
+                      for k2 in self.plan.root_grades()}
+                o = g.DeviceBatch.wrap_torch(ctx, w.n, ot)
+                o.tensors = ot
+            else:
+                o = self.plan.alloc_output(n, L.F32 if f32 else L.F64)
+            self.sets.append((t, i, o))
+        self.use_sum = w.sum_root if with_sum is None else with_sum
+        self.sums = torch.zeros(_root_cols(self.plan, w), dtype=torch.float64, device=self.dev)
+        self.engine = L.ENGINE_AUTO if engine is None else engine
+        self.counter = 0
+        self.comm = None
+
+    def step(self):
+        _, s_in, s_out = self.sets[self.counter % self.n_sets]
+        self.counter += 1
+        if self.use_sum:
+            self.plan.eval_sum(s_in, self.sums.data_ptr(), out=s_out, engine=self.engine)
+            if self.comm is not None:
+                # the only collective of the path: the root vector (66 doubles for cfg5), through the library's own
+                # communicator (gaast_comm_allreduce_sum: NCCL behind the C ABI), ordered on the ctx stream
+                self.comm.allreduce_sum([self.sums.data_ptr()], self.sums.numel())
+        else:
+            self.plan.eval(s_in, out=s_out, engine=self.engine)
+
+    def kernel(self):
+        return self.plan.last_kernel()
+
+
+def timed(res, steps, warmup, torch, dist, world, allow_graph=True):
+    """Warm up, then repeat the K-step loop until MIN_TIMED_SECONDS of device time has passed.
+    Every repetition is bracketed by CUDA events on the ctx stream; barrier + synchronize on both
+    sides of the whole region; per repetition the MAX over ranks; returns the median ms per step."""
+    ctx = res.ctx
+    dev = res.dev
+    for _ in range(max(3, warmup)):
+        res.step()
+    torch.cuda.synchronize()
+    # Launch-bound steps (cfg1: 185 MB, ~30 us per kernel) are captured once into a CUDA graph and
+    # replayed: the evaluation is stream-ordered and allocates nothing after its first call, so the
+    # C ABI is capturable as it is.  Everything else is launched directly.
+    expect_us = res.n * res.bytes_per_elem / 6.5e6
+    use_graph = (allow_graph and world == 1 and not res.use_sum and expect_us < 200.0
+                 and not os.environ.get("GAAST_BENCH_NO_GRAPH"))
+    graph = None
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=ctx.torch_stream):
+            for _ in range(steps):
+                res.step()
+        torch.cuda.synchronize()
+
+    def one_rep(e0, e1):
+        e0.record()
+        if graph is not None:
+            graph.replay()
+        else:
+            for _ in range(steps):
+                res.step()
+        e1.record()
+
+    # calibration repetition (untimed): how many repetitions fill MIN_TIMED_SECONDS
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    one_rep(c0, c1)
+    torch.cuda.synchronize()
+    cal_ms = max(c0.elapsed_time(c1), 1e-3)
+    reps = int(min(400, max(1, -(-MIN_TIMED_SECONDS * 1e3 // cal_ms))))
+    if world > 1:
+        t = torch.tensor([reps], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        reps = int(t.item())
+    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count
+    for e0, e1 in events:
+        one_rep(e0, e1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = ctx.launch_count - launches0  # this library's kernels only (NCCL's all-reduce kernel is not counted)
+    if graph is not None:
+        launches = reps * steps * max(1, launches_per_step(res))
+    ms = torch.tensor([e0.elapsed_time(e1) for e0, e1 in events], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # per repetition, the slowest rank
+    ms = [float(x) for x in ms.tolist()]
+    return {"ms_per_step": statistics.median(ms) / steps, "ms_per_step_min": min(ms) / steps,
+            "ms_per_step_max": max(ms) / steps, "reps": reps, "timed_region_s": sum(ms) / 1e3,
+            "launches": launches, "cuda_graph": graph is not None}
+
+
+def launches_per_step(res):
+    """Kernels one step launches (counted on an extra, untimed step; used for graph replays, whose launches
+    the library's counter does not see)."""
+    c0 = res.ctx.launch_count
+    res.step()
+    res.torch.cuda.synchronize()
+    return res.ctx.launch_count - c0
+
+
+def measure_e2e(res, steps, torch, dist, world, elements=None):
+    """Same metric through gaast_eval_host: pinned host arrays in and out, H2D + kernel + D2H in the timed
+    region.  Under torchrun EVERY rank runs its own pipeline at the same time (barrier before and after);
+    returns the slowest rank's time."""
     from math import comb
-    n = res["elements"]
-    plan = res["plan"]
+    w, plan = res.w, res.plan
+    n = min(res.n, elements or res.n)
+    tin = res.sets[0][0]
     host_in, grades, bcs = [], [], []
     h2d = 0
-    dt = next(iter(res["tin"][0].values())).dtype  # float64, or float32 for the f32 variant
+    dt = next(iter(tin[0].values())).dtype  # float64, or float32 for the f32 variant
     es = 4 if dt == torch.float32 else 8
-    for t, (gr, bc) in zip(res["tin"], w.inputs):
+    for t, (gr, bc) in zip(tin, w.inputs):
         rows = sum(comb(w.n, k) for k in gr)
         h = torch.empty((rows, 1 if bc else n), dtype=dt, pin_memory=True)
         r = 0
         for k in gr:
             c = comb(w.n, k)
-            h[r:r + c].copy_(t[k])
+            h[r:r + c].copy_(t[k] if bc else t[k][:, :n])
             r += c
         host_in.append(h)
         grades.append(gr)
@@ -310,6 +402,9 @@ def measure_e2e(ctx, w, res, steps, torch):
     host_out = torch.empty((out_rows, n), dtype=dt, pin_memory=True)
     torch.cuda.synchronize()
     plan.eval_host(host_in, grades, bcs, n, host_out)  # warm-up: allocates the device buffer sets
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -319,11 +414,111 @@ def measure_e2e(ctx, w, res, steps, torch):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     ms = max(e0.elapsed_time(e1), wall * 1e3)
-    # sanity: the result equals the resident path's
-    ref = res["out"].download(plan.root_grades()[0])[:, :1000]
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=res.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    # sanity: the result equals the resident path's (same inputs, same kernel)
+    res.counter = 0
+    res.step()
+    torch.cuda.synchronize()
+    k0 = plan.root_grades()[0]
+    o = res.sets[0][2]
+    ref = (o.tensors[k0][:, :1000].cpu().numpy() if hasattr(o, "tensors") else o.download(k0)[:, :1000])
     got = host_out[:ref.shape[0], :1000].numpy()
     ok = bool((ref == got).all())
-    return {"ms_per_step": ms / steps, "h2d": h2d, "d2h": out_rows * es * n, "matches_resident": ok}
+    return {"ms_per_step": ms / steps, "h2d": h2d, "d2h": out_rows * es * n, "matches_resident": ok, "elements": n}
+
+
+def _workload_record(res, t, peak_gbs, w):
+    s = t["ms_per_step"] / 1e3
+    n = res.n
+    kernel = res.kernel()
+    traffic, traffic_src = _ncu_traffic(kernel, n) if not res.f32 else (None, "no capture of the f32 kernels")
+    rec = {"elements_per_s": n / s, "products_per_s": n / s * w.products, "ms_per_step": t["ms_per_step"],
+           "ms_per_step_min": t["ms_per_step_min"], "ms_per_step_max": t["ms_per_step_max"],
+           "timed_reps": t["reps"], "timed_region_s": t["timed_region_s"],
+           "hbm_gbs": n * res.bytes_per_elem / s / 1e9, "hbm_frac": n * res.bytes_per_elem / s / 1e9 / peak_gbs,
+           "fp64_tflops": n * res.flops_per_elem / s / 1e12,
+           "fp64_frac": n * res.flops_per_elem / s / 1e12 / FP64_PEAK_TFLOPS,
+           "bound": w.bound, "ncu_traffic_bytes": traffic, "ncu_traffic_source": traffic_src,
+           "batch": n, "kernel": kernel, "io_sets_rotated": res.n_sets, "cuda_graph": t["cuda_graph"]}
+    fma = _executed_fma(kernel)
+    if fma is not None:
+        rec["fma_per_element_executed"] = fma
+        rec["fp64_tflops_executed"] = n * 2.0 * fma / s / 1e12
+    return rec
+
+
+def run_cfg5_sharded(ctx, torch, dist, rank, world, steps, warmup, peak_gbs):
+    """BASELINE configs[4]: ONE 32 M batch of G(8,4) (V*X*V.vinv()).g(2), sharded over the ranks, with the
+    batch-sum: gaast_eval_sum on every shard + gaast_comm_allreduce_sum of the 66-double root vector inside
+    the timed step.  Strong scaling; the single-GPU time of the same 32 M batch is measured on rank 0 first."""
+    import gaast_b200 as g
+    from gaast_b200 import workloads as W
+    from gaast_b200.dist import shard_range
+    w = W.WORKLOADS["cfg5"]
+    total = w.batch
+    rec = {"workload": f"{w.name}: {w.title}", "batch_total": total, "n_gpus": world, "scaling": "strong",
+           "collective": "gaast_comm_allreduce_sum (ncclAllReduce, 66 f64, sum) on the ctx stream, inside every timed step"}
+    one_ms = None
+    if world > 1:
+        # (1) the same 32 M batch on ONE GPU of this box (rank 0; the other ranks wait at the barrier inside timed())
+        if rank == 0:
+            r1 = Resident(ctx, w, torch, batch=total)
+            t1 = timed(r1, steps, warmup, torch, dist, 1, allow_graph=False)
+            one_ms = t1["ms_per_step"]
+            rec["one_gpu"] = {"ms_per_step": one_ms, "elements_per_s": total / one_ms * 1e3,
+                              "products_per_s": total / one_ms * 1e3 * w.products,
+                              "hbm_frac": total * r1.bytes_per_elem / one_ms / 1e6 / peak_gbs, "kernel": r1.kernel(),
+                              "note": "gaast_eval_sum over the whole batch on rank 0's GPU while the other ranks idle"}
+            del r1
+            torch.cuda.empty_cache()
+        dist.barrier()
+    b0, b1 = shard_range(total, rank, world)
+    res = Resident(ctx, w, torch, batch=b1 - b0, seed_shift=7919 * rank, torch_out=True)
+    if world > 1:
+        uid = [g.Comm.unique_id() if rank == 0 else None]  # torch.distributed only ships the 128-byte id
+        dist.broadcast_object_list(uid, src=0)
+        res.comm = g.Comm.join(ctx, world, rank, uid[0])
+    t = timed(res, steps, warmup, torch, dist, world, allow_graph=False)
+    s = t["ms_per_step"] / 1e3
+    rec.update({"ms_per_step": t["ms_per_step"], "ms_per_step_min": t["ms_per_step_min"], "timed_reps": t["reps"],
+                "timed_region_s": t["timed_region_s"], "shard_elements": res.n,
+                "elements_per_s": total / s, "products_per_s": total / s * w.products,
+                "hbm_gbs_per_gpu": res.n * res.bytes_per_elem / s / 1e9,
+                "hbm_frac_per_gpu": res.n * res.bytes_per_elem / s / 1e9 / peak_gbs,
+                "kernel": res.kernel(), "gpu_launches": t["launches"]})
+    # (2) the check: the all-reduced vector of the last step against torch.distributed's all-reduce of torch sums
+    res.counter = 0
+    res.step()
+    torch.cuda.synchronize()
+    got = res.sums.clone()
+    o = res.sets[0][2]
+    want = torch.cat([o.tensors[k].sum(dim=1) for k in sorted(o.tensors)])
+    mag = torch.cat([o.tensors[k].abs().sum(dim=1) for k in sorted(o.tensors)])
+    if world > 1:
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mag, op=dist.ReduceOp.SUM)
+    err = float(((got - want).abs() / mag.clamp_min(1e-300)).max().item())
+    rec["sum_check"] = bool(err <= 1e-12)
+    rec["sum_check_detail"] = {"max_abs_err_over_sum_abs": err, "tolerance": 1e-12,
+                               "against": "torch.distributed.all_reduce(SUM) of per-rank torch.sum over the output arrays"}
+    # (3) the same step without the collective: what the all-reduce costs
+    if world > 1:
+        comm, res.comm = res.comm, None
+        t0 = timed(res, steps, warmup, torch, dist, world, allow_graph=False)
+        res.comm = comm
+        rec["ms_per_step_without_allreduce"] = t0["ms_per_step"]
+        rec["allreduce_cost_ms"] = t["ms_per_step"] - t0["ms_per_step"]
+        one = torch.tensor([one_ms or 0.0], dtype=torch.float64, device=res.dev)
+        dist.all_reduce(one, op=dist.ReduceOp.MAX)
+        one_ms = float(one.item())
+        rec["speedup_vs_one_gpu_same_box"] = one_ms / t["ms_per_step"]
+        rec["scaling_efficiency"] = one_ms / t["ms_per_step"] / world
+        comm.close()
+    return rec
 
 
 def run_gpu(args):
@@ -333,71 +528,99 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import gaast_b200 as g
+    from gaast_b200 import _lib as L
     from gaast_b200 import workloads as W
     ctx = g.Ctx.on_torch_stream(local)
     w = W.WORKLOADS[args.workload]
     peak_gbs, peak_src = _peaks()
+    f32 = args.dtype == "f32"
 
-    sampler = ClockSampler(local) if rank == 0 else None
     batch = args.batch
     if args.strong and world > 1:
         from gaast_b200.dist import shard_range
         b0, b1 = shard_range(batch or w.batch, rank, world)
         batch = b1 - b0  # the BASELINE batch split into contiguous, 16-byte aligned slices
-    res = time_workload(ctx, w, args.steps, args.warmup, torch, dist, world, batch=batch,
-                        engine={'auto': 0, 'table': 1, 'specialized': 2}[args.engine],
-                        tuning=(args.ept, args.variant) if (args.ept or args.variant) else None,
-                        with_sum=False if args.no_sum else None, f32=args.dtype == "f32")
+    sampler = ClockSampler(local) if rank == 0 else None
+    res = Resident(ctx, w, torch, batch=batch, engine={'auto': 0, 'table': 1, 'specialized': 2}[args.engine],
+                   tuning=(args.ept, args.variant) if (args.ept or args.variant) else None,
+                   with_sum=False if args.no_sum else None, f32=f32)
+    if res.use_sum and world > 1:
+        uid = [g.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        res.comm = g.Comm.join(ctx, world, rank, uid[0])
+    t = timed(res, args.steps, args.warmup, torch, dist, world)
     clocks = sampler.stop() if sampler else None
 
-    n = res["elements"]
-    sec = res["ms_per_step"] / 1e3
+    n = res.n
+    sec = t["ms_per_step"] / 1e3
     elems_per_s = n * world / sec
     value = elems_per_s * w.products
-    gbs = n * res["bytes_per_elem"] / sec / 1e9
-    tflops = n * res["flops_per_elem"] / sec / 1e12
+    gbs = n * res.bytes_per_elem / sec / 1e9
+    tflops = n * res.flops_per_elem / sec / 1e12
+    kernel = res.kernel()
+    traffic, traffic_src = (None, "no capture of the f32 kernels") if f32 else _ncu_traffic(kernel, n)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+        "ms_per_step": t["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"{w.name}: {w.title}" + (" [f32 variant: not the reference's precision]" if args.dtype == "f32" else ""),
+        "config": {"workload": f"{w.name}: {w.title}" + (" [f32 variant: not the reference's precision]" if f32 else ""),
                    "batch_per_gpu": n, "elements_per_s": elems_per_s,
                    "products_per_element": w.products, "parallelism": f"batch-sharded x{world}, no data-path collective"
-                   + (" (+66-double NCCL all-reduce for the batch-sum, gaast_comm_allreduce_sum)" if w.sum_root and world > 1 else ""),
-                   "l2": f"inputs+outputs {n * res['bytes_per_elem'] / 1e9:.2f} GB per step (126 MB L2), "
-                         f"{res['n_sets']} input/output set(s) used in rotation",
-                   "kernel": res["kernel"], "cuda_graph": res["cuda_graph"]},
-        "gpu_launches": res["launches"],
+                   + (" (+66-double NCCL all-reduce for the batch-sum, gaast_comm_allreduce_sum)" if res.comm is not None else ""),
+                   "l2": f"inputs+outputs {n * res.bytes_per_elem / 1e9:.2f} GB per step (126 MB L2), "
+                         f"{res.n_sets} input/output set(s) used in rotation",
+                   "timing": f"{t['reps']} repetitions of the {args.steps}-step loop ({t['timed_region_s']:.2f} s of device time), "
+                             f"median of per-repetition max-over-ranks CUDA-event times; min {t['ms_per_step_min']:.4f} "
+                             f"max {t['ms_per_step_max']:.4f} ms/step",
+                   "kernel": kernel, "cuda_graph": t["cuda_graph"]},
+        "gpu_launches": t["launches"],
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
-                     "traffic": NCU_TRAFFIC_BYTES.get(w.name) if args.dtype == "f64" else None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": n * res["bytes_per_elem"], "fp64_tflops": tflops,
-                     "fp64_peak_tflops": FP64_PEAK_TFLOPS, "fp64_frac": tflops / FP64_PEAK_TFLOPS},
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": n * res.bytes_per_elem,
+                     "fp64_tflops_algorithmic": tflops, "fp64_peak_tflops": FP64_PEAK_TFLOPS,
+                     "fp64_peak_source": FP64_PEAK_SOURCE, "fp64_frac_algorithmic": tflops / FP64_PEAK_TFLOPS},
     }
+    fma = _executed_fma(kernel)
+    if fma is not None:
+        # a lowered plan executes fewer FMAs than the reference's term count (cfg2: the 160 terms of R X ~R become a
+        # 25-FMA linear map): the algorithmic figure counts the reference's terms, this one the kernel's own
+        line["roofline"]["fma_per_element_executed"] = fma
+        line["roofline"]["fp64_tflops_executed"] = n * 2.0 * fma / sec / 1e12
+        line["roofline"]["fp64_frac_executed"] = n * 2.0 * fma / sec / 1e12 / FP64_PEAK_TFLOPS
     if clocks is not None:
         line["clocks"] = clocks
 
-    if args.dtype == "f32":  # no CPU leg for the f32 variant (the reference is f64-only); its FMA-pipe peak is not the f64 one
+    if f32:  # no CPU leg for the f32 variant (the reference is f64-only); its FMA-pipe peak is not the f64 one
         args.no_cpu = True
         args.all = False
-        for key in ("fp64_tflops", "fp64_peak_tflops", "fp64_frac"):
+        for key in [k for k in line["roofline"] if k.startswith(("fp64_", "fma_"))]:
             line["roofline"].pop(key)
         line["roofline"]["fp32_tflops"] = tflops
-    if rank == 0 and not args.no_e2e:
+    if not args.no_e2e:
         try:
-            e = measure_e2e(ctx, w, res, max(2, min(args.steps, 3)), torch)
-            line["e2e"] = {"value": n / (e["ms_per_step"] / 1e3) * w.products * world, "unit": UNIT,
+            e = measure_e2e(res, max(2, min(args.steps, 3)), torch, dist, world)
+            line["e2e"] = {"value": e["elements"] * world / (e["ms_per_step"] / 1e3) * w.products, "unit": UNIT,
                            "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
                            "ms_per_step": e["ms_per_step"], "matches_resident": e["matches_resident"],
                            # PCIe is the bound of this leg: tools/pcie_peak.py measured 55.6 (H2D alone), 55.0 (D2H alone)
                            # and 47.1 GB/s each way at the same time on this pool (profiles/r1_pcie_peak.txt)
-                           "gbs_each_way": max(e["h2d"], e["d2h"]) / (e["ms_per_step"] * 1e6),
-                           "note": ("gaast_eval_host_f32" if args.dtype == "f32" else "gaast_eval_host")
+                           "gbs_each_way_per_gpu": max(e["h2d"], e["d2h"]) / (e["ms_per_step"] * 1e6),
+                           "note": ("gaast_eval_host_f32" if f32 else "gaast_eval_host")
                            + ": pinned host arrays, chunked H2D/kernel/D2H pipeline"
-                           + ("; measured on rank 0 and scaled by the rank count" if world > 1 else "")}
+                           + (f"; all {world} ranks at the same time between two barriers, slowest rank's time" if world > 1 else "")}
         except Exception as ex:  # keep the headline line even if the host leg fails
             line["e2e"] = {"error": f"{type(ex).__name__}: {ex}"}
     del res
+    torch.cuda.empty_cache()
+
+    if not args.no_sharded and not f32:
+        try:
+            rec = run_cfg5_sharded(ctx, torch, dist, rank, world, args.steps, args.warmup, peak_gbs)
+            line["cfg5_sharded"] = rec
+        except Exception as ex:
+            line["cfg5_sharded"] = {"error": f"{type(ex).__name__}: {ex}"}
+        torch.cuda.empty_cache()
 
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -421,19 +644,25 @@ def run_gpu(args):
             try:
                 torch.cuda.empty_cache()
                 ow = W.WORKLOADS[name]
-                r = time_workload(ctx, ow, args.steps, args.warmup, torch, dist, 1)
-                s = r["ms_per_step"] / 1e3
-                others[name] = {"elements_per_s": r["elements"] / s, "products_per_s": r["elements"] / s * ow.products,
-                                "ms_per_step": r["ms_per_step"], "hbm_gbs": r["elements"] * r["bytes_per_elem"] / s / 1e9,
-                                "hbm_frac": r["elements"] * r["bytes_per_elem"] / s / 1e9 / peak_gbs,
-                                "fp64_tflops": r["elements"] * r["flops_per_elem"] / s / 1e12,
-                                "fp64_frac": r["elements"] * r["flops_per_elem"] / s / 1e12 / FP64_PEAK_TFLOPS,
-                                "bound": ow.bound, "ncu_traffic_bytes": NCU_TRAFFIC_BYTES.get(name),
-                                "batch": r["elements"], "kernel": r["kernel"], "io_sets_rotated": r["n_sets"],
-                                "cuda_graph": r["cuda_graph"]}
+                r = Resident(ctx, ow, torch)
+                tt = timed(r, args.steps, args.warmup, torch, dist, 1)
+                others[name] = _workload_record(r, tt, peak_gbs, ow)
+                if name in ("cfg3", "cfg5") and not args.no_e2e:
+                    # end to end on a bounded sub-batch (the full batches are 26-37 GB of pinned host memory; the
+                    # leg is PCIe-bound, so its rate does not depend on the batch length)
+                    e = measure_e2e(r, 2, torch, dist, 1, elements=4 << 20)
+                    others[name]["e2e"] = {"value": e["elements"] / (e["ms_per_step"] / 1e3) * ow.products, "unit": UNIT,
+                                           "elements": e["elements"], "h2d_bytes_per_step": e["h2d"],
+                                           "d2h_bytes_per_step": e["d2h"], "ms_per_step": e["ms_per_step"],
+                                           "matches_resident": e["matches_resident"]}
                 del r
             except Exception as ex:
                 others[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        try:
+            torch.cuda.empty_cache()
+            others["dense_warp_g8"] = run_dense_warp(ctx, torch, dist, args.steps, args.warmup, peak_gbs)
+        except Exception as ex:
+            others["dense_warp_g8"] = {"error": f"{type(ex).__name__}: {ex}"}
         line["other_workloads"] = others
 
     if rank == 0:
@@ -441,6 +670,17 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_dense_warp(ctx, torch, dist, steps, warmup, peak_gbs):
+    """One full geometric product A*B of 256-component multivectors in G(8,0) on the dense-warp engine
+    (one warp per multivector): no BASELINE config exercises that engine, this entry is its driver-visible number."""
+    from gaast_b200 import workloads as W
+    w = W.Workload("dense_warp_g8", "G(8,0) A*B, full 256-component multivectors (dense-warp engine)", [1.0] * 8,
+                   [(tuple(range(9)), False)] * 2, lambda A, B: A * B, 256 * 1024, 1, bound="fp64")
+    r = Resident(ctx, w, torch)
+    tt = timed(r, steps, warmup, torch, dist, 1, allow_graph=False)
+    return _workload_record(r, tt, peak_gbs, w)
 
 
 def main():
@@ -457,12 +697,16 @@ def main():
     ap.add_argument("--no-sum", action="store_true", help="skip the batch-sum node of cfg5")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
                     help="f64 = the reference's precision (default, the BASELINE metric); f32 = the reduced-precision variant")
-    ap.add_argument("--strong", action="store_true", help="strong scaling: shard ONE BASELINE batch over the ranks")
+    ap.add_argument("--strong", action="store_true", help="headline workload: shard ONE BASELINE batch over the ranks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the cfg5_sharded section")
     ap.add_argument("--all", action="store_true", default=True, help="also time the other BASELINE workloads (N=1)")
-    ap.add_argument("--only", dest="all", action="store_false")
+    ap.add_argument("--only", dest="all", action="store_false",
+                    help="the headline workload only (no other_workloads, no cfg5_sharded)")
     args = ap.parse_args()
+    if not args.all:
+        args.no_sharded = True
     _claim_stdout()
     if args.impl == "reference":
         run_reference(args)

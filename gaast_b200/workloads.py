@@ -106,7 +106,9 @@ def specialize(w: Workload):
 
 # ---- synthetic inputs ----------------------------------------------
 def seed_of(w: Workload) -> int:
-    return 0x6AA57000 + sorted(WORKLOADS).index(w.name)
+    if w.name in WORKLOADS:
+        return 0x6AA57000 + sorted(WORKLOADS).index(w.name)
+    return 0x6AA57100 + sum(ord(c) for c in w.name)  # ad-hoc workloads (bench.py's dense-warp entry)
 
 
 def _vec_sq(metric, v):
