@@ -431,6 +431,9 @@ def measure_e2e(res, steps, torch, dist, world, elements=None):
     return {"ms_per_step": ms / steps, "h2d": h2d, "d2h": out_rows * es * n, "matches_resident": ok, "elements": n}
 
 
+FP64_LIVE_SUSTAINED = [None]  # set by run_gpu once measured; other_workloads report their fraction of it too
+
+
 def _workload_record(res, t, peak_gbs, w):
     s = t["ms_per_step"] / 1e3
     n = res.n
@@ -448,6 +451,8 @@ def _workload_record(res, t, peak_gbs, w):
     if fma is not None:
         rec["fma_per_element_executed"] = fma
         rec["fp64_tflops_executed"] = n * 2.0 * fma / s / 1e12
+    if FP64_LIVE_SUSTAINED[0]:
+        rec["fp64_frac_of_live_sustained_peak"] = rec["fp64_tflops"] / FP64_LIVE_SUSTAINED[0]
     return rec
 
 
@@ -540,6 +545,15 @@ def run_gpu(args):
         from gaast_b200.dist import shard_range
         b0, b1 = shard_range(batch or w.batch, rank, world)
         batch = b1 - b0  # the BASELINE batch split into contiguous, 16-byte aligned slices
+    # live FP64 FMA-pipe peak of THIS box (gaast_diag_fp64_peak: independent DFMA chains): a 20 ms burst on the idle
+    # GPU, and -- measured after the headline, below -- 0.5 s sustained, the like-for-like denominator of a kernel
+    # that is itself timed over >= 0.5 s (an FP64-heavy B200 is power-capped well below 1965 MHz by then)
+    fp64_live = None
+    if rank == 0 and not f32:
+        try:
+            fp64_live = {"burst_tflops": ctx.fp64_peak(0.02)}
+        except Exception as ex:
+            fp64_live = {"error": f"{type(ex).__name__}: {ex}"}
     sampler = ClockSampler(local) if rank == 0 else None
     res = Resident(ctx, w, torch, batch=batch, engine={'auto': 0, 'table': 1, 'specialized': 2}[args.engine],
                    tuning=(args.ept, args.variant) if (args.ept or args.variant) else None,
@@ -590,6 +604,18 @@ def run_gpu(args):
         line["roofline"]["fp64_frac_executed"] = n * 2.0 * fma / sec / 1e12 / FP64_PEAK_TFLOPS
     if clocks is not None:
         line["clocks"] = clocks
+    if fp64_live is not None and "error" not in fp64_live:
+        try:
+            if world > 1:
+                pass  # (rank 0 only measures while the other ranks wait at the next barrier)
+            fp64_live["sustained_tflops"] = ctx.fp64_peak(MIN_TIMED_SECONDS)
+            fp64_live["how"] = ("gaast_diag_fp64_peak on this GPU in this run: 20 ms burst before the timed region, "
+                                f"{MIN_TIMED_SECONDS} s sustained after it")
+        except Exception as ex:
+            fp64_live["error"] = f"{type(ex).__name__}: {ex}"
+    if fp64_live is not None:
+        line["roofline"]["fp64_peak_live"] = fp64_live
+        FP64_LIVE_SUSTAINED[0] = fp64_live.get("sustained_tflops")
 
     if f32:  # no CPU leg for the f32 variant (the reference is f64-only); its FMA-pipe peak is not the f64 one
         args.no_cpu = True

@@ -4,7 +4,7 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/fp64_reuse profiles/fp64_reuse.cu && /tmp/fp64_reuse > gpurun_out/fp64_reuse.txt 2>&1
 for v in "$@"; do
-  GAAST_KERNEL_CACHE=$PWD/exp/c3/$v python bench.py --workload cfg3 --only --no-e2e --no-cpu --steps 10 > gpurun_out/c3_$v.json 2> gpurun_out/c3_$v.err
+  GAAST_TEST_HOOKS=1 GAAST_KERNEL_CACHE=$PWD/exp/c3/$v python bench.py --workload cfg3 --only --no-e2e --no-cpu --steps 10 > gpurun_out/c3_$v.json 2> gpurun_out/c3_$v.err
   python - "$v" <<'PY'
 import json,sys
 v=sys.argv[1]

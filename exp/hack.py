@@ -1,5 +1,6 @@
 """Timing experiments: compile a hand-edited copy of a generated kernel into an alternative kernel
-cache under the SAME key, so that the runtime loads it (GAAST_KERNEL_CACHE=exp/<name>).  Results
+cache under the SAME key, so that the runtime loads it (GAAST_TEST_HOOKS=1 GAAST_KERNEL_CACHE=exp/<name>;
+such kernels report origin=override-unverified in gaast_plan_last_kernel).  Results
 of such kernels may be wrong: timing only.
     python exp/hack.py <key> <name> <transform>"""
 import os, re, shutil, subprocess, sys

@@ -89,6 +89,7 @@ def _proto(name, restype, *argtypes):
 PROTOTYPES = {
     # gaast_b200.h
     "gaast_last_error": (C.c_char_p,),
+    "gaast_reload_env": (None,),
     "gaast_version": (C.c_char_p,),
     "gaast_ctx_create": (C.c_int, C.c_int, vp, C.POINTER(vp)),
     "gaast_ctx_destroy": (C.c_int, vp),
@@ -107,6 +108,7 @@ PROTOTYPES = {
     "gaast_plan_precompile_typed": (C.c_int, vp, u64, C.c_int, C.c_int, C.c_int, C.c_int),
     "gaast_plan_set_tuning": (C.c_int, vp, C.c_int, C.c_int),
     "gaast_plan_last_kernel": (C.c_char_p, vp),
+    "gaast_diag_fp64_peak": (C.c_int, vp, C.c_double, C.POINTER(C.c_double)),
     "gaast_batch_alloc": (C.c_int, vp, u32, u32, u64, C.c_int, C.POINTER(vp)),
     "gaast_batch_wrap": (C.c_int, vp, u32, u32, u64, u64, C.c_int, C.POINTER(vp), C.POINTER(vp)),
     "gaast_batch_alloc_typed": (C.c_int, vp, u32, u32, u64, C.c_int, C.c_int, C.POINTER(vp)),

@@ -37,6 +37,7 @@ SOURCES = [
     "device/dense_warp.cu",
     "device/runtime.cu",
     "device/host_pipeline.cu",
+    "device/diag.cu",
 ]
 HEADERS = ["common.hpp", "device_plan.hpp", "runtime.hpp", "eval_args.h", "host/host.hpp", "device/dense_warp_kernel.h",
            "../../include/gaast_b200.h", "../../include/gaast_b200_host.h"]

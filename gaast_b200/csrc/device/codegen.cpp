@@ -1466,7 +1466,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             const Node& n = g.nodes[id];
             if (n.live && n.k == N_LOAD && n.reload && !n.uniform && !right.count(int(id))) only_right = false;
         }
-        if (only_right && int(right.size()) == n_smem_rows && !std::getenv("GAAST_DENSE_TABLE_ROWS")) {
+        if (only_right && int(right.size()) == n_smem_rows && !tuning().dense_table_rows) {
             for (size_t b = 0; b < g.dense.right.size(); ++b) g.nodes[g.dense.right[b]].smem_row = int(b);
             g.dense_by_blade = true;
         }
@@ -1525,6 +1525,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     if (pipelined) notes << "tma-pipelined ";
     res.parked = res_parked;
     res.parkable = res_parkable;
+    for (const Node& n : g.nodes) res.fma_per_elem += n.live && n.k == N_ACC && !n.uniform;
 
     std::ostringstream src;
     src << "// generated by gaast_b200 codegen: n=" << h.n << " terms=" << h.total_terms << " arith="

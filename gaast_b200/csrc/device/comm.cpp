@@ -50,10 +50,12 @@ Nccl& nccl() {
     static std::once_flag once;
     std::call_once(once, [] {
         std::vector<std::string> names;
-        if (const char* e = std::getenv("GAAST_NCCL")) names.push_back(e);
+        if (!gaast::tuning().nccl_path.empty()) names.push_back(gaast::tuning().nccl_path);
         names.insert(names.end(), {"libnccl.so.2", "libnccl.so"});
         for (const auto& nm : names) {
-            n.handle = dlopen(nm.c_str(), RTLD_NOW | RTLD_GLOBAL);
+            // RTLD_LOCAL: this library's nccl* symbols must not interpose on another copy in the process
+            // (torch bundles its own); a libnccl.so.2 that is already loaded is simply shared
+            n.handle = dlopen(nm.c_str(), RTLD_NOW | RTLD_LOCAL);
             if (n.handle) break;
         }
         if (!n.handle) {
@@ -130,7 +132,15 @@ gaast_status gaast_comm_create(gaast_ctx* const* ctxs, uint32_t n, gaast_comm** 
         c->ctxs.assign(ctxs, ctxs + n);
         c->comms.assign(n, nullptr);
         c->n_ranks = n;
-        nccl_check(nc.CommInitAll(c->comms.data(), int(n), devs.data()), "ncclCommInitAll");
+        int prev = -1;
+        cudaGetDevice(&prev);  // ncclCommInitAll visits every device: the caller's current one is restored
+        const int rc = nc.CommInitAll(c->comms.data(), int(n), devs.data());
+        if (prev >= 0) cudaSetDevice(prev);
+        if (rc != 0) {
+            for (ncclComm_t cm : c->comms)  // communicators created before the failure are not leaked
+                if (cm && nc.CommDestroy) nc.CommDestroy(cm);
+            nccl_check(rc, "ncclCommInitAll");
+        }
         *out = c.release();
     });
 }
@@ -158,8 +168,12 @@ gaast_status gaast_comm_create_rank(gaast_ctx* ctx, uint32_t n_ranks, uint32_t r
         c->ctxs.assign(1, ctx);
         c->comms.assign(1, nullptr);
         c->n_ranks = n_ranks;
+        int prev = -1;
+        cudaGetDevice(&prev);
         if (cudaSetDevice(ctx->device) != cudaSuccess) throw Error(GAAST_ERR_CUDA, "cudaSetDevice");
-        nccl_check(nc.CommInitRank(&c->comms[0], int(n_ranks), u, int(rank)), "ncclCommInitRank");
+        const int rc = nc.CommInitRank(&c->comms[0], int(n_ranks), u, int(rank));
+        if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);  // the caller's current device is left as it was
+        nccl_check(rc, "ncclCommInitRank");
         *out = c.release();
     });
 }

@@ -56,9 +56,43 @@ uint32_t rows_of(uint32_t n, uint32_t mask) {
 
 }  // namespace
 
+namespace {
+// Restores the caller's current device when the call returns, on every path.
+struct ScopedDevice {
+    int prev = -1;
+    void enter(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) ck(cudaSetDevice(dev), "cudaSetDevice");
+    }
+    ~ScopedDevice() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+}  // namespace
+
 static gaast_status eval_host_impl(gaast_plan* plan, const void* const* host_in_v, const uint32_t* in_masks,
                                    const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
                                    void* host_out_v, int dtype, int engine, int arith) {
+    ScopedDevice dev_guard;
+    gaast::HostPipe* live_pipe = nullptr;  // set once copies may be in flight: the error path drains them
+    uint64_t live_chunk = 0;
+    // On an error in the middle of the pipeline earlier H2D / D2H copies still touch the caller's host arrays:
+    // drain the three streams before returning, and give the buffer sets their full length back.
+    auto drain = [&] {
+        if (!live_pipe || !plan || !plan->ctx) return;
+        gaast_ctx* c = plan->ctx;
+        if (c->h2d) cudaStreamSynchronize(c->h2d);
+        cudaStreamSynchronize(c->stream);
+        if (c->d2h) cudaStreamSynchronize(c->d2h);
+        for (int set = 0; set < gaast::HostPipe::kSets; ++set) {
+            for (size_t s = 0; s < live_pipe->in[set].size(); ++s)
+                if (live_pipe->in[set][s]) live_pipe->in[set][s]->len = live_pipe->bcast[s] ? 1 : live_chunk;
+            if (live_pipe->out[set]) live_pipe->out[set]->len = live_chunk;
+        }
+        cudaGetLastError();
+    };
     try {
         if (dtype != GAAST_F64 && dtype != GAAST_F32) throw Error(GAAST_ERR_INVALID, "eval_host: unknown dtype");
         const size_t es = dtype == GAAST_F32 ? 4 : 8;
@@ -71,7 +105,7 @@ static gaast_status eval_host_impl(gaast_plan* plan, const void* const* host_in_
         if ((n_inputs && (!host_in || !in_masks || !in_broadcast)) || !host_out)
             throw Error(GAAST_ERR_INVALID, "eval_host: null argument");
         if (host_stride < len) throw Error(GAAST_ERR_INVALID, "eval_host: host stride smaller than the batch length");
-        ck(cudaSetDevice(ctx->device), "cudaSetDevice");
+        dev_guard.enter(ctx->device);
         if (!ctx->h2d) ck(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking), "stream");
         if (!ctx->d2h) ck(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking), "stream");
 
@@ -81,8 +115,7 @@ static gaast_status eval_host_impl(gaast_plan* plan, const void* const* host_in_
             if (!in_broadcast[s]) in_rows += rows_of(h.n, in_masks[s]);
         const uint32_t out_rows = h.buf_cols[0];
         const uint32_t wide = std::max<uint32_t>(1, std::max(in_rows, out_rows));
-        uint64_t chunk_mib = 32;
-        if (const char* e = std::getenv("GAAST_HOST_CHUNK_MIB")) chunk_mib = std::max(1, std::atoi(e));
+        const uint64_t chunk_mib = uint64_t(gaast::tuning().host_chunk_mib);
         uint64_t chunk = (chunk_mib << 20) / (uint64_t(es) * wide);
         chunk = std::max<uint64_t>(4096, chunk / 4096 * 4096);
         chunk = std::min<uint64_t>(chunk, (len + 4095) / 4096 * 4096);
@@ -130,6 +163,8 @@ static gaast_status eval_host_impl(gaast_plan* plan, const void* const* host_in_
 
         // the caller's stream must have finished producing before we read; it also owns ordering afterwards
         ck(cudaStreamSynchronize(ctx->stream), "sync");
+        live_pipe = p;
+        live_chunk = chunk;
         uint64_t it = 0;
         for (uint64_t off = 0; off < len; off += chunk, ++it) {
             const int set = int(it % gaast::HostPipe::kSets);
@@ -167,9 +202,11 @@ static gaast_status eval_host_impl(gaast_plan* plan, const void* const* host_in_
         }
         return GAAST_OK;
     } catch (const Error& e) {
+        drain();
         gaast::set_last_error(e.what());
         return e.status;
     } catch (const std::exception& e) {
+        drain();
         gaast::set_last_error(e.what());
         return GAAST_ERR_INVALID;
     }

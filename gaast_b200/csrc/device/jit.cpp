@@ -3,7 +3,13 @@
 // The cubin comes from the in-tree cache (gaast_b200/kernel_cache/<key>.cubin,
 // filled at build time for the plans of the shipped workloads and tests) or,
 // for a plan never seen before, from NVRTC found with dlopen.  The key is a hash
-// of the source and the compile options, so a stale entry can never be used.
+// of the source and the compile options.  A cached cubin is only loaded when the
+// manifest written next to it (<key>.manifest: sha256 of the source, sha256 of the
+// cubin, NVRTC version, architecture, options) matches the source just generated
+// and the bytes on disk; anything else counts as a miss and is recompiled.  The
+// cache directory is the one next to the library; GAAST_KERNEL_CACHE redirects it
+// only together with GAAST_TEST_HOOKS=1 (tests, timing experiments), and kernels
+// loaded that way report origin=override in gaast_plan_last_kernel.
 // Nothing here needs a device: cubins are built for a named architecture.
 #include <dlfcn.h>
 #include <sys/stat.h>
@@ -44,7 +50,7 @@ Nvrtc& nvrtc() {
     static std::once_flag once;
     std::call_once(once, [] {
         std::vector<std::string> names;
-        if (const char* e = std::getenv("GAAST_NVRTC")) names.push_back(e);
+        if (!tuning().nvrtc_path.empty()) names.push_back(tuning().nvrtc_path);
         names.insert(names.end(), {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
                                    "/usr/local/cuda/lib64/libnvrtc.so"});
         for (const auto& nm : names) {
@@ -122,7 +128,7 @@ void write_file_atomic(const std::string& path, const char* data, size_t n) {
 }  // namespace
 
 std::string jit_cache_dir() {
-    if (const char* e = std::getenv("GAAST_KERNEL_CACHE")) return e;
+    if (!tuning().kernel_cache_override.empty()) return tuning().kernel_cache_override;
     Dl_info info;
     if (dladdr(reinterpret_cast<void*>(&jit_cache_dir), &info) && info.dli_fname) {
         std::string p = info.dli_fname;
@@ -132,6 +138,66 @@ std::string jit_cache_dir() {
     }
     return "kernel_cache";
 }
+
+namespace {
+
+std::string options_line() {
+    std::string o;
+    for (const char* x : kOptions) o += std::string(o.empty() ? "" : " ") + x;
+    return o;
+}
+
+std::string nvrtc_version_string() {
+    Nvrtc& n = nvrtc();
+    int major = 0, minor = 0;
+    if (n.handle && n.Version && n.Version(&major, &minor) == 0) return std::to_string(major) + "." + std::to_string(minor);
+    return "unknown";
+}
+
+std::string manifest_text(const std::string& source, const std::vector<char>& cubin) {
+    std::ostringstream m;
+    m << "gaast_b200 cubin manifest v1\n"
+      << "source_sha256 " << sha256_hex(source.data(), source.size()) << "\n"
+      << "cubin_sha256 " << sha256_hex(cubin.data(), cubin.size()) << "\n"
+      << "cubin_bytes " << cubin.size() << "\n"
+      << "arch sm_100a\n"
+      << "nvrtc " << nvrtc_version_string() << "\n"
+      << "options " << options_line() << "\n";
+    return m.str();
+}
+
+std::string manifest_field(const std::string& text, const std::string& name) {
+    std::istringstream in(text);
+    std::string line;
+    while (std::getline(in, line))
+        if (line.compare(0, name.size() + 1, name + " ") == 0) return line.substr(name.size() + 1);
+    return "";
+}
+
+// True when <base>.cubin may be loaded for `source`: the manifest names this source and these bytes.
+bool cached_cubin_verified(const std::string& base, const std::string& source, const std::vector<char>& cubin, std::string* why) {
+    std::vector<char> mf;
+    if (!read_file(base + ".manifest", mf)) {
+        *why = "no manifest";
+        return false;
+    }
+    const std::string text(mf.begin(), mf.end());
+    if (manifest_field(text, "source_sha256") != sha256_hex(source.data(), source.size())) {
+        *why = "manifest names another source";
+        return false;
+    }
+    if (manifest_field(text, "cubin_sha256") != sha256_hex(cubin.data(), cubin.size())) {
+        *why = "cubin bytes do not match the manifest";
+        return false;
+    }
+    if (manifest_field(text, "arch") != "sm_100a" || manifest_field(text, "options") != options_line()) {
+        *why = "manifest names another architecture or other compile options";
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
 
 bool jit_available(std::string* why) {
     Nvrtc& n = nvrtc();
@@ -148,15 +214,25 @@ std::vector<char> jit_cubin(const CodegenResult& cg, std::string* key_out, std::
     const std::string dir = jit_cache_dir();
     const std::string base = dir + "/" + key;
     std::vector<char> cubin;
-    if (!std::getenv("GAAST_NO_KERNEL_CACHE") && read_file(base + ".cubin", cubin)) {
-        if (origin) *origin = "cache";
-        std::vector<char> cached_log;
-        if (log_out && read_file(base + ".log", cached_log)) log_out->assign(cached_log.begin(), cached_log.end());
-        return cubin;
+    std::string miss = "no cached cubin";
+    if (!tuning().no_kernel_cache && read_file(base + ".cubin", cubin)) {
+        std::string why;
+        const bool verified = cached_cubin_verified(base, cg.source, cubin, &why);
+        const bool overridden = !tuning().kernel_cache_override.empty();
+        // (with GAAST_TEST_HOOKS=1 + GAAST_KERNEL_CACHE an unverified cubin is accepted -- that is what the
+        // timing experiments of exp/ swap in -- and says so in its origin)
+        if (verified || overridden) {
+            if (origin) *origin = overridden ? (verified ? "override" : "override-unverified") : "cache";
+            std::vector<char> cached_log;
+            if (log_out && read_file(base + ".log", cached_log)) log_out->assign(cached_log.begin(), cached_log.end());
+            return cubin;
+        }
+        miss = "cached cubin rejected (" + why + ")";
+        cubin.clear();
     }
     Nvrtc& n = nvrtc();
     if (!n.error.empty() || !n.handle)
-        throw Error(GAAST_ERR_JIT, "no cached cubin for this plan (" + key + ") and " + n.error);
+        throw Error(GAAST_ERR_JIT, miss + " for this plan (" + key + ") and " + n.error);
     mkdir(dir.c_str(), 0755);
     const std::string src_path = base + ".cu";
     write_file_atomic(src_path, cg.source.data(), cg.source.size());
@@ -185,6 +261,8 @@ std::vector<char> jit_cubin(const CodegenResult& cg, std::string* key_out, std::
     n.DestroyProgram(&prog);
     if (rc != 0 || cubin.empty()) throw Error(GAAST_ERR_JIT, "NVRTC produced no cubin");
     write_file_atomic(base + ".cubin", cubin.data(), cubin.size());
+    const std::string manifest = manifest_text(cg.source, cubin);
+    write_file_atomic(base + ".manifest", manifest.data(), manifest.size());
     if (!log.empty()) write_file_atomic(base + ".log", log.data(), log.size());
     if (origin) *origin = "nvrtc";
     return cubin;
@@ -217,7 +295,7 @@ std::vector<char> build_specialized(const DevicePlanHost& h, CodegenOptions opt,
         cubin = jit_cubin(cg, key, origin, &log);
         const size_t spill = spill_bytes_from_log(log, cg.kernel_name);
         const bool can_park_more = cg.parked < cg.parkable && cg.elems_per_thread == 1;
-        if (std::getenv("GAAST_CODEGEN_DEBUG"))
+        if (tuning().codegen_debug)
             std::fprintf(stderr, "[gaast codegen] attempt %d: parked=%d/%d spill=%zuB smem=%zuB %s\n", attempt, cg.parked,
                          cg.parkable, spill, cg.smem_bytes, cg.notes.c_str());
         if (spill <= 8 || !can_park_more || attempt >= 8) {

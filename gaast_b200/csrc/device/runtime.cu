@@ -165,7 +165,8 @@ gaast_status gaast_ctx_create(int device, void* stream, gaast_ctx** out) {
             throw Error(GAAST_ERR_NO_DEVICE, std::string("no CUDA device: gaast_b200 has no CPU path (") +
                                                  (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + ")");
         if (device < 0 || device >= count) throw Error(GAAST_ERR_NO_DEVICE, "device ordinal out of range");
-        cuda_check(cudaSetDevice(device), "cudaSetDevice");
+        (void)gaast::tuning();  // the environment is read here, once, never on the evaluation path
+        DeviceGuard dg(device);  // the caller's current device is restored on return
         auto ctx = std::make_unique<gaast_ctx>();
         ctx->device = device;
         cudaDeviceProp prop;
@@ -232,6 +233,11 @@ gaast_status gaast_plan_destroy(gaast_plan* plan) {
         if (!plan) return;
         if (plan->ctx) {
             DeviceGuard dg(plan->ctx->device);
+            // kernels of this plan may still be in flight (an asynchronous eval on a temporary plan): nothing is
+            // unloaded or freed before the stream has drained
+            cudaStreamSynchronize(plan->ctx->stream);
+            if (plan->ctx->h2d) cudaStreamSynchronize(plan->ctx->h2d);
+            if (plan->ctx->d2h) cudaStreamSynchronize(plan->ctx->d2h);
             plan->jit.clear();
             if (plan->pipe) gaast::host_pipe_destroy(plan->pipe);
             cudaFree(plan->d_micro);
@@ -338,7 +344,8 @@ gaast_status gaast_plan_precompile_typed(gaast_plan* plan, uint64_t broadcast_sl
             }
             cg.notes += " x" + std::to_string(dw.steps.size()) + " product(s)";
         }
-        plan->last_kernel = cg.kernel_name + " key=" + key + " origin=" + origin + " " + cg.notes;
+        plan->last_kernel = cg.kernel_name + " key=" + key + " origin=" + origin + " fma/elem=" + std::to_string(cg.fma_per_elem) +
+                            " " + cg.notes;
     });
 }
 
@@ -490,15 +497,26 @@ static std::shared_ptr<gaast::JitKernel> get_specialized(gaast_plan* plan, const
     auto key = std::make_tuple(opt.broadcast_slots, opt.arith, int(opt.with_sum), int(opt.store_out),
                                opt.elems_per_thread, opt.variant, int(opt.pipelined), int(opt.tma_stage), int(opt.f32));
     auto it = plan->jit.find(key);
-    if (it != plan->jit.end()) return it->second;
-    gaast::CodegenResult cg;
-    std::string ckey, origin;
-    std::vector<char> cubin = gaast::build_specialized(plan->h, opt, &cg, &ckey, &origin);
-    auto k = gaast::jit_load(cg, cubin);
-    k->key = ckey;
-    k->origin = origin;
-    plan->jit.emplace(key, k);
-    return k;
+    if (it != plan->jit.end()) {
+        // a negative entry: THIS variant failed to build before (other variants of the plan are unaffected)
+        if (!it->second) throw Error(GAAST_ERR_JIT, plan->jit_errors[key]);
+        return it->second;
+    }
+    try {
+        gaast::CodegenResult cg;
+        std::string ckey, origin;
+        std::vector<char> cubin = gaast::build_specialized(plan->h, opt, &cg, &ckey, &origin);
+        auto k = gaast::jit_load(cg, cubin);
+        k->key = ckey;
+        k->origin = origin;
+        k->fma_per_elem = cg.fma_per_elem;
+        plan->jit.emplace(key, k);
+        return k;
+    } catch (const Error& e) {
+        plan->jit.emplace(key, nullptr);
+        plan->jit_errors[key] = e.what();
+        throw;
+    }
 }
 
 static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out, double* dev_sum,
@@ -526,7 +544,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     // dense-warp engine: the per-plan kernel (warp-uniform signs folded at compile time) when NVRTC or the
     // cache has it, else null = the generic kernel compiled into the library
     auto dense_warp_kernel_for = [&](int step, const gaast::DenseWarpLaunch& shape) -> std::shared_ptr<gaast::JitKernel> {
-        if (plan->dw_jit_failed || std::getenv("GAAST_DENSE_WARP_GENERIC")) return nullptr;
+        if (plan->dw_jit_failed || gaast::tuning().dense_warp_generic) return nullptr;
         const auto jkey = std::make_pair(step, shape.threads);
         auto it = plan->dw_jit.find(jkey);
         if (it != plan->dw_jit.end()) return it->second;
@@ -578,7 +596,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     if (use_dense_warp) {
         // chosen explicitly
     } else if ((engine == GAAST_ENGINE_AUTO && !tiny) || engine == GAAST_ENGINE_SPECIALIZED) {
-        if (plan->jit_error.empty() || engine == GAAST_ENGINE_SPECIALIZED) {
+        {
             try {
                 gaast::CodegenOptions opt;
                 opt.broadcast_slots = bslots;
@@ -596,17 +614,36 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                     if (bc || !a.sptr[i]) continue;
                     if ((a.srow[i] % quantum) || (reinterpret_cast<uintptr_t>(a.sptr[i]) & 15)) aligned = false;
                 }
+                // An odd-length batch (the ragged tail of a chunked run) still takes the aligned kernel when the
+                // library owns the output batch: rows are padded to 128 bytes, so the launch simply covers the
+                // padding column(s) too.  Inputs are only read there; caller-owned (wrapped) outputs are never
+                // written beyond their length, and a batch-sum must not see the padding.
+                if (!aligned && !with_sum && (!out || out->owned) && n % quantum != 0) {
+                    const long long padded = (n + quantum - 1) / quantum * quantum;
+                    bool fits = true;
+                    for (size_t i = 0; i < h.streams.size(); ++i) {
+                        const bool bc = (a.bcast[i >> 6] >> (i & 63)) & 1;
+                        if (bc || !a.sptr[i]) continue;
+                        if (a.srow[i] < padded || (a.srow[i] % quantum) || (reinterpret_cast<uintptr_t>(a.sptr[i]) & 15)) fits = false;
+                    }
+                    if (fits) {
+                        aligned = true;
+                        n = padded;
+                        a.n = padded;
+                    }
+                }
                 if (!aligned) opt.elems_per_thread = 1;
                 // TMA-pipelined staging is opt-in (variant bit 3): measured slower than plain blocks on cfg3 / cfg5
                 opt.pipelined = aligned && (opt.variant & 8);  // TMA bulk copies need 16-byte aligned row segments
                 opt.tma_stage = aligned && !opt.pipelined && !with_sum && !(opt.variant & 1024);
                 jk = get_specialized(plan, opt);
-            } catch (const Error& e) {
+            } catch (const Error&) {
+                // AUTO: this variant cannot be specialised (too large, or no NVRTC and no cached cubin): the table
+                // engine evaluates it.  The failure is remembered per variant (get_specialized), so an odd-length
+                // call that needs another kernel does not take the fast path away from aligned calls.
                 if (engine == GAAST_ENGINE_SPECIALIZED) throw;
-                plan->jit_error = e.what();
             }
         }
-        if (!jk && engine == GAAST_ENGINE_SPECIALIZED) throw Error(GAAST_ERR_JIT, plan->jit_error);
         // too large / too wide to specialise: a full high-dimensional product still has a fast engine
         // (the engine always runs COMPLETE 4^n products.  Measured per kept pair: 12-15 TFLOP/s against 1.2-2.1 on
         // the table engine at n = 7, 8 -- worth it while the plan keeps at least 1/8 of the pairs; at n = 9, 10 the
@@ -677,16 +714,19 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         const long long blocks = (n + per_block - 1) / per_block;
         if (blocks > 0x7fffffffLL) throw Error(GAAST_ERR_SHAPE, "batch too long for one launch");
         grid = int(blocks);
-        if ((with_sum || jk->pipelined || std::getenv("GAAST_FORCE_PERSISTENT")) && !jk->one_tile_blocks) {
+        size_t max_grid = size_t(grid);
+        if ((with_sum || jk->pipelined || gaast::tuning().force_persistent) && !jk->one_tile_blocks) {
             // persistent grid: the batch-sum epilogue keeps per-block partials, and the TMA-pipelined
             // kernels loop over their tiles; blocks stride over the batch
             long long mult = jk->pipelined ? 1 : 16;  // sum-only kernels: many short-lived blocks overlap better
-            if (const char* e = std::getenv("GAAST_GRID_MULT")) mult = std::max(1, std::atoi(e));
+            if (gaast::tuning().grid_mult > 0) mult = gaast::tuning().grid_mult;
             const long long cap = (long long)ctx->sm_count * jk->blocks_per_sm * mult;
             if (grid > cap) grid = int(cap);
+            max_grid = size_t(cap);
         }
         if (with_sum) {
-            ensure(plan->d_partials, plan->partials_cap, size_t(grid) * sum_cols);
+            // sized for the largest grid this kernel can get: allocated by the first call, never again
+            ensure(plan->d_partials, plan->partials_cap, std::max(max_grid, size_t(grid)) * sum_cols);
             a.partials = plan->d_partials;
         }
         if (jk->n_uniform > 0) {
@@ -699,26 +739,30 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
             ctx->launches++;
         }
         a.lookahead = ctx->sm_count * jk->blocks_per_sm;  // resident blocks: the look-ahead distance of the L2 prefetch variant
-        if (const char* e = std::getenv("GAAST_LOOKAHEAD")) a.lookahead = std::atoi(e);
+        if (gaast::tuning().lookahead >= 0) a.lookahead = gaast::tuning().lookahead;
         void* params[] = {&a};
         cuda_check(cudaLaunchKernel(reinterpret_cast<const void*>(jk->kernel), dim3(grid), dim3(jk->threads), params, jk->smem_bytes,
                                     ctx->stream),
                    "launch specialised kernel");
         ctx->launches++;
         char desc[512];
-        std::snprintf(desc, sizeof desc, "%s engine=specialized origin=%s grid=%d block=%d elems/thread=%d regs=%d spill=%zuB key=%s",
+        std::snprintf(desc, sizeof desc,
+                      "%s engine=specialized origin=%s grid=%d block=%d elems/thread=%d regs=%d spill=%zuB fma/elem=%d key=%s",
                       jk->name.c_str(), jk->origin.c_str(), grid, jk->threads, jk->elems_per_thread, jk->regs,
-                      jk->local_bytes, jk->key.c_str());
+                      jk->local_bytes, jk->fma_per_elem, jk->key.c_str());
         plan->last_kernel = desc;
     } else {
         gaast::TableLaunch shape = gaast::table_engine_shape(*ctx, h, n, with_sum, f32);
         grid = shape.grid;
+        // scratch is sized for the largest grid the engine ever launches (8 blocks per SM), so that only the
+        // first call allocates
+        const size_t max_grid = std::max(size_t(grid), size_t(ctx->sm_count) * 8);
         if (shape.global_ws) {
-            ensure(plan->d_ws, plan->ws_cap, size_t(grid) * shape.ws_doubles_per_block);
+            ensure(plan->d_ws, plan->ws_cap, max_grid * shape.ws_doubles_per_block);
             a.ws_global = plan->d_ws;
         }
         if (with_sum) {
-            ensure(plan->d_partials, plan->partials_cap, size_t(grid) * sum_cols);
+            ensure(plan->d_partials, plan->partials_cap, max_grid * sum_cols);
             a.partials = plan->d_partials;
         }
         a.micro = plan->d_micro;

@@ -52,7 +52,12 @@ gaast_expr* gaast_expr_input(uint32_t slot, uint32_t grade_mask) {
     return guard_expr([&] { return Expr::input(slot, grade_mask); });
 }
 gaast_expr* gaast_expr_const(uint32_t dim, uint32_t grade_mask, const double* values, size_t n_values) {
-    return guard_expr([&] { return Expr::constant(dim, grade_mask, std::vector<double>(values, values + n_values)); });
+    return guard_expr([&] {
+        if (dim > GAAST_MAX_DIM) throw gaast::Error(GAAST_ERR_INVALID, "dimension above GAAST_MAX_DIM");
+        if (n_values && !values) throw gaast::Error(GAAST_ERR_INVALID, "null values pointer");
+        if (n_values > (size_t(1) << GAAST_MAX_DIM)) throw gaast::Error(GAAST_ERR_INVALID, "more values than a multivector has components");
+        return Expr::constant(dim, grade_mask, n_values ? std::vector<double>(values, values + n_values) : std::vector<double>());
+    });
 }
 gaast_expr* gaast_expr_scalar(double x) {
     return guard_expr([&] { return Expr::scalar(x); });
@@ -136,6 +141,7 @@ gaast_status gaast_specialize(gaast_expr* root, uint32_t n, const double* metric
     return guard([&] {
         if (!out) throw gaast::Error(GAAST_ERR_INVALID, "null output pointer");
         *out = nullptr;
+        if (n > GAAST_MAX_DIM) throw gaast::Error(GAAST_ERR_INVALID, "dimension above GAAST_MAX_DIM");
         if (n && !metric) throw gaast::Error(GAAST_ERR_INVALID, "null metric");
         auto ast = gaast::specialize(ref(root), std::vector<double>(metric, metric + n));
         *out = new gaast_spec{std::move(ast)};

@@ -33,6 +33,7 @@ struct JitKernel {
     int regs = 0;
     size_t local_bytes = 0; // spills
     int blocks_per_sm = 1;
+    int fma_per_elem = 0;   // FMAs (or mul + add pairs) one element executes in this kernel
     ~JitKernel();
 };
 
@@ -62,6 +63,7 @@ struct CodegenResult {
     bool pipelined = false;
     bool one_tile_blocks = false;  // the kernel handles exactly one tile per block: the grid must cover the batch
     int parked = 0, parkable = 0;  // input rows parked in shared memory / rows that could be
+    int fma_per_elem = 0;          // product terms the per-element kernel executes (after lowering / dead-code removal)
     std::string notes;  // human-readable summary of the decisions taken
 };
 
@@ -186,7 +188,8 @@ struct gaast_plan {
     std::string last_kernel;
     // specialised kernels, keyed by (broadcast slots, arith, with_sum, store_out, elems/thread, variant)
     std::map<std::tuple<uint64_t, int, int, int, int, int, int, int, int>, std::shared_ptr<gaast::JitKernel>> jit;
-    std::string jit_error;  // sticky: why the specialised engine is unavailable
+    // why a variant could not be built (its entry in `jit` is null): per variant, never sticky for the plan
+    std::map<std::tuple<uint64_t, int, int, int, int, int, int, int, int>, std::string> jit_errors;
     int variant = 0;
     int force_ept = 0;
     gaast::HostPipe* pipe = nullptr;  // device buffer sets of gaast_eval_host

@@ -46,6 +46,12 @@ class Ctx:
     def launch_count(self) -> int:
         return L.lib.gaast_ctx_launch_count(self._h)
 
+    def fp64_peak(self, seconds: float = 0.02) -> float:
+        """Live FP64 FMA-pipe throughput of this device in TFLOP/s (gaast_diag_fp64_peak)."""
+        out = C.c_double(0.0)
+        L.check(L.lib.gaast_diag_fp64_peak(self._h, float(seconds), C.byref(out)))
+        return out.value
+
     def close(self):
         h, self._h = self._h, None
         if h:

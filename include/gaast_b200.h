@@ -14,10 +14,22 @@
  * with gaast_last_error().  There is NO CPU fallback: without a CUDA device
  * gaast_ctx_create() fails with GAAST_ERR_NO_DEVICE.
  *
- * Threading: handles are thread-compatible (no internal locking on the hot
- * path); use one ctx per host thread / device.  A plan is immutable after
- * creation and may be evaluated any number of times with new inputs -- the
+ * Threading: handles are thread-compatible, not thread-safe (no internal locking
+ * on the hot path): use one ctx per host thread / device.  A plan belongs to the
+ * ctx it was created on and is NOT shareable between threads or streams: besides
+ * its immutable description it owns per-call device scratch (batch-sum partials,
+ * hoisted shared-operand values, workspaces) and its compiled kernels, all ordered
+ * on the ctx stream.  Create one plan per ctx from the same description -- that is
+ * cheap, the cubins come from the cache.  A plan's description is immutable after
+ * creation and it may be evaluated any number of times with new inputs: the
  * "precompiled AST reused with new inputs" the reference's README:80-83 asks for.
+ *
+ * Allocation: gaast_eval / gaast_eval_sum allocate device scratch (and load their
+ * kernel) only on the FIRST call of a plan with a given kernel variant -- engine,
+ * arithmetic, dtype, broadcast pattern, alignment class -- sized for the largest
+ * launch of that variant; the dense-warp engine also when the batch grows.  Every
+ * later call only enqueues kernels on the ctx stream and can be captured in a CUDA
+ * graph.  No environment variable is read on that path (see gaast_reload_env).
  */
 #ifndef GAAST_B200_H
 #define GAAST_B200_H
@@ -148,6 +160,11 @@ typedef enum gaast_dtype {
 
 /* Last error message of the calling thread (never NULL). */
 const char* gaast_last_error(void);
+/* The library reads its tuning / diagnostic environment variables (GAAST_HOST_CHUNK_MIB, GAAST_GRID_MULT,
+ * GAAST_NO_KERNEL_CACHE, GAAST_NVRTC, GAAST_NCCL, ... and, only together with GAAST_TEST_HOOKS=1,
+ * GAAST_KERNEL_CACHE) ONCE, at the first gaast_ctx_create / first use -- never on the evaluation path.
+ * This re-reads them: for tests and timing experiments, not thread-safe against running evaluations. */
+void gaast_reload_env(void);
 /* Library version string, and the CUDA arch the embedded kernels were built for. */
 const char* gaast_version(void);
 
@@ -239,8 +256,11 @@ gaast_status gaast_eval_sum(gaast_plan* plan, gaast_batch* const* inputs, uint32
  * arrays out, chunked so that H2D, kernels and D2H overlap.  host_in[s] points
  * to [comps of slot s][host_stride] (grades of in_masks[s] ascending), or, for a
  * broadcast slot, to [comps of slot s] contiguous values; host_out is
- * [root comps][host_stride].  Pinned host memory is needed for the copies to
- * overlap.  Synchronous: returns when host_out is complete. */
+ * [root comps][host_stride].  Pinned (page-locked) host memory is needed for the
+ * copies to overlap; pageable arrays give the same result, but the driver then
+ * stages every copy and the three streams serialise.  Synchronous: returns when
+ * host_out is complete.  On an error all copies already issued are drained before
+ * the call returns, so the caller may release its arrays. */
 gaast_status gaast_eval_host(gaast_plan* plan, const double* const* host_in, const uint32_t* in_masks,
                              const int* in_broadcast, uint32_t n_inputs, uint64_t len, uint64_t host_stride,
                              double* host_out, int engine, int arith);
@@ -272,6 +292,13 @@ uint32_t gaast_comm_size(const gaast_comm* comm);
  * device holds the element-wise total over all ranks.  Ordered on each ctx's stream, asynchronous. */
 gaast_status gaast_comm_allreduce_sum(gaast_comm* comm, double* const* dev_sums, size_t count);
 gaast_status gaast_comm_destroy(gaast_comm* comm);
+
+/* Diagnostic: the FP64 FMA-pipe throughput of ctx's device in TFLOP/s, measured by running independent
+ * DFMA chains (64 DFMA / clk / SM is the pipe's limit) for about `seconds` of device time on the ctx
+ * stream.  The roofline denominator of the compute-bound workloads, taken on the same box under the same
+ * conditions as the kernel: a short call (0.02) gives the burst figure, a long one (0.5) the sustained,
+ * power-capped one.  Synchronous. */
+gaast_status gaast_diag_fp64_peak(gaast_ctx* ctx, double seconds, double* tflops);
 
 /* Name and launch shape of the kernel the last gaast_eval on this plan used. */
 const char* gaast_plan_last_kernel(const gaast_plan* plan);

@@ -58,16 +58,84 @@ def test_algorithmic_cost_of_the_workloads(name, cost):
     assert g.Plan(None, W.specialize(w)).cost(w.broadcast_mask()) == cost
 
 
-def test_generated_kernels_compile_for_sm100a(tmp_path, monkeypatch):
-    """NVRTC cross-compiles the specialised kernel without a GPU (fresh cache dir)."""
+@pytest.fixture
+def scratch_cache(tmp_path, monkeypatch):
+    """A private kernel-cache directory: GAAST_KERNEL_CACHE is honoured only together with
+    GAAST_TEST_HOOKS=1, and the library reads its environment once -- gaast_reload_env() re-reads it."""
+    monkeypatch.setenv("GAAST_TEST_HOOKS", "1")
     monkeypatch.setenv("GAAST_KERNEL_CACHE", str(tmp_path))
+    L.lib.gaast_reload_env()
+    yield tmp_path
+    monkeypatch.delenv("GAAST_TEST_HOOKS")
+    monkeypatch.delenv("GAAST_KERNEL_CACHE")
+    L.lib.gaast_reload_env()
+
+
+def test_generated_kernels_compile_for_sm100a(scratch_cache):
+    """NVRTC cross-compiles the specialised kernel without a GPU (fresh cache dir); the second
+    request is served from the cache after its manifest has been verified."""
     w = W.WORKLOADS["cfg2"]
     plan = g.Plan(None, W.specialize(w))
     info = plan.precompile(w.broadcast_mask())
     assert "origin=nvrtc" in info
-    assert any(f.endswith(".cubin") for f in os.listdir(tmp_path))
+    assert any(f.endswith(".cubin") for f in os.listdir(scratch_cache))
+    assert any(f.endswith(".manifest") for f in os.listdir(scratch_cache))
     info2 = plan.precompile(w.broadcast_mask())
-    assert "origin=cache" in info2
+    assert "origin=override" in info2 and "unverified" not in info2  # a redirected cache says so in the origin
+
+
+def test_kernel_cache_override_needs_the_test_hook(tmp_path, monkeypatch):
+    """GAAST_KERNEL_CACHE alone does not redirect the cache: the in-tree one keeps serving."""
+    monkeypatch.setenv("GAAST_KERNEL_CACHE", str(tmp_path))
+    L.lib.gaast_reload_env()
+    try:
+        w = W.WORKLOADS["cfg1"]
+        info = g.Plan(None, W.specialize(w)).precompile(w.broadcast_mask())
+        assert os.listdir(tmp_path) == []
+        assert "origin=cache" in info or "origin=nvrtc" in info
+    finally:
+        monkeypatch.delenv("GAAST_KERNEL_CACHE")
+        L.lib.gaast_reload_env()
+
+
+def test_cached_cubins_are_verified_against_their_manifest(tmp_path):
+    """A cached cubin is loaded only when the manifest next to it names the source just generated and the
+    bytes on disk (sha256 of both, architecture, compile options).  One flipped byte, or a missing manifest,
+    makes the entry a cache miss: it is recompiled and rewritten, never loaded."""
+    import hashlib
+    import shutil
+    cache = os.path.join(os.path.dirname(os.path.abspath(g.__file__)), "kernel_cache")
+    w = W.WORKLOADS["cfg1"]
+    plan = g.Plan(None, W.specialize(w))
+    info = plan.precompile(w.broadcast_mask())
+    key = [t for t in info.split() if t.startswith("key=")][0][4:]
+    cubin, manifest = os.path.join(cache, key + ".cubin"), os.path.join(cache, key + ".manifest")
+    text = open(manifest).read()
+    fields = dict(l.split(" ", 1) for l in text.strip().split("\n")[1:])
+    assert fields["cubin_sha256"] == hashlib.sha256(open(cubin, "rb").read()).hexdigest()
+    assert fields["source_sha256"] == hashlib.sha256(open(os.path.join(cache, key + ".cu"), "rb").read()).hexdigest()
+    assert fields["arch"] == "sm_100a"
+    assert "origin=cache" in plan.precompile(w.broadcast_mask())
+    keep = tmp_path / "cubin.bak"
+    shutil.copy(cubin, keep)
+    try:
+        with open(cubin, "r+b") as f:  # flip one byte of the cached cubin
+            f.seek(100)
+            b = f.read(1)
+            f.seek(100)
+            f.write(bytes([b[0] ^ 0xFF]))
+        assert "origin=nvrtc" in plan.precompile(w.broadcast_mask())  # rejected, recompiled, rewritten
+        again = dict(l.split(" ", 1) for l in open(manifest).read().strip().split("\n")[1:])
+        assert again["cubin_sha256"] == hashlib.sha256(open(cubin, "rb").read()).hexdigest()
+        assert again["source_sha256"] == fields["source_sha256"]
+        assert "origin=cache" in plan.precompile(w.broadcast_mask())
+        os.remove(manifest)  # a cubin without a manifest is not trusted either
+        assert "origin=nvrtc" in plan.precompile(w.broadcast_mask())
+        assert os.path.exists(manifest)
+    finally:
+        if not os.path.exists(manifest):  # leave a loadable entry behind whatever happened
+            shutil.copy(keep, cubin)
+            open(manifest, "w").write(text)
 
 
 def test_no_device_means_no_compute():

@@ -164,10 +164,12 @@ def test_f32_eval_host_matches_resident(ctx):
     rows = sum(comb(w.n, k) for k in plan.root_grades())
     out = np.zeros((rows, batch), dtype=np.float32)
     os.environ["GAAST_HOST_CHUNK_MIB"] = "1"
+    L.lib.gaast_reload_env()  # the library reads its environment once
     try:
         plan.eval_host(flat_in, grades, bcs, batch, out)
     finally:
         del os.environ["GAAST_HOST_CHUNK_MIB"]
+        L.lib.gaast_reload_env()
     r = 0
     for k in plan.root_grades():
         c = comb(w.n, k)

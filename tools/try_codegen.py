@@ -6,6 +6,7 @@ name, ept, variant = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 w = W.WORKLOADS[name]
 d = tempfile.mkdtemp()
 os.environ["GAAST_KERNEL_CACHE"] = d
+os.environ["GAAST_TEST_HOOKS"] = "1"
 plan = Plan(None, W.specialize(w))
 plan.set_tuning(ept, variant)
 info = plan.precompile(w.broadcast_mask(), L.ARITH_FMA, len(sys.argv) > 4, True)
