@@ -443,6 +443,157 @@ struct Gen {
         return rewritten;
     }
 
+    // ---- reflection lowering: a vector sandwich  (v X) w  with  w = s v ------------------------
+    // For a vector v and ANY multivector X:  v X = X^ v + 2 (v _| X)   (X^ = grade involution, _| = left
+    // contraction; from e_i e_j = -e_j e_i + 2 g_ij, valid for every diagonal metric).  With w parallel to v
+    // the product v w is a scalar c = sum_i m_i v_i w_i, so
+    //        (v X) w  =  c X^  +  2 (v _| X) w.
+    // The reference evaluates the left side literally (eval.rs:61-86 twice): for cfg5's versor sandwich
+    // V X V^-1 with a grade-1 versor that is 792 + 792 terms through a 232-component intermediate; the right
+    // side needs the 12-component contraction (132 terms), its product with w restricted to the root's
+    // grades (132 terms), c (12) and one FMA per root component -- the kernel becomes a pure HBM stream.
+    // Everything is checked on the plan before rewriting: both products are complete geometric products on
+    // the grades they keep, v and w are grade-1 buffers, every w_i is the SAME scalar node times v_i, the
+    // intermediate has no other reader, and the metric is recovered (and cross-checked) from the first
+    // product's own coefficients.  A different rounding sequence (still within the 1e-12 bar, checked against
+    // the oracle and the strict engine): FMA arithmetic only.  variant bit 16 switches the pass off.
+    size_t lower_reflections(int pseudo_op) {
+        if (strict) return 0;
+        if (slot_blade.empty()) compute_blades();
+        size_t rewritten = 0;
+        const size_t n_ops = h.ops.size();
+        auto grade_of = [](uint32_t blade) { return uint32_t(__builtin_popcount(blade)); };
+        for (size_t oR = 0; oR < n_ops; ++oR) {
+            const gaast_op& R = h.ops[oR];
+            if (R.kind != GAAST_OP_MUL_TERMS) continue;
+            const uint32_t D = R.dst, T = R.a, Wb = R.b;
+            if (T == 0 || T == D || Wb == T || h.buffer_masks[Wb] != 2u) continue;
+            // the one op that writes T: a product V * X with a grade-1 left operand, before R
+            int oK = -1;
+            bool ok = true;
+            for (size_t i = 0; i < n_ops && ok; ++i) {
+                const gaast_op& o = h.ops[i];
+                if (o.dst == T) {
+                    if (oK >= 0 || o.kind != GAAST_OP_MUL_TERMS || i > oR) ok = false;
+                    oK = int(i);
+                }
+                if (o.kind == GAAST_OP_MUL_TERMS && i != oR && (o.a == T || o.b == T)) ok = false;  // T has another reader
+                if (i > oR && o.dst == D) ok = false;                                               // D is modified after R
+            }
+            if (!ok || oK < 0) continue;
+            const gaast_op& K = h.ops[size_t(oK)];
+            const uint32_t Vb = K.a, Xb = K.b;
+            if (h.buffer_masks[Vb] != 2u || Vb == T || Xb == T || Xb == D || Vb == D) continue;
+            for (size_t i = size_t(oK) + 1; i < n_ops && ok; ++i)  // operands must keep the value the products saw
+                if (h.ops[i].dst == Vb || h.ops[i].dst == Xb || (i > oR && h.ops[i].dst == Wb)) ok = false;
+            for (size_t i = size_t(oK) + 1; i < oR && ok; ++i)
+                if (h.ops[i].dst == T) ok = false;
+            if (!ok) continue;
+            const uint32_t n = h.n;
+            const auto& bV = slot_blade[Vb];
+            const auto& bX = slot_blade[Xb];
+            const auto& bT = slot_blade[T];
+            const auto& bD = slot_blade[D];
+            const auto& bW = slot_blade[Wb];
+            if (bV.size() != n || bW.size() != n) continue;
+            // w_i = (one common scalar node) * v_i, with one common sign and coefficient
+            int s_id = -1;
+            bool sign0 = false;
+            double coef0 = 0.0;
+            for (uint32_t i = 0; i < n && ok; ++i) {
+                const Ref wr = buf[Wb][i], vr = buf[Vb][i];
+                const Node& w = nodes[wr.id];
+                if (w.k != N_ACC || !is_zero(w.a) || w.uniform) { ok = false; break; }
+                const bool v_left = w.b.id == vr.id, v_right = w.c.id == vr.id;
+                if (!v_left && !v_right) { ok = false; break; }
+                const Ref other = v_left ? w.c : w.b;
+                if (other.id == vr.id) { ok = false; break; }
+                const bool sign = wr.neg ^ w.b.neg ^ w.c.neg ^ vr.neg ^ (w.cval < 0);
+                if (i == 0) { s_id = other.id; sign0 = sign; coef0 = std::fabs(w.cval); }
+                else if (other.id != s_id || sign != sign0 || std::fabs(w.cval) != coef0) ok = false;
+            }
+            if (!ok || s_id < 0) continue;
+            // both products complete on the grades they keep (a geometric product, not an outer / inner one)
+            auto complete = [&](const gaast_op& op, const std::vector<uint32_t>& bl, const std::vector<uint32_t>& br,
+                                const std::vector<uint32_t>& bo, uint32_t out_mask) {
+                size_t expect = 0;
+                for (uint32_t a : bl)
+                    for (uint32_t b : br) expect += (out_mask >> grade_of(a ^ b)) & 1;
+                if (expect != op.term_count) return false;
+                for (uint32_t t = op.term_begin; t < op.term_begin + op.term_count; ++t) {
+                    const gaast_term& tm = h.terms[t];
+                    if (tm.a >= bl.size() || tm.b >= br.size() || tm.out >= bo.size()) return false;
+                    if ((bl[tm.a] ^ br[tm.b]) != bo[tm.out]) return false;
+                }
+                return true;
+            };
+            if (!complete(K, bV, bX, bT, h.buffer_masks[T]) || !complete(R, bT, bW, bD, h.buffer_masks[D])) continue;
+            // metric from the first product's coefficients:  e_i B = (-1)^(bits of B below i) m_i (B \ i)  for i in B
+            std::vector<double> metric(n, 0.0);
+            std::vector<char> have(n, 0);
+            for (uint32_t t = K.term_begin; t < K.term_begin + K.term_count && ok; ++t) {
+                const gaast_term& tm = h.terms[t];
+                const uint32_t a = bV[tm.a], b = bX[tm.b];
+                const uint32_t i = uint32_t(__builtin_ctz(a));
+                if (!(b & a)) continue;
+                const double m = tm.coeff * ((__builtin_popcount(b & (a - 1)) & 1) ? -1.0 : 1.0);
+                if (m == 0.0) ok = false;
+                if (have[i] && metric[i] != m) ok = false;
+                metric[i] = m;
+                have[i] = 1;
+            }
+            for (uint32_t i = 0; i < n; ++i) ok = ok && have[bV[i] ? uint32_t(__builtin_ctz(bV[i])) : 0];
+            if (!ok) continue;
+            // R's chains must sit directly on the buffer's prior content, and be what the root reads now
+            std::vector<Ref> prior(bD.size(), Ref{0, false});
+            std::vector<char> touched(bD.size(), 0);
+            for (int id : op_accs[oR]) {
+                const Node& nd = nodes[id];
+                if (!touched[nd.out_slot]) { prior[nd.out_slot] = nd.a; touched[nd.out_slot] = 1; }
+            }
+            std::vector<int> last(bD.size(), -1);
+            for (int id : op_accs[oR]) last[nodes[id].out_slot] = id;
+            for (size_t o = 0; o < bD.size() && ok; ++o) {
+                if (!touched[o]) prior[o] = buf[D][o];
+                else if (buf[D][o].id != last[o] || buf[D][o].neg) ok = false;
+            }
+            if (!ok) continue;
+            // ---- build the right-hand side ----
+            Ref c{0, false};  // v . w
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint32_t e = uint32_t(__builtin_ctz(bV[i]));
+                uint32_t wi = 0;
+                while (wi < n && bW[wi] != bV[i]) ++wi;
+                c = make_acc(c, buf[Vb][i], buf[Wb][wi], metric[e], pseudo_op);
+            }
+            std::vector<Ref> U(bT.size(), Ref{0, false});  // v _| X: the terms of V * X that lower the grade
+            for (uint32_t t = K.term_begin; t < K.term_begin + K.term_count; ++t) {
+                const gaast_term& tm = h.terms[t];
+                if (grade_of(bT[tm.out]) + 1 != grade_of(bX[tm.b])) continue;
+                U[tm.out] = make_acc(U[tm.out], buf[Vb][tm.a], buf[Xb][tm.b], tm.coeff, pseudo_op);
+            }
+            std::map<uint32_t, uint32_t> x_slot_of_blade;
+            for (uint32_t sx = 0; sx < bX.size(); ++sx) x_slot_of_blade[bX[sx]] = sx;
+            std::vector<Ref> res(bD.size());
+            for (size_t o = 0; o < bD.size(); ++o) {
+                Ref acc = prior[o];
+                auto xs = x_slot_of_blade.find(bD[o]);
+                if (xs != x_slot_of_blade.end()) {
+                    const Ref x = buf[Xb][xs->second];
+                    acc = make_acc(acc, flip(x, grade_of(bD[o]) & 1), c, 1.0, pseudo_op);  // c X^
+                }
+                res[o] = acc;
+            }
+            for (uint32_t t = R.term_begin; t < R.term_begin + R.term_count; ++t) {
+                const gaast_term& tm = h.terms[t];
+                res[tm.out] = make_acc(res[tm.out], U[tm.a], buf[Wb][tm.b], 2.0 * tm.coeff, pseudo_op);  // 2 (v _| X) w
+            }
+            for (size_t o = 0; o < bD.size(); ++o) buf[D][o] = res[o];
+            ++rewritten;
+        }
+        return rewritten;
+    }
+
     void mark_live() {
         std::vector<int> stack;
         for (Ref r : buf[0]) stack.push_back(r.id);
@@ -496,6 +647,7 @@ struct Gen {
         // popcount in ascending numeric order (algebra.rs:221-246)
         std::vector<std::vector<uint32_t>> of_grade(h.n + 1);
         for (uint32_t b = 0; b < (1u << h.n); ++b) of_grade[__builtin_popcount(b)].push_back(b);
+        if (!slot_blade.empty()) return;
         slot_blade.resize(h.buffer_masks.size());
         for (size_t b = 0; b < h.buffer_masks.size(); ++b)
             for (uint32_t k = 0; k <= h.n; ++k)
@@ -1329,6 +1481,14 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             notes << "scalar-factored(" << factored << " products) ";
         }
     }
+    if (!(opt.variant & 65536)) {
+        const size_t reflected = g.lower_reflections(pseudo_op);
+        if (reflected) {
+            for (Node& n : g.nodes) n.live = false;
+            g.mark_live();
+            notes << "reflection(" << reflected << " sandwich" << (reflected > 1 ? "es) " : ") ");
+        }
+    }
     if (!(opt.variant & 2048)) {
         const size_t lowered = g.lower_linear(pseudo_op);
         if (lowered) {
@@ -1439,7 +1599,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         size_t pressure = widest_table + kept + 12;
         live_estimate = pressure;
         size_t want = pressure > kLiveBudget ? pressure - kLiveBudget : 0;
-        if (opt.variant >> 16) want = size_t(opt.variant >> 16) - 1;  // tuning override: variant |= (count + 1) << 16
+        if (opt.variant >> 24) want = size_t(opt.variant >> 24) - 1;  // tuning override: variant |= (count + 1) << 24
         want += size_t(opt.extra_parked);  // raised by the compile-and-check loop while ptxas reports spills
         std::sort(cand.begin(), cand.end());
         size_t n_reload = 0;

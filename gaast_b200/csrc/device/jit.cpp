@@ -299,6 +299,12 @@ std::vector<char> build_specialized(const DevicePlanHost& h, CodegenOptions opt,
             std::fprintf(stderr, "[gaast codegen] attempt %d: parked=%d/%d spill=%zuB smem=%zuB %s\n", attempt, cg.parked,
                          cg.parkable, spill, cg.smem_bytes, cg.notes.c_str());
         if (spill <= 8 || !can_park_more || attempt >= 8) {
+            // A kernel that still spills kilobytes per thread (a wide strict-arithmetic product that cannot be
+            // blocked: G(7) A*B in reference order keeps 128 accumulators + 256 operands live) moves its working
+            // set through local memory on every term; the table engine keeps it in shared memory instead.
+            if (spill > 4096 && !(opt.variant & 64))
+                throw Error(GAAST_ERR_JIT, "plan too wide for the specialised engine (the kernel spills " + std::to_string(spill) +
+                                               " bytes per thread): use the table engine");
             *cg_out = std::move(cg);
             return cubin;
         }
