@@ -997,6 +997,14 @@ struct Gen {
         std::vector<double> sigma;      // [ah * H + bh]
         std::vector<double> lambda;     // [al * 16 + bl]
         bool unit_sigma = true;
+        // matrix-representation product (n = 6, +-1 metric): see plan_matrep
+        struct MatRep {
+            bool ok = false;
+            int tau_blade[64], tau_sign[64];  // tensor basis element tau = k0 + 4 k1 + 16 k2  ==  sign * e_blade
+            int F[3][4][4];                   // fast factors (0 and 2): matrix entry e = 2 row + col from basis coefficient k
+            int s1_k[4][4], s1_sign[4][4];    // middle factor: b[p] b[q] = sign * b[k]
+            int perm[6];
+        } mr;
     } dense;
     std::ostringstream file_scope, kernel_setup;
     bool dense_tmem = false;  // DENSE: left operand parked in tensor memory (3 blocks per SM instead of 2)
@@ -1067,12 +1075,301 @@ struct Gen {
                 const double chi = (__builtin_popcount(ah) * __builtin_popcount(bl)) & 1 ? -1.0 : 1.0;
                 if (coeff[a * B + b] != d.sigma[ah * d.H + bh] * chi * d.lambda[al * 16 + bl]) return false;
             }
+        if (d.unit_sigma) plan_matrep(d, coeff);
         dense = d;
         return true;
     }
 
+    // ---- the full geometric product of G(6) through its matrix representation ------------------
+    // G(p,q), p + q = 6, is a tensor product of three 4-dimensional algebras that commute with each other:
+    // with Omega_j = g_1 ... g_2j (the generators taken in some order g), factor j is generated by
+    // x_j = Omega_j g_(2j+1) and y_j = Omega_j g_(2j+2), which anticommute and square to +-1.  A factor with a
+    // generator of square +1 is the algebra of real 2 x 2 matrices, M_2(R): in the basis of matrix units its
+    // product costs 8 multiplications instead of 16; a factor with x^2 = y^2 = -1 is the quaternions.  Every
+    // basis element of the tensor product is +- one blade (a signed permutation of the 64 components), the
+    // change to matrix units is one add / subtract per component and factor, and the 4 096-term product
+    // becomes  2 x 128 (operand transforms) + 8 x 16 x 8 = 1 024 FMAs + 128 + 64 (result transform, scaling)
+    // = 1 472 FP64 operations: G(6,0) = M_2(R) (x) H (x) M_2(R) = M_4(H).  The generator order is searched so
+    // that factors 0 and 2 are M_2(R) (the middle factor is multiplied out in full, whatever its type).
+    // The tables are derived from the plan's own coefficient table and the scheme is checked numerically
+    // against that table before it is used (variant bit 17 switches it off: the 4 096-FMA rolled product).
+    // A different summation order and 5 roundings per component more than the reference: FMA arithmetic only.
+    using MatRep = Dense::MatRep;
+    static void matrep_apply(const MatRep& m, const double* A, const double* Bv, double* C) {
+        double a2[64], b2[64], c2[64] = {};
+        auto fwd = [&](const double* in, double* out) {
+            double t[64], u[64];
+            for (int tau = 0; tau < 64; ++tau) t[tau] = m.tau_sign[tau] * in[m.tau_blade[tau]];
+            for (int k1 = 0; k1 < 4; ++k1)
+                for (int k2 = 0; k2 < 4; ++k2)
+                    for (int e0 = 0; e0 < 4; ++e0) {
+                        double v = 0;
+                        for (int k0 = 0; k0 < 4; ++k0) v += m.F[0][e0][k0] * t[k0 + 4 * k1 + 16 * k2];
+                        u[e0 + 4 * k1 + 16 * k2] = v;
+                    }
+            for (int e0 = 0; e0 < 4; ++e0)
+                for (int k1 = 0; k1 < 4; ++k1)
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        double v = 0;
+                        for (int k2 = 0; k2 < 4; ++k2) v += m.F[2][e2][k2] * u[e0 + 4 * k1 + 16 * k2];
+                        out[e0 + 4 * k1 + 16 * e2] = v;
+                    }
+        };
+        fwd(A, a2);
+        fwd(Bv, b2);
+        for (int p = 0; p < 4; ++p)
+            for (int q = 0; q < 4; ++q) {
+                const int k1 = m.s1_k[p][q];
+                const double sg = m.s1_sign[p][q];
+                for (int i0 = 0; i0 < 2; ++i0)
+                    for (int j0 = 0; j0 < 2; ++j0)
+                        for (int l0 = 0; l0 < 2; ++l0)
+                            for (int i2 = 0; i2 < 2; ++i2)
+                                for (int j2 = 0; j2 < 2; ++j2)
+                                    for (int l2 = 0; l2 < 2; ++l2)
+                                        c2[(2 * i0 + l0) + 4 * k1 + 16 * (2 * i2 + l2)] +=
+                                            sg * a2[(2 * i0 + j0) + 4 * p + 16 * (2 * i2 + j2)] * b2[(2 * j0 + l0) + 4 * q + 16 * (2 * j2 + l2)];
+            }
+        for (int k0 = 0; k0 < 4; ++k0)
+            for (int k1 = 0; k1 < 4; ++k1)
+                for (int k2 = 0; k2 < 4; ++k2) {
+                    double v = 0;
+                    for (int e0 = 0; e0 < 4; ++e0)
+                        for (int e2 = 0; e2 < 4; ++e2) v += m.F[0][e0][k0] * m.F[2][e2][k2] * c2[e0 + 4 * k1 + 16 * e2];
+                    const int tau = k0 + 4 * k1 + 16 * k2;
+                    C[m.tau_blade[tau]] = 0.25 * m.tau_sign[tau] * v;
+                }
+    }
+
+    bool plan_matrep(Dense& d, const std::vector<double>& coeff) const {
+        if (d.n != 6 || (opt.variant & 131072)) return false;
+        const int B = 64;
+        for (double c : coeff)
+            if (std::fabs(c) != 1.0) return false;
+        struct SB { int blade; int sign; };
+        auto mul = [&](SB a, SB b) { return SB{a.blade ^ b.blade, a.sign * b.sign * (coeff[size_t(a.blade) * B + b.blade] < 0 ? -1 : 1)}; };
+        int perm[6] = {0, 1, 2, 3, 4, 5};
+        do {
+            MatRep m;
+            SB basis[3][4];
+            SB omega{0, 1};
+            int alpha[3], beta[3];
+            for (int j = 0; j < 3; ++j) {
+                const SB g1{1 << perm[2 * j], 1}, g2{1 << perm[2 * j + 1], 1};
+                const SB x = mul(omega, g1), y = mul(omega, g2);
+                basis[j][0] = SB{0, 1};
+                basis[j][1] = x;
+                basis[j][2] = y;
+                basis[j][3] = mul(x, y);
+                alpha[j] = mul(x, x).sign;
+                beta[j] = mul(y, y).sign;
+                omega = mul(mul(omega, g1), g2);
+            }
+            if ((alpha[0] < 0 && beta[0] < 0) || (alpha[2] < 0 && beta[2] < 0)) continue;  // factors 0 and 2 must be M_2(R)
+            // tensor basis -> signed blade (must be a bijection)
+            bool seen[64] = {};
+            bool ok = true;
+            for (int k2 = 0; k2 < 4 && ok; ++k2)
+                for (int k1 = 0; k1 < 4 && ok; ++k1)
+                    for (int k0 = 0; k0 < 4; ++k0) {
+                        const SB t = mul(mul(basis[0][k0], basis[1][k1]), basis[2][k2]);
+                        if (seen[t.blade]) { ok = false; break; }
+                        seen[t.blade] = true;
+                        m.tau_blade[k0 + 4 * k1 + 16 * k2] = t.blade;
+                        m.tau_sign[k0 + 4 * k1 + 16 * k2] = t.sign;
+                    }
+            if (!ok) continue;
+            // 2 x 2 real representations of the fast factors
+            for (int j : {0, 2}) {
+                int X[4], Y[4];  // row-major 2 x 2
+                if (alpha[j] > 0) {
+                    X[0] = 1; X[1] = 0; X[2] = 0; X[3] = -1;
+                    Y[0] = 0; Y[1] = 1; Y[2] = beta[j]; Y[3] = 0;
+                } else {
+                    Y[0] = 1; Y[1] = 0; Y[2] = 0; Y[3] = -1;
+                    X[0] = 0; X[1] = 1; X[2] = alpha[j]; X[3] = 0;
+                }
+                const int XY[4] = {X[0] * Y[0] + X[1] * Y[2], X[0] * Y[1] + X[1] * Y[3], X[2] * Y[0] + X[3] * Y[2], X[2] * Y[1] + X[3] * Y[3]};
+                const int I[4] = {1, 0, 0, 1};
+                for (int e = 0; e < 4; ++e) {
+                    m.F[j][e][0] = I[e];
+                    m.F[j][e][1] = X[e];
+                    m.F[j][e][2] = Y[e];
+                    m.F[j][e][3] = XY[e];
+                }
+            }
+            for (int e = 0; e < 4; ++e)
+                for (int k = 0; k < 4; ++k) m.F[1][e][k] = e == k;
+            // the middle factor's multiplication table
+            for (int pp = 0; pp < 4 && ok; ++pp)
+                for (int q = 0; q < 4; ++q) {
+                    const SB r = mul(basis[1][pp], basis[1][q]);
+                    int k = -1;
+                    for (int c = 0; c < 4; ++c)
+                        if (basis[1][c].blade == r.blade) k = c;
+                    if (k < 0) { ok = false; break; }
+                    m.s1_k[pp][q] = k;
+                    m.s1_sign[pp][q] = r.sign * basis[1][k].sign;
+                }
+            if (!ok) continue;
+            // numerical check of the whole scheme against the plan's own table
+            double A[64], Bv[64], want[64] = {}, got[64];
+            uint64_t seed = 0x9E3779B97F4A7C15ull;
+            auto rnd = [&]() {
+                seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17;
+                return double(int64_t(seed >> 11) % 2001 - 1000) / 1000.0;
+            };
+            for (int i = 0; i < 64; ++i) { A[i] = rnd(); Bv[i] = rnd(); }
+            for (int a = 0; a < 64; ++a)
+                for (int b = 0; b < 64; ++b) want[a ^ b] += coeff[size_t(a) * B + b] * A[a] * Bv[b];
+            matrep_apply(m, A, Bv, got);
+            for (int i = 0; i < 64; ++i)
+                if (std::fabs(got[i] - want[i]) > 1e-9) ok = false;
+            if (!ok) continue;
+            for (int i = 0; i < 6; ++i) m.perm[i] = perm[i];
+            m.ok = true;
+            d.mr = m;
+            return true;
+        } while (std::next_permutation(perm, perm + 6));
+        return false;
+    }
+
+    // c1 * x1 + c2 * x2 with c in {+1, -1}: one add (negations are operand modifiers)
+    std::string pm(int c1, const std::string& x1, int c2, const std::string& x2) const {
+        const std::string a = c1 > 0 ? x1 : "d_neg(" + x1 + ")", b = c2 > 0 ? x2 : "d_neg(" + x2 + ")";
+        return "d_add(" + a + ", " + b + ")";
+    }
+    // the two nonzero entries of row e of F[j] (basis coefficient -> matrix entry), or of column k (the transpose)
+    void nz_row(const MatRep& m, int j, int e, int idx[2], int sg[2]) const {
+        int c = 0;
+        for (int k = 0; k < 4; ++k)
+            if (m.F[j][e][k]) { idx[c] = k; sg[c] = m.F[j][e][k]; ++c; }
+    }
+    void nz_col(const MatRep& m, int j, int k, int idx[2], int sg[2]) const {
+        int c = 0;
+        for (int e = 0; e < 4; ++e)
+            if (m.F[j][e][k]) { idx[c] = e; sg[c] = m.F[j][e][k]; ++c; }
+    }
+
+    void emit_op_dense_matrep(int op) {
+        const Dense& d = dense;
+        const MatRep& m = d.mr;
+        std::vector<std::pair<size_t, uint32_t>> col_at;
+        for (size_t si = h.n_in_streams; si < h.streams.size(); ++si)
+            for (uint32_t r = 0; r < h.streams[si].rows; ++r) col_at.push_back({si, r});
+        auto T = [](int k0, int k1, int k2) { return k0 + 4 * k1 + 16 * k2; };
+        // shared-memory row of the right operand's component: before the transform the row of its blade, after it the
+        // same 64 rows re-labelled by (e0, k1, e2)
+        auto srow = [&](int i0, int k1, int i2) {
+            return "xs_ld<" + std::to_string(size_t(nodes[d.right[m.tau_blade[T(i0, k1, i2)]]].smem_row) * esize) + " * GAAST_THREADS>(xb)";
+        };
+        auto srow_st = [&](int i0, int k1, int i2, const std::string& v) {
+            return "xs_st<" + std::to_string(size_t(nodes[d.right[m.tau_blade[T(i0, k1, i2)]]].smem_row) * esize) + " * GAAST_THREADS>(xb, " + v + ");";
+        };
+        int idx[2], sg[2];
+        // ---- right operand: signed permutation + the two fast transforms, in place in shared memory ----
+        for (int k1 = 0; k1 < 4; ++k1) {
+            line("{");
+            ++indent;
+            for (int k2 = 0; k2 < 4; ++k2)
+                for (int k0 = 0; k0 < 4; ++k0) line("const " + S + " r" + std::to_string(k0) + "_" + std::to_string(k2) + " = " + srow(k0, k1, k2) + ";");
+            for (int k2 = 0; k2 < 4; ++k2)
+                for (int e0 = 0; e0 < 4; ++e0) {
+                    nz_row(m, 0, e0, idx, sg);
+                    line("const " + S + " u" + std::to_string(e0) + "_" + std::to_string(k2) + " = " +
+                         pm(sg[0] * m.tau_sign[T(idx[0], k1, k2)], "r" + std::to_string(idx[0]) + "_" + std::to_string(k2),
+                            sg[1] * m.tau_sign[T(idx[1], k1, k2)], "r" + std::to_string(idx[1]) + "_" + std::to_string(k2)) + ";");
+                }
+            for (int e0 = 0; e0 < 4; ++e0)
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    nz_row(m, 2, e2, idx, sg);
+                    line(srow_st(e0, k1, e2, pm(sg[0], "u" + std::to_string(e0) + "_" + std::to_string(idx[0]), sg[1],
+                                                "u" + std::to_string(e0) + "_" + std::to_string(idx[1]))));
+                }
+            --indent;
+            line("}");
+        }
+        // ---- left operand: the same transforms in registers ----
+        for (int a = 0; a < 64; ++a) emit(d.left[a].id);
+        auto am = [](int e0, int k1, int e2) { return "am" + std::to_string(e0) + "_" + std::to_string(k1) + "_" + std::to_string(e2); };
+        for (int k1 = 0; k1 < 4; ++k1) {
+            for (int k2 = 0; k2 < 4; ++k2)
+                for (int e0 = 0; e0 < 4; ++e0) {
+                    nz_row(m, 0, e0, idx, sg);
+                    const Ref x0 = d.left[m.tau_blade[T(idx[0], k1, k2)]], x1 = d.left[m.tau_blade[T(idx[1], k1, k2)]];
+                    line("const " + S + " au" + std::to_string(e0) + "_" + std::to_string(k1) + "_" + std::to_string(k2) + " = d_add(" +
+                         opnd(x0, true, sg[0] * m.tau_sign[T(idx[0], k1, k2)] < 0) + ", " +
+                         opnd(x1, true, sg[1] * m.tau_sign[T(idx[1], k1, k2)] < 0) + ");");
+                }
+            for (int e0 = 0; e0 < 4; ++e0)
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    nz_row(m, 2, e2, idx, sg);
+                    line("const " + S + " " + am(e0, k1, e2) + " = " +
+                         pm(sg[0], "au" + std::to_string(e0) + "_" + std::to_string(k1) + "_" + std::to_string(idx[0]), sg[1],
+                            "au" + std::to_string(e0) + "_" + std::to_string(k1) + "_" + std::to_string(idx[1])) + ";");
+                }
+        }
+        // ---- C''[(i0,l0)][k1][(i2,l2)] = sum_{p q -> k1} s sum_{j0 j2} A''[(i0,j0)][p][(i2,j2)] B''[(j0,l0)][q][(j2,l2)] ----
+        int bcount = 0;
+        for (int k1 = 0; k1 < 4; ++k1) {
+            line("{");
+            ++indent;
+            bool started[16] = {};
+            for (int c = 0; c < 16; ++c) line(S + " c" + std::to_string(c) + ";");
+            for (int p = 0; p < 4; ++p) {
+                int q = -1;
+                for (int qq = 0; qq < 4; ++qq)
+                    if (m.s1_k[p][qq] == k1) q = qq;
+                const bool neg = m.s1_sign[p][q] < 0;
+                for (int j0 = 0; j0 < 2; ++j0)
+                    for (int l0 = 0; l0 < 2; ++l0)
+                        for (int j2 = 0; j2 < 2; ++j2)
+                            for (int l2 = 0; l2 < 2; ++l2) {
+                                // right-operand-major: the 4 FMAs that share one value fresh from shared memory are consecutive
+                                const std::string b = "b" + std::to_string(bcount++);
+                                line("const " + S + " " + b + " = " + srow(2 * j0 + l0, q, 2 * j2 + l2) + ";");
+                                for (int i0 = 0; i0 < 2; ++i0)
+                                    for (int i2 = 0; i2 < 2; ++i2) {
+                                        const int ci = (2 * i0 + l0) + 4 * (2 * i2 + l2);
+                                        const std::string c = "c" + std::to_string(ci);
+                                        const std::string A = std::string(neg ? "d_neg(" : "") + am(2 * i0 + j0, p, 2 * i2 + j2) + (neg ? ")" : "");
+                                        if (!started[ci]) line(c + " = d_mul(" + A + ", " + b + ");");
+                                        else line(c + " = d_fma(" + A + ", " + b + ", " + c + ");");
+                                        started[ci] = true;
+                                    }
+                            }
+            }
+            // back to the tensor basis (the transposes of the two transforms, 1/4 overall), sign, store
+            for (int e2 = 0; e2 < 4; ++e2)
+                for (int k0 = 0; k0 < 4; ++k0) {
+                    nz_col(m, 0, k0, idx, sg);
+                    line("const " + S + " x" + std::to_string(k0) + "_" + std::to_string(e2) + " = " +
+                         pm(sg[0], "c" + std::to_string(idx[0] + 4 * e2), sg[1], "c" + std::to_string(idx[1] + 4 * e2)) + ";");
+                }
+            for (int k0 = 0; k0 < 4; ++k0)
+                for (int k2 = 0; k2 < 4; ++k2) {
+                    nz_col(m, 2, k2, idx, sg);
+                    const int tau = T(k0, k1, k2);
+                    const auto at = col_at[size_t(d.out_col[m.tau_blade[tau]])];
+                    const std::string v = "d_mul(U(" + std::string(m.tau_sign[tau] < 0 ? "-0.25" : "0.25") + "), " +
+                                          pm(sg[0], "x" + std::to_string(k0) + "_" + std::to_string(idx[0]), sg[1],
+                                             "x" + std::to_string(k0) + "_" + std::to_string(idx[1])) + ")";
+                    if (opt.store_out)
+                        line("d_store(s" + std::to_string(at.first) + " + " + std::to_string(at.second) + " * r" + std::to_string(at.first) + " + e, " + v + ");");
+                }
+            --indent;
+            line("}");
+        }
+        for (int id : op_accs[op]) emitted[id] = 1;
+        for (int o = 0; o < 64; ++o) root_done[d.out_col[o]] = 1;
+    }
+
     void emit_op_dense(int op) {
         const Dense& d = dense;
+        if (d.mr.ok && !dense_tmem) {
+            emit_op_dense_matrep(op);
+            return;
+        }
         const int hb = blocked_low_bits, B = 1 << d.n;
         // root column -> (stream, row)
         std::vector<std::pair<size_t, uint32_t>> col_at;
@@ -1575,7 +1872,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         if (pol == P_TABLE) widest_table = std::max(widest_table, outs.size());
         widest = std::max(widest, outs.size());
         notes << "op" << oi << ":"
-              << (pol == P_TABLE ? "table" : pol == P_GATHER ? "gather" : pol == P_DENSE ? "dense-rolled" : "blocked")
+              << (pol == P_TABLE ? "table" : pol == P_GATHER ? "gather" : pol == P_DENSE ? (g.dense.mr.ok ? "dense-matrep" : "dense-rolled") : "blocked")
               << "(outs=" << outs.size() << ",terms=" << live_terms << ") ";
     }
     for (int id : g.op_accs[pseudo_op]) {
@@ -1686,6 +1983,11 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     res.parked = res_parked;
     res.parkable = res_parkable;
     for (const Node& n : g.nodes) res.fma_per_elem += n.live && n.k == N_ACC && !n.uniform;
+    if (g.dense.op >= 0 && g.dense.mr.ok && !g.dense_tmem) {
+        // the matrix-representation product executes 1 024 FMAs + 448 additions / scalings for the op's 4 096 terms:
+        // reported as flop / 2, so that 2 x fma/elem stays the executed flop count
+        res.fma_per_elem += (2 * 1024 + 448) / 2 - 4096;
+    }
 
     std::ostringstream src;
     src << "// generated by gaast_b200 codegen: n=" << h.n << " terms=" << h.total_terms << " arith="

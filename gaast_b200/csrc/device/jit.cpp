@@ -302,7 +302,7 @@ std::vector<char> build_specialized(const DevicePlanHost& h, CodegenOptions opt,
             // A kernel that still spills kilobytes per thread (a wide strict-arithmetic product that cannot be
             // blocked: G(7) A*B in reference order keeps 128 accumulators + 256 operands live) moves its working
             // set through local memory on every term; the table engine keeps it in shared memory instead.
-            if (spill > 4096 && !(opt.variant & 64))
+            if (spill > 8192 && !(opt.variant & 64))
                 throw Error(GAAST_ERR_JIT, "plan too wide for the specialised engine (the kernel spills " + std::to_string(spill) +
                                                " bytes per thread): use the table engine");
             *cg_out = std::move(cg);
