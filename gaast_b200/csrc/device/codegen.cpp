@@ -478,7 +478,6 @@ struct Gen {
                     oK = int(i);
                 }
                 if (o.kind == GAAST_OP_MUL_TERMS && i != oR && (o.a == T || o.b == T)) ok = false;  // T has another reader
-                if (i > oR && o.dst == D) ok = false;                                               // D is modified after R
             }
             if (!ok || oK < 0) continue;
             const gaast_op& K = h.ops[size_t(oK)];
@@ -544,7 +543,8 @@ struct Gen {
             }
             for (uint32_t i = 0; i < n; ++i) ok = ok && have[bV[i] ? uint32_t(__builtin_ctz(bV[i])) : 0];
             if (!ok) continue;
-            // R's chains must sit directly on the buffer's prior content, and be what the root reads now
+            // R's chain per output: what it was started from (the buffer's content before R) and its last link --
+            // the value every later reader of the buffer sees (sign flips live in the references to it)
             std::vector<Ref> prior(bD.size(), Ref{0, false});
             std::vector<char> touched(bD.size(), 0);
             for (int id : op_accs[oR]) {
@@ -553,12 +553,9 @@ struct Gen {
             }
             std::vector<int> last(bD.size(), -1);
             for (int id : op_accs[oR]) last[nodes[id].out_slot] = id;
-            for (size_t o = 0; o < bD.size() && ok; ++o) {
-                if (!touched[o]) prior[o] = buf[D][o];
-                else if (buf[D][o].id != last[o] || buf[D][o].neg) ok = false;
-            }
-            if (!ok) continue;
+            if (op_accs[oR].empty()) continue;  // nothing of this product survives (an empty root)
             // ---- build the right-hand side ----
+            const size_t first_new = nodes.size();
             Ref c{0, false};  // v . w
             for (uint32_t i = 0; i < n; ++i) {
                 const uint32_t e = uint32_t(__builtin_ctz(bV[i]));
@@ -576,6 +573,7 @@ struct Gen {
             for (uint32_t sx = 0; sx < bX.size(); ++sx) x_slot_of_blade[bX[sx]] = sx;
             std::vector<Ref> res(bD.size());
             for (size_t o = 0; o < bD.size(); ++o) {
+                if (!touched[o]) continue;
                 Ref acc = prior[o];
                 auto xs = x_slot_of_blade.find(bD[o]);
                 if (xs != x_slot_of_blade.end()) {
@@ -586,9 +584,29 @@ struct Gen {
             }
             for (uint32_t t = R.term_begin; t < R.term_begin + R.term_count; ++t) {
                 const gaast_term& tm = h.terms[t];
+                if (!touched[tm.out]) continue;
                 res[tm.out] = make_acc(res[tm.out], U[tm.a], buf[Wb][tm.b], 2.0 * tm.coeff, pseudo_op);  // 2 (v _| X) w
             }
-            for (size_t o = 0; o < bD.size(); ++o) buf[D][o] = res[o];
+            // every reader of the old chain ends (later ops on the same buffer, the root) now reads the new values
+            std::map<int, Ref> replace;
+            for (size_t o = 0; o < bD.size(); ++o)
+                if (touched[o]) replace[last[o]] = res[o];
+            // (the nodes created above, from first_new on, never refer to the old chain ends)
+            auto fix = [&](Ref& r) {
+                auto it = replace.find(r.id);
+                if (it != replace.end()) r = Ref{it->second.id, bool(r.neg ^ it->second.neg)};
+            };
+            for (size_t id = 0; id < first_new && id < nodes.size(); ++id) {
+                Node& nd = nodes[id];
+                if (nd.k == N_ACC && nd.op == int(oR)) continue;  // the old chain itself (now dead)
+                if (nd.k == N_ACC || nd.k == N_ADD || nd.k == N_INV || nd.k == N_SQRT) {
+                    fix(nd.a);
+                    if (nd.k == N_ACC || nd.k == N_ADD) fix(nd.b);
+                    if (nd.k == N_ACC) fix(nd.c);
+                }
+            }
+            for (auto& bb : buf)
+                for (Ref& r : bb) fix(r);
             ++rewritten;
         }
         return rewritten;
@@ -999,12 +1017,17 @@ struct Gen {
         bool unit_sigma = true;
         // matrix-representation product (n = 6, +-1 metric): see plan_matrep
         struct MatRep {
+            struct Tri { int out, a, b, sign; };
             bool ok = false;
             int tau_blade[64], tau_sign[64];  // tensor basis element tau = k0 + 4 k1 + 16 k2  ==  sign * e_blade
-            int F[3][4][4];                   // fast factors (0 and 2): matrix entry e = 2 row + col from basis coefficient k
-            int s1_k[4][4], s1_sign[4][4];    // middle factor: b[p] b[q] = sign * b[k]
+            bool fast[3] = {false, false, false};  // the factor is M_2(R) and is multiplied in its matrix-unit basis
+            int F[3][4][4];                   // fast factor: matrix entry e = 2 row + col from basis coefficient k; else identity
+            std::vector<Tri> tri[3];          // the factor's multiplication table: 8 entries (2 x 2 matmul) or 16
+            int group = 1;                    // a full-table factor: its output index labels the four accumulator groups
+            int n_fma = 0, n_add = 0;         // operations per element
             int perm[6];
         } mr;
+        std::vector<char> right_neg;          // [blade] the right operand enters negated (A * B.ginvol()); matrix path only
     } dense;
     std::ostringstream file_scope, kernel_setup;
     bool dense_tmem = false;  // DENSE: left operand parked in tensor memory (3 blocks per SM instead of 2)
@@ -1022,6 +1045,7 @@ struct Gen {
         d.H = 1 << (n - hb);
         d.left.assign(B, Ref{-1, false});
         d.right.assign(B, -1);
+        d.right_neg.assign(B, 0);
         d.out_col.assign(B, -1);
         d.out_neg.assign(B, 0);
         d.sigma.assign(size_t(d.H) * d.H, 0.0);
@@ -1042,9 +1066,10 @@ struct Gen {
             if (d.left[a].id >= 0 && (d.left[a].id != nd.b.id || d.left[a].neg != nd.b.neg)) return false;
             d.left[a] = nd.b;
             const Node& r = nodes[nd.c.id];
-            if (r.k != N_LOAD || r.uniform || nd.c.neg) return false;
-            if (d.right[b] >= 0 && d.right[b] != nd.c.id) return false;
+            if (r.k != N_LOAD || r.uniform) return false;
+            if (d.right[b] >= 0 && (d.right[b] != nd.c.id || bool(d.right_neg[b]) != nd.c.neg)) return false;
             d.right[b] = nd.c.id;
+            d.right_neg[b] = nd.c.neg;
             if (last[o] < 0 && !is_zero(nd.a)) return false;  // accumulators must start from zero
             last[o] = id;
         }
@@ -1075,7 +1100,11 @@ struct Gen {
                 const double chi = (__builtin_popcount(ah) * __builtin_popcount(bl)) & 1 ? -1.0 : 1.0;
                 if (coeff[a * B + b] != d.sigma[ah * d.H + bh] * chi * d.lambda[al * 16 + bl]) return false;
             }
+        // (a negated right operand is folded into the signs: undo it in the table the schemes are derived from)
+        bool any_right_neg = false;
+        for (size_t b = 0; b < B; ++b) any_right_neg |= bool(d.right_neg[b]);
         if (d.unit_sigma) plan_matrep(d, coeff);
+        if (any_right_neg && !(d.mr.ok && !(opt.variant & 8192))) return false;  // only the matrix path takes per-blade signs
         dense = d;
         return true;
     }
@@ -1088,57 +1117,45 @@ struct Gen {
     // product costs 8 multiplications instead of 16; a factor with x^2 = y^2 = -1 is the quaternions.  Every
     // basis element of the tensor product is +- one blade (a signed permutation of the 64 components), the
     // change to matrix units is one add / subtract per component and factor, and the 4 096-term product
-    // becomes  2 x 128 (operand transforms) + 8 x 16 x 8 = 1 024 FMAs + 128 + 64 (result transform, scaling)
-    // = 1 472 FP64 operations: G(6,0) = M_2(R) (x) H (x) M_2(R) = M_4(H).  The generator order is searched so
-    // that factors 0 and 2 are M_2(R) (the middle factor is multiplied out in full, whatever its type).
-    // The tables are derived from the plan's own coefficient table and the scheme is checked numerically
-    // against that table before it is used (variant bit 17 switches it off: the 4 096-FMA rolled product).
-    // A different summation order and 5 roundings per component more than the reference: FMA arithmetic only.
+    // becomes, with two factors in matrix form,  2 x 128 (operand transforms) + 8 x 16 x 8 = 1 024 FMAs + 128 + 64
+    // (result transform, scaling) = 1 472 FP64 operations: G(6,0) = M_2(R) (x) H (x) M_2(R) = M_4(H).  The generator
+    // order is searched for the most M_2(R) factors; one factor is always multiplied out in full (its output index
+    // labels the accumulator groups), so at most two are taken in matrix form (G(0,6) = H (x) M_2(R) (x) H has one:
+    // 2 048 FMAs).  The tables are derived from the plan's own coefficient table and the scheme is checked
+    // numerically against that table before it is used (variant bit 17 switches it off: the 4 096-FMA rolled product).
+    // A different summation order and a few roundings per component more than the reference: FMA arithmetic only.
     using MatRep = Dense::MatRep;
     static void matrep_apply(const MatRep& m, const double* A, const double* Bv, double* C) {
-        double a2[64], b2[64], c2[64] = {};
-        auto fwd = [&](const double* in, double* out) {
-            double t[64], u[64];
-            for (int tau = 0; tau < 64; ++tau) t[tau] = m.tau_sign[tau] * in[m.tau_blade[tau]];
-            for (int k1 = 0; k1 < 4; ++k1)
-                for (int k2 = 0; k2 < 4; ++k2)
-                    for (int e0 = 0; e0 < 4; ++e0) {
-                        double v = 0;
-                        for (int k0 = 0; k0 < 4; ++k0) v += m.F[0][e0][k0] * t[k0 + 4 * k1 + 16 * k2];
-                        u[e0 + 4 * k1 + 16 * k2] = v;
-                    }
-            for (int e0 = 0; e0 < 4; ++e0)
-                for (int k1 = 0; k1 < 4; ++k1)
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        double v = 0;
-                        for (int k2 = 0; k2 < 4; ++k2) v += m.F[2][e2][k2] * u[e0 + 4 * k1 + 16 * k2];
-                        out[e0 + 4 * k1 + 16 * e2] = v;
-                    }
-        };
-        fwd(A, a2);
-        fwd(Bv, b2);
-        for (int p = 0; p < 4; ++p)
-            for (int q = 0; q < 4; ++q) {
-                const int k1 = m.s1_k[p][q];
-                const double sg = m.s1_sign[p][q];
-                for (int i0 = 0; i0 < 2; ++i0)
-                    for (int j0 = 0; j0 < 2; ++j0)
-                        for (int l0 = 0; l0 < 2; ++l0)
-                            for (int i2 = 0; i2 < 2; ++i2)
-                                for (int j2 = 0; j2 < 2; ++j2)
-                                    for (int l2 = 0; l2 < 2; ++l2)
-                                        c2[(2 * i0 + l0) + 4 * k1 + 16 * (2 * i2 + l2)] +=
-                                            sg * a2[(2 * i0 + j0) + 4 * p + 16 * (2 * i2 + j2)] * b2[(2 * j0 + l0) + 4 * q + 16 * (2 * j2 + l2)];
-            }
-        for (int k0 = 0; k0 < 4; ++k0)
-            for (int k1 = 0; k1 < 4; ++k1)
-                for (int k2 = 0; k2 < 4; ++k2) {
-                    double v = 0;
-                    for (int e0 = 0; e0 < 4; ++e0)
-                        for (int e2 = 0; e2 < 4; ++e2) v += m.F[0][e0][k0] * m.F[2][e2][k2] * c2[e0 + 4 * k1 + 16 * e2];
-                    const int tau = k0 + 4 * k1 + 16 * k2;
-                    C[m.tau_blade[tau]] = 0.25 * m.tau_sign[tau] * v;
+        auto along = [&](double* v, int j, bool transpose) {  // apply F[j] (or its transpose) along axis j
+            const int stride = j == 0 ? 1 : j == 1 ? 4 : 16;
+            double out[64];
+            for (int base = 0; base < 64; ++base) {
+                if ((base / stride) % 4) continue;
+                for (int e = 0; e < 4; ++e) {
+                    double acc = 0;
+                    for (int k = 0; k < 4; ++k) acc += (transpose ? m.F[j][k][e] : m.F[j][e][k]) * v[base + k * stride];
+                    out[base + e * stride] = acc;
                 }
+            }
+            for (int i = 0; i < 64; ++i) v[i] = out[i];
+        };
+        double a2[64], b2[64], c2[64] = {};
+        for (int tau = 0; tau < 64; ++tau) {
+            a2[tau] = m.tau_sign[tau] * A[m.tau_blade[tau]];
+            b2[tau] = m.tau_sign[tau] * Bv[m.tau_blade[tau]];
+        }
+        for (int j = 0; j < 3; ++j) { along(a2, j, false); along(b2, j, false); }
+        for (const auto& t0 : m.tri[0])
+            for (const auto& t1 : m.tri[1])
+                for (const auto& t2 : m.tri[2])
+                    c2[t0.out + 4 * t1.out + 16 * t2.out] +=
+                        t0.sign * t1.sign * t2.sign * a2[t0.a + 4 * t1.a + 16 * t2.a] * b2[t0.b + 4 * t1.b + 16 * t2.b];
+        double scale = 1.0;
+        for (int j = 0; j < 3; ++j) {
+            along(c2, j, true);
+            if (m.fast[j]) scale *= 0.5;
+        }
+        for (int tau = 0; tau < 64; ++tau) C[m.tau_blade[tau]] = scale * m.tau_sign[tau] * c2[tau];
     }
 
     bool plan_matrep(Dense& d, const std::vector<double>& coeff) const {
@@ -1149,6 +1166,8 @@ struct Gen {
         struct SB { int blade; int sign; };
         auto mul = [&](SB a, SB b) { return SB{a.blade ^ b.blade, a.sign * b.sign * (coeff[size_t(a.blade) * B + b.blade] < 0 ? -1 : 1)}; };
         int perm[6] = {0, 1, 2, 3, 4, 5};
+        MatRep best;
+        int best_fast = 0;
         do {
             MatRep m;
             SB basis[3][4];
@@ -1165,7 +1184,14 @@ struct Gen {
                 beta[j] = mul(y, y).sign;
                 omega = mul(mul(omega, g1), g2);
             }
-            if ((alpha[0] < 0 && beta[0] < 0) || (alpha[2] < 0 && beta[2] < 0)) continue;  // factors 0 and 2 must be M_2(R)
+            int n_fast = 0;
+            for (int j = 0; j < 3; ++j) {
+                m.fast[j] = alpha[j] > 0 || beta[j] > 0;
+                n_fast += m.fast[j];
+            }
+            if (n_fast == 3) { m.fast[1] = false; n_fast = 2; }  // one factor stays in full form: the accumulator groups
+            if (n_fast <= best_fast) continue;
+            m.group = !m.fast[1] ? 1 : !m.fast[0] ? 0 : 2;
             // tensor basis -> signed blade (must be a bijection)
             bool seen[64] = {};
             bool ok = true;
@@ -1179,38 +1205,42 @@ struct Gen {
                         m.tau_sign[k0 + 4 * k1 + 16 * k2] = t.sign;
                     }
             if (!ok) continue;
-            // 2 x 2 real representations of the fast factors
-            for (int j : {0, 2}) {
-                int X[4], Y[4];  // row-major 2 x 2
-                if (alpha[j] > 0) {
-                    X[0] = 1; X[1] = 0; X[2] = 0; X[3] = -1;
-                    Y[0] = 0; Y[1] = 1; Y[2] = beta[j]; Y[3] = 0;
+            for (int j = 0; j < 3 && ok; ++j) {
+                for (int e = 0; e < 4; ++e)
+                    for (int k = 0; k < 4; ++k) m.F[j][e][k] = e == k;
+                if (m.fast[j]) {
+                    // 2 x 2 real representation: a generator of square +1 is diag(1, -1), the other one off-diagonal
+                    int X[4], Y[4];  // row-major
+                    if (alpha[j] > 0) {
+                        X[0] = 1; X[1] = 0; X[2] = 0; X[3] = -1;
+                        Y[0] = 0; Y[1] = 1; Y[2] = beta[j]; Y[3] = 0;
+                    } else {
+                        Y[0] = 1; Y[1] = 0; Y[2] = 0; Y[3] = -1;
+                        X[0] = 0; X[1] = 1; X[2] = alpha[j]; X[3] = 0;
+                    }
+                    const int XY[4] = {X[0] * Y[0] + X[1] * Y[2], X[0] * Y[1] + X[1] * Y[3], X[2] * Y[0] + X[3] * Y[2], X[2] * Y[1] + X[3] * Y[3]};
+                    const int I2[4] = {1, 0, 0, 1};
+                    for (int e = 0; e < 4; ++e) {
+                        m.F[j][e][0] = I2[e];
+                        m.F[j][e][1] = X[e];
+                        m.F[j][e][2] = Y[e];
+                        m.F[j][e][3] = XY[e];
+                    }
+                    for (int i = 0; i < 2; ++i)  // C(i,l) += A(i,jj) B(jj,l)
+                        for (int jj = 0; jj < 2; ++jj)
+                            for (int l = 0; l < 2; ++l) m.tri[j].push_back({2 * i + l, 2 * i + jj, 2 * jj + l, 1});
                 } else {
-                    Y[0] = 1; Y[1] = 0; Y[2] = 0; Y[3] = -1;
-                    X[0] = 0; X[1] = 1; X[2] = alpha[j]; X[3] = 0;
-                }
-                const int XY[4] = {X[0] * Y[0] + X[1] * Y[2], X[0] * Y[1] + X[1] * Y[3], X[2] * Y[0] + X[3] * Y[2], X[2] * Y[1] + X[3] * Y[3]};
-                const int I[4] = {1, 0, 0, 1};
-                for (int e = 0; e < 4; ++e) {
-                    m.F[j][e][0] = I[e];
-                    m.F[j][e][1] = X[e];
-                    m.F[j][e][2] = Y[e];
-                    m.F[j][e][3] = XY[e];
+                    for (int pp = 0; pp < 4 && ok; ++pp)
+                        for (int q = 0; q < 4; ++q) {
+                            const SB r = mul(basis[j][pp], basis[j][q]);
+                            int k = -1;
+                            for (int c = 0; c < 4; ++c)
+                                if (basis[j][c].blade == r.blade) k = c;
+                            if (k < 0) { ok = false; break; }
+                            m.tri[j].push_back({k, pp, q, r.sign * basis[j][k].sign});
+                        }
                 }
             }
-            for (int e = 0; e < 4; ++e)
-                for (int k = 0; k < 4; ++k) m.F[1][e][k] = e == k;
-            // the middle factor's multiplication table
-            for (int pp = 0; pp < 4 && ok; ++pp)
-                for (int q = 0; q < 4; ++q) {
-                    const SB r = mul(basis[1][pp], basis[1][q]);
-                    int k = -1;
-                    for (int c = 0; c < 4; ++c)
-                        if (basis[1][c].blade == r.blade) k = c;
-                    if (k < 0) { ok = false; break; }
-                    m.s1_k[pp][q] = k;
-                    m.s1_sign[pp][q] = r.sign * basis[1][k].sign;
-                }
             if (!ok) continue;
             // numerical check of the whole scheme against the plan's own table
             double A[64], Bv[64], want[64] = {}, got[64];
@@ -1225,30 +1255,38 @@ struct Gen {
             matrep_apply(m, A, Bv, got);
             for (int i = 0; i < 64; ++i)
                 if (std::fabs(got[i] - want[i]) > 1e-9) ok = false;
+            if (tuning().codegen_debug)
+                std::fprintf(stderr, "[gaast codegen] matrep: order %d%d%d%d%d%d fast=%d%d%d check %s (got[0]=%g want[0]=%g)\n", perm[0], perm[1],
+                             perm[2], perm[3], perm[4], perm[5], int(m.fast[0]), int(m.fast[1]), int(m.fast[2]), ok ? "ok" : "FAILED", got[0], want[0]);
             if (!ok) continue;
             for (int i = 0; i < 6; ++i) m.perm[i] = perm[i];
+            m.n_fma = int(m.tri[0].size() * m.tri[1].size() * m.tri[2].size());
+            m.n_add = 64 * n_fast * 3 + 64;  // two operand transforms and the result's, one scaling per component
             m.ok = true;
-            d.mr = m;
-            return true;
+            best = m;
+            best_fast = n_fast;
+            if (best_fast == 2) break;
         } while (std::next_permutation(perm, perm + 6));
-        return false;
+        if (!best.ok) return false;
+        d.mr = best;
+        return true;
     }
 
-    // c1 * x1 + c2 * x2 with c in {+1, -1}: one add (negations are operand modifiers)
-    std::string pm(int c1, const std::string& x1, int c2, const std::string& x2) const {
-        const std::string a = c1 > 0 ? x1 : "d_neg(" + x1 + ")", b = c2 > 0 ? x2 : "d_neg(" + x2 + ")";
-        return "d_add(" + a + ", " + b + ")";
-    }
-    // the two nonzero entries of row e of F[j] (basis coefficient -> matrix entry), or of column k (the transpose)
-    void nz_row(const MatRep& m, int j, int e, int idx[2], int sg[2]) const {
-        int c = 0;
+    // A value of the matrix path under construction: an expression text and a pending sign (signs are free: they
+    // end up as operand modifiers of the add or FMA that consumes the value).
+    struct SV {
+        std::string text;
+        int sign = 1;
+    };
+    std::string sv_text(const SV& v, int extra = 1) const { return v.sign * extra < 0 ? "d_neg(" + v.text + ")" : v.text; }
+    // sum_k coef[k] * in[k] over the nonzero coefficients (one or two of them): an alias, or one add
+    SV sv_combine(const std::string& name, const int coef[4], const SV in[4]) {
+        int idx[4], c = 0;
         for (int k = 0; k < 4; ++k)
-            if (m.F[j][e][k]) { idx[c] = k; sg[c] = m.F[j][e][k]; ++c; }
-    }
-    void nz_col(const MatRep& m, int j, int k, int idx[2], int sg[2]) const {
-        int c = 0;
-        for (int e = 0; e < 4; ++e)
-            if (m.F[j][e][k]) { idx[c] = e; sg[c] = m.F[j][e][k]; ++c; }
+            if (coef[k]) idx[c++] = k;
+        if (c == 1) return SV{in[idx[0]].text, in[idx[0]].sign * coef[idx[0]]};
+        line("const " + S + " " + name + " = d_add(" + sv_text(in[idx[0]], coef[idx[0]]) + ", " + sv_text(in[idx[1]], coef[idx[1]]) + ");");
+        return SV{name, 1};
     }
 
     void emit_op_dense_matrep(int op) {
@@ -1257,103 +1295,100 @@ struct Gen {
         std::vector<std::pair<size_t, uint32_t>> col_at;
         for (size_t si = h.n_in_streams; si < h.streams.size(); ++si)
             for (uint32_t r = 0; r < h.streams[si].rows; ++r) col_at.push_back({si, r});
-        auto T = [](int k0, int k1, int k2) { return k0 + 4 * k1 + 16 * k2; };
-        // shared-memory row of the right operand's component: before the transform the row of its blade, after it the
-        // same 64 rows re-labelled by (e0, k1, e2)
-        auto srow = [&](int i0, int k1, int i2) {
-            return "xs_ld<" + std::to_string(size_t(nodes[d.right[m.tau_blade[T(i0, k1, i2)]]].smem_row) * esize) + " * GAAST_THREADS>(xb)";
+        const int g = m.group, ja = g == 0 ? 1 : 0, jb = g == 2 ? 1 : 2;  // the group factor and the two others (ja < jb)
+        const int st[3] = {1, 4, 16};
+        auto T = [&](int kg, int ka, int kb) { return kg * st[g] + ka * st[ja] + kb * st[jb]; };
+        auto smem_off = [&](int tau) { return std::to_string(size_t(nodes[d.right[m.tau_blade[tau]]].smem_row) * esize) + " * GAAST_THREADS"; };
+        auto tag = [](int a, int b) { return std::to_string(a) + "_" + std::to_string(b); };
+        // transforms a 4 x 4 block (ka, kb) along both axes; `out[ea][eb]`
+        auto transform = [&](const std::string& prefix, SV in[4][4], SV out[4][4], bool transpose) {
+            SV mid[4][4];
+            for (int kb = 0; kb < 4; ++kb)
+                for (int ea = 0; ea < 4; ++ea) {
+                    int coef[4];
+                    SV col[4];
+                    for (int ka = 0; ka < 4; ++ka) { coef[ka] = transpose ? m.F[ja][ka][ea] : m.F[ja][ea][ka]; col[ka] = in[ka][kb]; }
+                    mid[ea][kb] = sv_combine(prefix + "u" + tag(ea, kb), coef, col);
+                }
+            for (int ea = 0; ea < 4; ++ea)
+                for (int eb = 0; eb < 4; ++eb) {
+                    int coef[4];
+                    SV row[4];
+                    for (int kb = 0; kb < 4; ++kb) { coef[kb] = transpose ? m.F[jb][kb][eb] : m.F[jb][eb][kb]; row[kb] = mid[ea][kb]; }
+                    out[ea][eb] = sv_combine(prefix + "w" + tag(ea, eb), coef, row);
+                }
         };
-        auto srow_st = [&](int i0, int k1, int i2, const std::string& v) {
-            return "xs_st<" + std::to_string(size_t(nodes[d.right[m.tau_blade[T(i0, k1, i2)]]].smem_row) * esize) + " * GAAST_THREADS>(xb, " + v + ");";
-        };
-        int idx[2], sg[2];
-        // ---- right operand: signed permutation + the two fast transforms, in place in shared memory ----
-        for (int k1 = 0; k1 < 4; ++k1) {
+        // ---- right operand: signed permutation + the fast transforms, in place in shared memory, one group index at a time ----
+        for (int kg = 0; kg < 4; ++kg) {
             line("{");
             ++indent;
-            for (int k2 = 0; k2 < 4; ++k2)
-                for (int k0 = 0; k0 < 4; ++k0) line("const " + S + " r" + std::to_string(k0) + "_" + std::to_string(k2) + " = " + srow(k0, k1, k2) + ";");
-            for (int k2 = 0; k2 < 4; ++k2)
-                for (int e0 = 0; e0 < 4; ++e0) {
-                    nz_row(m, 0, e0, idx, sg);
-                    line("const " + S + " u" + std::to_string(e0) + "_" + std::to_string(k2) + " = " +
-                         pm(sg[0] * m.tau_sign[T(idx[0], k1, k2)], "r" + std::to_string(idx[0]) + "_" + std::to_string(k2),
-                            sg[1] * m.tau_sign[T(idx[1], k1, k2)], "r" + std::to_string(idx[1]) + "_" + std::to_string(k2)) + ";");
+            SV in[4][4], out[4][4];
+            for (int kb = 0; kb < 4; ++kb)
+                for (int ka = 0; ka < 4; ++ka) {
+                    const int tau = T(kg, ka, kb);
+                    line("const " + S + " r" + tag(ka, kb) + " = xs_ld<" + smem_off(tau) + ">(xb);");
+                    in[ka][kb] = SV{"r" + tag(ka, kb), m.tau_sign[tau] * (d.right_neg[size_t(m.tau_blade[tau])] ? -1 : 1)};
                 }
-            for (int e0 = 0; e0 < 4; ++e0)
-                for (int e2 = 0; e2 < 4; ++e2) {
-                    nz_row(m, 2, e2, idx, sg);
-                    line(srow_st(e0, k1, e2, pm(sg[0], "u" + std::to_string(e0) + "_" + std::to_string(idx[0]), sg[1],
-                                                "u" + std::to_string(e0) + "_" + std::to_string(idx[1]))));
-                }
+            transform("", in, out, false);
+            for (int ea = 0; ea < 4; ++ea)
+                for (int eb = 0; eb < 4; ++eb) line("xs_st<" + smem_off(T(kg, ea, eb)) + ">(xb, " + sv_text(out[ea][eb]) + ");");
             --indent;
             line("}");
         }
         // ---- left operand: the same transforms in registers ----
         for (int a = 0; a < 64; ++a) emit(d.left[a].id);
-        auto am = [](int e0, int k1, int e2) { return "am" + std::to_string(e0) + "_" + std::to_string(k1) + "_" + std::to_string(e2); };
-        for (int k1 = 0; k1 < 4; ++k1) {
-            for (int k2 = 0; k2 < 4; ++k2)
-                for (int e0 = 0; e0 < 4; ++e0) {
-                    nz_row(m, 0, e0, idx, sg);
-                    const Ref x0 = d.left[m.tau_blade[T(idx[0], k1, k2)]], x1 = d.left[m.tau_blade[T(idx[1], k1, k2)]];
-                    line("const " + S + " au" + std::to_string(e0) + "_" + std::to_string(k1) + "_" + std::to_string(k2) + " = d_add(" +
-                         opnd(x0, true, sg[0] * m.tau_sign[T(idx[0], k1, k2)] < 0) + ", " +
-                         opnd(x1, true, sg[1] * m.tau_sign[T(idx[1], k1, k2)] < 0) + ");");
+        SV am[4][4][4];  // [kg][ea][eb]
+        for (int kg = 0; kg < 4; ++kg) {
+            SV in[4][4];
+            for (int kb = 0; kb < 4; ++kb)
+                for (int ka = 0; ka < 4; ++ka) {
+                    const int tau = T(kg, ka, kb);
+                    const Ref x = d.left[size_t(m.tau_blade[tau])];
+                    in[ka][kb] = SV{opnd(Ref{x.id, false}, true), m.tau_sign[tau] * (x.neg ? -1 : 1)};
                 }
-            for (int e0 = 0; e0 < 4; ++e0)
-                for (int e2 = 0; e2 < 4; ++e2) {
-                    nz_row(m, 2, e2, idx, sg);
-                    line("const " + S + " " + am(e0, k1, e2) + " = " +
-                         pm(sg[0], "au" + std::to_string(e0) + "_" + std::to_string(k1) + "_" + std::to_string(idx[0]), sg[1],
-                            "au" + std::to_string(e0) + "_" + std::to_string(k1) + "_" + std::to_string(idx[1])) + ";");
-                }
+            transform("a" + std::to_string(kg), in, am[kg], false);
         }
-        // ---- C''[(i0,l0)][k1][(i2,l2)] = sum_{p q -> k1} s sum_{j0 j2} A''[(i0,j0)][p][(i2,j2)] B''[(j0,l0)][q][(j2,l2)] ----
+        // ---- the product: per output index of the group factor, 16 accumulators over the two other factors ----
         int bcount = 0;
-        for (int k1 = 0; k1 < 4; ++k1) {
+        for (int og = 0; og < 4; ++og) {
             line("{");
             ++indent;
-            bool started[16] = {};
-            for (int c = 0; c < 16; ++c) line(S + " c" + std::to_string(c) + ";");
-            for (int p = 0; p < 4; ++p) {
-                int q = -1;
-                for (int qq = 0; qq < 4; ++qq)
-                    if (m.s1_k[p][qq] == k1) q = qq;
-                const bool neg = m.s1_sign[p][q] < 0;
-                for (int j0 = 0; j0 < 2; ++j0)
-                    for (int l0 = 0; l0 < 2; ++l0)
-                        for (int j2 = 0; j2 < 2; ++j2)
-                            for (int l2 = 0; l2 < 2; ++l2) {
-                                // right-operand-major: the 4 FMAs that share one value fresh from shared memory are consecutive
-                                const std::string b = "b" + std::to_string(bcount++);
-                                line("const " + S + " " + b + " = " + srow(2 * j0 + l0, q, 2 * j2 + l2) + ";");
-                                for (int i0 = 0; i0 < 2; ++i0)
-                                    for (int i2 = 0; i2 < 2; ++i2) {
-                                        const int ci = (2 * i0 + l0) + 4 * (2 * i2 + l2);
-                                        const std::string c = "c" + std::to_string(ci);
-                                        const std::string A = std::string(neg ? "d_neg(" : "") + am(2 * i0 + j0, p, 2 * i2 + j2) + (neg ? ")" : "");
-                                        if (!started[ci]) line(c + " = d_mul(" + A + ", " + b + ");");
-                                        else line(c + " = d_fma(" + A + ", " + b + ", " + c + ");");
-                                        started[ci] = true;
-                                    }
+            bool started[4][4] = {};
+            for (int c = 0; c < 16; ++c) line(S + " c" + tag(c / 4, c % 4) + ";");
+            for (const auto& tg : m.tri[g]) {
+                if (tg.out != og) continue;
+                for (int ba = 0; ba < 4; ++ba)
+                    for (int bb = 0; bb < 4; ++bb) {
+                        // right-operand-major: the FMAs that share one value fresh from shared memory are consecutive
+                        const std::string b = "b" + std::to_string(bcount++);
+                        line("const " + S + " " + b + " = xs_ld<" + smem_off(T(tg.b, ba, bb)) + ">(xb);");
+                        for (const auto& ta : m.tri[ja]) {
+                            if (ta.b != ba) continue;
+                            for (const auto& tb : m.tri[jb]) {
+                                if (tb.b != bb) continue;
+                                const std::string c = "c" + tag(ta.out, tb.out);
+                                const std::string A = sv_text(am[tg.a][ta.a][tb.a], tg.sign * ta.sign * tb.sign);
+                                if (!started[ta.out][tb.out]) line(c + " = d_mul(" + A + ", " + b + ");");
+                                else line(c + " = d_fma(" + A + ", " + b + ", " + c + ");");
+                                started[ta.out][tb.out] = true;
                             }
+                        }
+                    }
             }
-            // back to the tensor basis (the transposes of the two transforms, 1/4 overall), sign, store
-            for (int e2 = 0; e2 < 4; ++e2)
-                for (int k0 = 0; k0 < 4; ++k0) {
-                    nz_col(m, 0, k0, idx, sg);
-                    line("const " + S + " x" + std::to_string(k0) + "_" + std::to_string(e2) + " = " +
-                         pm(sg[0], "c" + std::to_string(idx[0] + 4 * e2), sg[1], "c" + std::to_string(idx[1] + 4 * e2)) + ";");
-                }
-            for (int k0 = 0; k0 < 4; ++k0)
-                for (int k2 = 0; k2 < 4; ++k2) {
-                    nz_col(m, 2, k2, idx, sg);
-                    const int tau = T(k0, k1, k2);
-                    const auto at = col_at[size_t(d.out_col[m.tau_blade[tau]])];
-                    const std::string v = "d_mul(U(" + std::string(m.tau_sign[tau] < 0 ? "-0.25" : "0.25") + "), " +
-                                          pm(sg[0], "x" + std::to_string(k0) + "_" + std::to_string(idx[0]), sg[1],
-                                             "x" + std::to_string(k0) + "_" + std::to_string(idx[1])) + ")";
+            // back to the tensor basis (the transposed transforms, 1/2 per matrix-form factor), sign, store
+            SV cin[4][4], cout[4][4];
+            for (int ea = 0; ea < 4; ++ea)
+                for (int eb = 0; eb < 4; ++eb) cin[ea][eb] = SV{"c" + tag(ea, eb), 1};
+            transform("o", cin, cout, true);
+            double scale = 1.0;
+            for (int j = 0; j < 3; ++j)
+                if (m.fast[j]) scale *= 0.5;
+            for (int ka = 0; ka < 4; ++ka)
+                for (int kb = 0; kb < 4; ++kb) {
+                    const int tau = T(og, ka, kb);
+                    const auto at = col_at[size_t(d.out_col[size_t(m.tau_blade[tau])])];
+                    const double f = scale * m.tau_sign[tau] * cout[ka][kb].sign;
+                    const std::string v = f == 1.0 ? cout[ka][kb].text : "d_mul(U(" + lit(f) + "), " + cout[ka][kb].text + ")";
                     if (opt.store_out)
                         line("d_store(s" + std::to_string(at.first) + " + " + std::to_string(at.second) + " * r" + std::to_string(at.first) + " + e, " + v + ");");
                 }
@@ -1984,9 +2019,9 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     res.parkable = res_parkable;
     for (const Node& n : g.nodes) res.fma_per_elem += n.live && n.k == N_ACC && !n.uniform;
     if (g.dense.op >= 0 && g.dense.mr.ok && !g.dense_tmem) {
-        // the matrix-representation product executes 1 024 FMAs + 448 additions / scalings for the op's 4 096 terms:
+        // the matrix-representation product executes 1 024 (2 048) FMAs + 448 (256) additions / scalings for the op's 4 096 terms:
         // reported as flop / 2, so that 2 x fma/elem stays the executed flop count
-        res.fma_per_elem += (2 * 1024 + 448) / 2 - 4096;
+        res.fma_per_elem += (2 * g.dense.mr.n_fma + g.dense.mr.n_add) / 2 - 4096;
     }
 
     std::ostringstream src;

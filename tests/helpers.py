@@ -148,3 +148,39 @@ def run_plan_numpy(plan: Dict, inputs: Sequence[Dict[int, np.ndarray]], batch: i
         out[k] = bufs[0][c:c + gd[k]]
         c += gd[k]
     return out
+
+
+# ---- the sum-of-|terms| scale of a plan, evaluated by the library itself ------------------------
+class AbsPlanAst:
+    """A stand-in for gaast_b200.expr.SpecializedAst whose lower() returns a copy of `ast`'s flat plan
+    with every term coefficient replaced by its absolute value and every sign flip dropped.  Evaluated
+    in strict arithmetic on |inputs| it yields, per root component, the sum of |l * r * coeff| over the
+    reference's terms (products of sums of magnitudes for nested products): the scale SURVEY.md 8d
+    measures the tolerance against, computed on the device so that EVERY element of a full BASELINE
+    batch can be checked.  (1/x is applied to the magnitude sum, as oracle_abs_scale does.)"""
+
+    def __init__(self, ast):
+        import ctypes as C
+        from gaast_b200 import _lib as L
+        src = ast.lower().contents
+        self._keep = ast
+        self._masks = (L.u32 * max(1, src.n_buffers))(*[src.buffer_masks[i] for i in range(src.n_buffers)])
+        self._inputs = (L.InputDesc * max(1, src.n_inputs))()
+        for i in range(src.n_inputs):
+            self._inputs[i] = src.inputs[i]
+        self._consts = (C.c_double * max(1, src.n_const_values))(*[abs(src.const_values[i]) for i in range(src.n_const_values)])
+        self._ops = (L.Op * max(1, src.n_ops))()
+        for i in range(src.n_ops):
+            o = src.ops[i]
+            self._ops[i] = L.Op(o.kind, o.dst, o.a, o.b, 0 if o.kind == L.OP_NEG_GRADES else o.mask, o.term_begin,
+                                o.term_count, 0)
+        self._terms = (L.Term * max(1, src.n_terms))()
+        for i in range(src.n_terms):
+            t = src.terms[i]
+            self._terms[i] = L.Term(t.out, t.a, t.b, 0, abs(t.coeff))
+        self._desc = L.PlanDesc(src.n, src.n_buffers, self._masks, src.n_inputs, self._inputs, src.n_const_values,
+                                self._consts, src.n_ops, self._ops, src.n_terms, self._terms, src.n_slots, 0)
+
+    def lower(self):
+        import ctypes as C
+        return C.pointer(self._desc)

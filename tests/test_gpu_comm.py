@@ -66,3 +66,28 @@ def test_comm_sharded_batch_sum_two_devices():
     for plan, dev, out, b0, b1 in outs:  # and the per-element results are the slices of the whole
         np.testing.assert_allclose(out.to_host()[2], want[:, b0:b1], rtol=0, atol=1e-12 * np.abs(want).max())
     comm.close()
+
+
+def test_bench_cfg5_sharded_under_torchrun_two_ranks(tmp_path):
+    """bench.py --gpus 2 under torchrun (one process per GPU): the cfg5_sharded section shards ONE 32 M batch over
+    both ranks, joins the library's communicator with gaast_comm_create_rank and times gaast_eval_sum +
+    gaast_comm_allreduce_sum; the all-reduced vector must agree with torch.distributed."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "bench.py"),
+                        "--gpus", "2", "--steps", "2", "--warmup", "1", "--no-e2e"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().split("\n")[-1])
+    assert line["n_gpus"] == 2
+    sh = line["cfg5_sharded"]
+    assert sh["n_gpus"] == 2 and sh["scaling"] == "strong" and sh["sum_check"] is True, sh
+    assert sh["shard_elements"] * 2 == sh["batch_total"]
+    assert sh["speedup_vs_one_gpu_same_box"] > 1.5

@@ -261,6 +261,9 @@ LINEAR_SHAPES = {
 }
 
 
+LINEAR_TOL = {}  # shape -> tolerance above the 1e-12 bar, with the reason (none needed: see the test)
+
+
 @pytest.mark.parametrize("shape", sorted(LINEAR_SHAPES))
 @pytest.mark.parametrize("xgrades", [(1,), (0, 1, 2, 3, 4, 5)], ids=["X=vector", "X=full"])
 def test_shared_operand_lowering(ctx, shape, xgrades):
@@ -281,7 +284,7 @@ def test_shared_operand_lowering(ctx, shape, xgrades):
     dev = [g.DeviceBatch.from_host(ctx, n, host[0], broadcast=True), g.DeviceBatch.from_host(ctx, n, host[1])]
     out = plan.eval(dev, engine=L.ENGINE_SPECIALIZED, arith=L.ARITH_FMA)
     ctx.sync()
-    assert_close(out.to_host(), want, scale, rel=4e-12, what=f"{shape} fma")
+    assert_close(out.to_host(), want, scale, rel=LINEAR_TOL.get(shape, 1e-12), what=f"{shape} fma")
     out = plan.eval(dev, engine=L.ENGINE_SPECIALIZED, arith=L.ARITH_STRICT)
     ctx.sync()
     assert_bit_exact(out.to_host(), want, f"{shape} strict")
