@@ -360,7 +360,7 @@ def timed(res, steps, warmup, torch, dist, world, allow_graph=True):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # per repetition, the slowest rank
     ms = [float(x) for x in ms.tolist()]
-    return {"ms_per_step": statistics.median(ms) / steps, "ms_per_step_min": min(ms) / steps,
+    return {"ms_per_step": statistics.median(ms) / steps, "ms_per_step_min": min(ms) / steps, "ms_per_step_first_rep": ms[0] / steps,
             "ms_per_step_max": max(ms) / steps, "reps": reps, "timed_region_s": sum(ms) / 1e3,
             "launches": launches, "cuda_graph": graph is not None}
 
@@ -441,6 +441,9 @@ def _workload_record(res, t, peak_gbs, w):
     traffic, traffic_src = _ncu_traffic(kernel, n) if not res.f32 else (None, "no capture of the f32 kernels")
     rec = {"elements_per_s": n / s, "products_per_s": n / s * w.products, "ms_per_step": t["ms_per_step"],
            "ms_per_step_min": t["ms_per_step_min"], "ms_per_step_max": t["ms_per_step_max"],
+           # the first repetition starts on a GPU that has idled through the set-up: the burst figure, before the
+           # 1 kW power cap pulls the SM clock down (tools/power_probe.py); the median is the sustained one
+           "ms_per_step_first_rep": t["ms_per_step_first_rep"],
            "timed_reps": t["reps"], "timed_region_s": t["timed_region_s"],
            "hbm_gbs": n * res.bytes_per_elem / s / 1e9, "hbm_frac": n * res.bytes_per_elem / s / 1e9 / peak_gbs,
            "fp64_tflops": n * res.flops_per_elem / s / 1e12,
@@ -681,6 +684,20 @@ def run_gpu(args):
                                            "elements": e["elements"], "h2d_bytes_per_step": e["h2d"],
                                            "d2h_bytes_per_step": e["d2h"], "ms_per_step": e["ms_per_step"],
                                            "matches_resident": e["matches_resident"]}
+                del r
+            except Exception as ex:
+                others[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        # the same two workloads with their algebraic lowering switched off (code generator variant bits 17 / 16): the
+        # reference's own term count executed FMA by FMA -- what the lowered kernels above are to be compared with
+        for name, base, variant, what in (("cfg3_unlowered", "cfg3", 131072, "rolled 4 096-FMA dense product (no matrix representation)"),
+                                          ("cfg5_unlowered", "cfg5", 65536, "1 608-FMA sandwich through the 232-component intermediate (no reflection lowering)")):
+            try:
+                torch.cuda.empty_cache()
+                ow = W.WORKLOADS[base]
+                r = Resident(ctx, ow, torch, tuning=(0, variant))
+                tt = timed(r, args.steps, args.warmup, torch, dist, 1)
+                others[name] = _workload_record(r, tt, peak_gbs, ow)
+                others[name]["what"] = what
                 del r
             except Exception as ex:
                 others[name] = {"error": f"{type(ex).__name__}: {ex}"}

@@ -1104,7 +1104,7 @@ struct Gen {
         bool any_right_neg = false;
         for (size_t b = 0; b < B; ++b) any_right_neg |= bool(d.right_neg[b]);
         if (d.unit_sigma) plan_matrep(d, coeff);
-        if (any_right_neg && !(d.mr.ok && !(opt.variant & 8192))) return false;  // only the matrix path takes per-blade signs
+        if (any_right_neg && !d.mr.ok) return false;  // only the matrix path takes per-blade signs
         dense = d;
         return true;
     }
@@ -1319,6 +1319,7 @@ struct Gen {
                 }
         };
         // ---- right operand: signed permutation + the fast transforms, in place in shared memory, one group index at a time ----
+        auto right_operand = [&]() {
         for (int kg = 0; kg < 4; ++kg) {
             line("{");
             ++indent;
@@ -1335,10 +1336,15 @@ struct Gen {
             --indent;
             line("}");
         }
+        };
+        if (!dense_tmem) right_operand();  // (tensor-memory variant: the left operand first, its 128 registers die early)
         // ---- left operand: the same transforms in registers ----
+        // (variant bit 13: the transformed operand is then parked in the thread's tensor-memory lane, 16 components
+        // per tcgen05.st / tcgen05.ld, and the kernel needs ~110 registers instead of 250: 3 blocks per SM)
         for (int a = 0; a < 64; ++a) emit(d.left[a].id);
         SV am[4][4][4];  // [kg][ea][eb]
         for (int kg = 0; kg < 4; ++kg) {
+            if (dense_tmem) { line("{"); ++indent; }
             SV in[4][4];
             for (int kb = 0; kb < 4; ++kb)
                 for (int ka = 0; ka < 4; ++ka) {
@@ -1347,6 +1353,18 @@ struct Gen {
                     in[ka][kb] = SV{opnd(Ref{x.id, false}, true), m.tau_sign[tau] * (x.neg ? -1 : 1)};
                 }
             transform("a" + std::to_string(kg), in, am[kg], false);
+            if (dense_tmem) {
+                std::string args;
+                for (int ea = 0; ea < 4; ++ea)
+                    for (int eb = 0; eb < 4; ++eb) args += ", " + sv_text(am[kg][ea][eb]);
+                line("tm_put16(tb + " + std::to_string(32 * kg) + "u" + args + ");");
+                --indent;
+                line("}");
+            }
+        }
+        if (dense_tmem) {
+            line("tm_wait_st();");
+            right_operand();
         }
         // ---- the product: per output index of the group factor, 16 accumulators over the two other factors ----
         int bcount = 0;
@@ -1357,6 +1375,20 @@ struct Gen {
             for (int c = 0; c < 16; ++c) line(S + " c" + tag(c / 4, c % 4) + ";");
             for (const auto& tg : m.tri[g]) {
                 if (tg.out != og) continue;
+                SV aslice[4][4];
+                if (dense_tmem) {
+                    line("{");
+                    ++indent;
+                    std::string names;
+                    for (int c = 0; c < 16; ++c) names += std::string(c ? ", " : "") + "a" + std::to_string(c);
+                    line("double " + names + ";");
+                    line("tm_get16(tb + " + std::to_string(32 * tg.a) + "u, " + names + ");");
+                    for (int ea = 0; ea < 4; ++ea)
+                        for (int eb = 0; eb < 4; ++eb) aslice[ea][eb] = SV{"a" + std::to_string(4 * ea + eb), 1};
+                } else {
+                    for (int ea = 0; ea < 4; ++ea)
+                        for (int eb = 0; eb < 4; ++eb) aslice[ea][eb] = am[tg.a][ea][eb];
+                }
                 for (int ba = 0; ba < 4; ++ba)
                     for (int bb = 0; bb < 4; ++bb) {
                         // right-operand-major: the FMAs that share one value fresh from shared memory are consecutive
@@ -1367,13 +1399,14 @@ struct Gen {
                             for (const auto& tb : m.tri[jb]) {
                                 if (tb.b != bb) continue;
                                 const std::string c = "c" + tag(ta.out, tb.out);
-                                const std::string A = sv_text(am[tg.a][ta.a][tb.a], tg.sign * ta.sign * tb.sign);
+                                const std::string A = sv_text(aslice[ta.a][tb.a], tg.sign * ta.sign * tb.sign);
                                 if (!started[ta.out][tb.out]) line(c + " = d_mul(" + A + ", " + b + ");");
                                 else line(c + " = d_fma(" + A + ", " + b + ", " + c + ");");
                                 started[ta.out][tb.out] = true;
                             }
                         }
                     }
+                if (dense_tmem) { --indent; line("}"); }
             }
             // back to the tensor basis (the transposed transforms, 1/2 per matrix-form factor), sign, store
             SV cin[4][4], cout[4][4];
@@ -1390,7 +1423,8 @@ struct Gen {
                     const double f = scale * m.tau_sign[tau] * cout[ka][kb].sign;
                     const std::string v = f == 1.0 ? cout[ka][kb].text : "d_mul(U(" + lit(f) + "), " + cout[ka][kb].text + ")";
                     if (opt.store_out)
-                        line("d_store(s" + std::to_string(at.first) + " + " + std::to_string(at.second) + " * r" + std::to_string(at.first) + " + e, " + v + ");");
+                        line(std::string(guard_stores ? "if (active) " : "") + "d_store(s" + std::to_string(at.first) + " + " +
+                             std::to_string(at.second) + " * r" + std::to_string(at.first) + " + e, " + v + ");");
                 }
             --indent;
             line("}");
@@ -1401,7 +1435,7 @@ struct Gen {
 
     void emit_op_dense(int op) {
         const Dense& d = dense;
-        if (d.mr.ok && !dense_tmem) {
+        if (d.mr.ok) {
             emit_op_dense_matrep(op);
             return;
         }
@@ -2018,7 +2052,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     res.parked = res_parked;
     res.parkable = res_parkable;
     for (const Node& n : g.nodes) res.fma_per_elem += n.live && n.k == N_ACC && !n.uniform;
-    if (g.dense.op >= 0 && g.dense.mr.ok && !g.dense_tmem) {
+    if (g.dense.op >= 0 && g.dense.mr.ok) {
         // the matrix-representation product executes 1 024 (2 048) FMAs + 448 (256) additions / scalings for the op's 4 096 terms:
         // reported as flop / 2, so that 2 x fma/elem stays the executed flop count
         res.fma_per_elem += (2 * g.dense.mr.n_fma + g.dense.mr.n_add) / 2 - 4096;

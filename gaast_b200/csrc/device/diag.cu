@@ -42,17 +42,18 @@ extern "C" gaast_status gaast_diag_fp64_peak(gaast_ctx* ctx, double seconds, dou
                 if (prev >= 0 && prev != dev) cudaSetDevice(prev);
             }
         } restore{prev, ctx->device};
-        constexpr int kIlp = 8, kThreads = 1024, kIters = 4096;
+        constexpr int kIlp = 8, kThreads = 1024;
+        // one launch is ~5 ms at 37 TFLOP/s (a few launches per call: the launch list of a bench run stays readable)
+        const int kIters = seconds >= 0.1 ? 4096 * 20 : 4096;
         const int grid = ctx->sm_count * 2;
         double* d_out = nullptr;
         if (cudaMalloc(&d_out, 8) != cudaSuccess) throw gaast::Error(GAAST_ERR_OOM, "diag_fp64_peak: cudaMalloc");
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        const double flops_per_launch = 2.0 * grid * double(kThreads) * kIlp * kIters;
-        // one launch is ~0.27 ms at 37 TFLOP/s
-        for (int w = 0; w < 3; ++w) dfma_chain<kIlp><<<grid, kThreads, 0, ctx->stream>>>(d_out, 1.0000001, 1e-9, kIters);
-        const int reps = std::max(4, int(std::min(1e5, std::max(0.0, seconds) * 37e12 / flops_per_launch)));
+        const double flops_per_launch = 2.0 * grid * double(kThreads) * kIlp * double(kIters);
+        for (int w = 0; w < 2; ++w) dfma_chain<kIlp><<<grid, kThreads, 0, ctx->stream>>>(d_out, 1.0000001, 1e-9, 4096);
+        const int reps = std::max(2, int(std::min(1e5, std::max(0.0, seconds) * 37e12 / flops_per_launch)));
         cudaEventRecord(e0, ctx->stream);
         for (int r = 0; r < reps; ++r) dfma_chain<kIlp><<<grid, kThreads, 0, ctx->stream>>>(d_out, 1.0000001, 1e-9, kIters);
         cudaEventRecord(e1, ctx->stream);
@@ -62,7 +63,7 @@ extern "C" gaast_status gaast_diag_fp64_peak(gaast_ctx* ctx, double seconds, dou
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         cudaFree(d_out);
-        ctx->launches += uint64_t(reps) + 3;
+        ctx->launches += uint64_t(reps) + 2;
         if (e != cudaSuccess || ms <= 0) throw gaast::Error(GAAST_ERR_CUDA, std::string("diag_fp64_peak: ") + cudaGetErrorString(e));
         *tflops = flops_per_launch * reps / (double(ms) * 1e-3) / 1e12;
         return GAAST_OK;

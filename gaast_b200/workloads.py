@@ -236,4 +236,14 @@ def precompile_all(verbose: bool = False, fresh: bool = True) -> int:
                 print(f"  {w.name:10s} {'f32' if dtype else 'f64'} arith={'strict' if arith else 'fma':6s} sum={int(with_sum)} "
                       f"store={int(store)}: {info}")
         plan.free()
+    # bench.py also times cfg3 / cfg5 with their algebraic lowering switched off (variant bits 17 / 16)
+    for name, variant, with_sum in (("cfg3", 131072, False), ("cfg5", 65536, True)):
+        w = WORKLOADS[name]
+        plan = Plan(None, specialize(w))
+        plan.set_tuning(0, variant)
+        info = plan.precompile(w.broadcast_mask(), L.ARITH_FMA, with_sum, True, L.F64)
+        count += 1
+        if verbose:
+            print(f"  {name:10s} f64 arith=fma    sum={int(with_sum)} store=1 variant={variant}: {info}")
+        plan.free()
     return count
