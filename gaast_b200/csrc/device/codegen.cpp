@@ -2020,7 +2020,12 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2 * root_cols) tmem_cols *= 2;
     while (tmem_cols < 4 * root_cols && tmem_cols < 256) tmem_cols *= 2;
-    const bool tmem_sum = opt.with_sum && ept == 1 && !opt.pipelined && !(opt.variant & 32) && tmem_cols <= 256;
+    // Tensor memory pays when shared memory (MIO) is the busy resource, i.e. when input rows are parked there
+    // (round-1 cfg5: per-thread column sums in shared memory 10.0 ms, TMEM stash 8.35 ms).  A kernel without parked rows
+    // -- cfg5 after the reflection lowering -- has the LSU idle and keeps its column sums in shared memory: 5.92 ms
+    // against 5.98 ms with the stash (and 5.75 ms without any sum), at 64 blocks per resident slot.
+    const bool tmem_sum = opt.with_sum && ept == 1 && !opt.pipelined && !(opt.variant & 32) && tmem_cols <= 256 &&
+                          (n_smem_rows > 0 || (opt.variant & 262144));
     const size_t sum_doubles = g.dense.op >= 0 ? (size_t(1) << h.n)  // table of output offsets (dense excludes the sum)
                                : !opt.with_sum ? 0
                                : tmem_sum      ? ((threads / 32) * root_cols + 2 + 15) / 16 * 16

@@ -718,7 +718,9 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         if ((with_sum || jk->pipelined || gaast::tuning().force_persistent) && !jk->one_tile_blocks) {
             // persistent grid: the batch-sum epilogue keeps per-block partials, and the TMA-pipelined
             // kernels loop over their tiles; blocks stride over the batch
-            long long mult = jk->pipelined ? 1 : 16;  // sum-only kernels: many short-lived blocks overlap better
+            // sum-only kernels: many short-lived blocks overlap better (cfg5 + sum: 6.42 / 6.20 / 5.97 / 5.92 / 5.99 ms at
+            // 4 / 8 / 32 / 64 / 128 blocks per resident slot; the partials are 66 doubles per block)
+            long long mult = jk->pipelined ? 1 : 64;
             if (gaast::tuning().grid_mult > 0) mult = gaast::tuning().grid_mult;
             const long long cap = (long long)ctx->sm_count * jk->blocks_per_sm * mult;
             if (grid > cap) grid = int(cap);
