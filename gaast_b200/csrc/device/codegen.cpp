@@ -582,10 +582,18 @@ struct Gen {
                 }
                 res[o] = acc;
             }
+            // 2 (v _| X) w: the factor 2 goes into the contraction once per component (exact), so that every term
+            // below keeps a +-1 coefficient and stays ONE FMA
+            const Ref two = constant(2.0);
+            std::vector<char> doubled(U.size(), 0);
             for (uint32_t t = R.term_begin; t < R.term_begin + R.term_count; ++t) {
                 const gaast_term& tm = h.terms[t];
-                if (!touched[tm.out]) continue;
-                res[tm.out] = make_acc(res[tm.out], U[tm.a], buf[Wb][tm.b], 2.0 * tm.coeff, pseudo_op);  // 2 (v _| X) w
+                if (!touched[tm.out] || is_zero(U[tm.a])) continue;
+                if (!doubled[tm.a]) {
+                    U[tm.a] = make_acc(Ref{0, false}, U[tm.a], two, 1.0, pseudo_op);
+                    doubled[tm.a] = 1;
+                }
+                res[tm.out] = make_acc(res[tm.out], U[tm.a], buf[Wb][tm.b], tm.coeff, pseudo_op);
             }
             // every reader of the old chain ends (later ops on the same buffer, the root) now reads the new values
             std::map<int, Ref> replace;

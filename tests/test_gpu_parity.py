@@ -225,10 +225,9 @@ DENSE_METRICS = {
 @pytest.mark.parametrize("name", sorted(DENSE_METRICS))
 @pytest.mark.parametrize("shape", ["A*B", "A*B+C", "-(A*B)", "(A*B).g(2)", "A.rev()*B"])
 def test_dense_products_every_signature(ctx, name, shape):
-    """Full 64-component geometric products: the DENSE-ROLLED / BLOCKED policies (FMA
-    arithmetic) against the oracle, and strict arithmetic bit for bit."""
-    if shape != "A*B" and name not in ("G(6,0)", "G(3,3)"):
-        pytest.skip("shape variants are exercised on two signatures only (NVRTC time)")
+    """Full 64-component geometric products: the DENSE (matrix representation for +-1 metrics, rolled
+    otherwise) / BLOCKED policies (FMA arithmetic) against the oracle, and strict arithmetic bit for bit --
+    every shape on every metric, the degenerate and the non-unit one included."""
     metric = DENSE_METRICS[name]
     n = 6
     full = tuple(range(n + 1))
