@@ -113,6 +113,10 @@ PROTOTYPES = {
     "gaast_batch_wrap": (C.c_int, vp, u32, u32, u64, u64, C.c_int, C.POINTER(vp), C.POINTER(vp)),
     "gaast_batch_alloc_typed": (C.c_int, vp, u32, u32, u64, C.c_int, C.c_int, C.POINTER(vp)),
     "gaast_batch_wrap_typed": (C.c_int, vp, u32, u32, u64, u64, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp)),
+    "gaast_batch_alloc_sparse": (C.c_int, vp, u32, u32, u64, C.c_int, C.c_int, C.POINTER(C.POINTER(u64)), C.POINTER(vp)),
+    "gaast_batch_wrap_sparse": (C.c_int, vp, u32, u32, u64, u64, C.c_int, C.c_int, C.POINTER(C.POINTER(u64)),
+                                C.POINTER(vp), C.POINTER(vp)),
+    "gaast_batch_stored_rows": (u32, vp, u32),
     "gaast_batch_dtype": (C.c_int, vp),
     "gaast_batch_free": (C.c_int, vp),
     "gaast_batch_len": (u64, vp),

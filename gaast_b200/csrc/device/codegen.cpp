@@ -105,6 +105,16 @@ struct Gen {
     bool slot_broadcast(uint32_t slot) const { return (opt.broadcast_slots >> slot) & 1; }
 
     Ref load(int stream, uint32_t row) {
+        // sparse per-grade storage: a component the bound batch does not store is the constant zero (and every term
+        // that reads it is dropped below); a stored one is addressed by its rank among the stored rows
+        if (size_t(stream) < opt.sparse.size() && !opt.sparse[size_t(stream)].empty()) {
+            const auto& bits = opt.sparse[size_t(stream)];
+            if (!(bits[row / 64] >> (row % 64) & 1)) return Ref{0, false};
+            uint32_t rank = 0;
+            for (uint32_t w = 0; w < row / 64; ++w) rank += uint32_t(__builtin_popcountll(bits[w]));
+            rank += uint32_t(__builtin_popcountll(bits[row / 64] & ((1ull << (row % 64)) - 1)));
+            row = rank;
+        }
         auto key = std::make_pair(stream, row);
         auto it = loads.find(key);
         if (it != loads.end()) return Ref{it->second, false};

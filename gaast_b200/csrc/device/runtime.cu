@@ -75,7 +75,8 @@ void ensure(double*& p, size_t& cap, size_t want) {
 
 // Fills the stream table of EvalArgs and validates the bound batches.
 void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out, bool need_out,
-                  gaast::EvalArgs& a, uint64_t* broadcast_slots, long long* n_out, int* dtype_out) {
+                  gaast::EvalArgs& a, uint64_t* broadcast_slots, long long* n_out, int* dtype_out,
+                  std::vector<std::vector<uint64_t>>* sparse_out = nullptr, uint64_t* sparse_hash = nullptr) {
     const gaast::DevicePlanHost& h = plan->h;
     if (n_inputs != h.n_slots) throw Error(GAAST_ERR_SHAPE, "eval: the plan expects " + std::to_string(h.n_slots) + " input batches");
     if (h.n_slots && !inputs) throw Error(GAAST_ERR_INVALID, "eval: null inputs array");
@@ -91,6 +92,7 @@ void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_input
         if (out->mask != h.buffer_masks[0])
             throw Error(GAAST_ERR_SHAPE, "eval: output batch must carry exactly the root grade set");
         if (out->broadcast) throw Error(GAAST_ERR_SHAPE, "eval: output batch cannot be a broadcast operand");
+        if (out->sparse) throw Error(GAAST_ERR_SHAPE, "eval: the output batch must be dense (sparse storage is for inputs)");
         n = (long long)out->len;
     } else if (need_out) {
         throw Error(GAAST_ERR_INVALID, "eval: null output batch");
@@ -125,6 +127,13 @@ void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_input
             a.sptr[i] = b->grade_ptr[st.grade];
             a.srow[i] = (long long)b->stride;
             if (b->broadcast) a.bcast[i >> 6] |= 1ull << (i & 63);
+            if (sparse_out && !b->present[st.grade].empty()) {
+                if (sparse_out->empty()) sparse_out->resize(h.streams.size());
+                (*sparse_out)[i] = b->present[st.grade];
+                uint64_t hsh = 0x9E3779B97F4A7C15ull * (i + 1);
+                for (uint64_t w : b->present[st.grade]) hsh = (hsh ^ w) * 0xD6E8FEB86659FD93ull + 0x632BE59BD9B4E019ull;
+                *sparse_hash ^= hsh;
+            }
         }
     }
     // results are stored component by component while later components still read the inputs:
@@ -134,7 +143,8 @@ void bind_streams(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_input
         const char* oe = ob + size_t(h.streams[o].rows) * size_t(a.srow[o]) * esize;
         for (size_t i = 0; i < h.n_in_streams; ++i) {
             const char* ib = reinterpret_cast<const char*>(a.sptr[i]);
-            const char* ie = ib + size_t(h.streams[i].rows) * size_t(a.srow[i]) * esize;
+            const gaast_batch* ibatch = inputs[h.streams[i].slot];
+            const char* ie = ib + size_t(ibatch->stored[h.streams[i].grade]) * size_t(a.srow[i]) * esize;
             if (ob < ie && ib < oe) throw Error(GAAST_ERR_INVALID, "eval: the output batch overlaps an input batch");
         }
     }
@@ -351,7 +361,8 @@ gaast_status gaast_plan_precompile_typed(gaast_plan* plan, uint64_t broadcast_sl
 
 // --------------------------------------------------------------- batch ----
 static gaast_status batch_make(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
-                               int broadcast, int dtype, void* const* grade_ptrs, gaast_batch** out) {
+                               int broadcast, int dtype, void* const* grade_ptrs, gaast_batch** out,
+                               const uint64_t* const* present = nullptr) {
     return guard([&] {
         if (!out) throw Error(GAAST_ERR_INVALID, "null output pointer");
         *out = nullptr;
@@ -369,7 +380,26 @@ static gaast_status batch_make(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, 
         b->mask = grade_mask;
         b->len = len;
         b->broadcast = broadcast != 0;
-        b->rows = rows_of(n, grade_mask);
+        b->rows = 0;
+        {
+            uint32_t gi = 0;
+            for (uint32_t k = 0; k <= n; ++k) {
+                if (!(grade_mask >> k & 1)) continue;
+                const uint32_t full = uint32_t(gaast::binomial(n, k));
+                b->stored[k] = full;
+                if (present && present[gi]) {
+                    const size_t words = (full + 63) / 64;
+                    b->present[k].assign(present[gi], present[gi] + words);
+                    if (full % 64) b->present[k].back() &= (~0ull) >> (64 - full % 64);
+                    uint32_t cnt = 0;
+                    for (uint64_t w : b->present[k]) cnt += uint32_t(__builtin_popcountll(w));
+                    if (cnt == full) b->present[k].clear();  // every component stored: a dense grade
+                    else { b->stored[k] = cnt; b->sparse = true; }
+                }
+                b->rows += b->stored[k];
+                ++gi;
+            }
+        }
         DeviceGuard dg(ctx->device);
         if (grade_ptrs) {
             if (stride < len) throw Error(GAAST_ERR_INVALID, "stride smaller than the batch length");
@@ -377,7 +407,7 @@ static gaast_status batch_make(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, 
             uint32_t i = 0;
             for (uint32_t k = 0; k <= n; ++k)
                 if (grade_mask >> k & 1) {
-                    if (!grade_ptrs[i] && len) throw Error(GAAST_ERR_INVALID, "null grade pointer");
+                    if (!grade_ptrs[i] && len && b->stored[k]) throw Error(GAAST_ERR_INVALID, "null grade pointer");
                     b->grade_ptr[k] = static_cast<double*>(grade_ptrs[i++]);
                 }
         } else {
@@ -392,7 +422,7 @@ static gaast_status batch_make(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, 
             for (uint32_t k = 0; k <= n; ++k)
                 if (grade_mask >> k & 1) {
                     b->grade_ptr[k] = reinterpret_cast<double*>(reinterpret_cast<char*>(b->base) + row * b->stride * es);
-                    row += gaast::binomial(n, k);
+                    row += b->stored[k];
                 }
         }
         *out = b.release();
@@ -427,6 +457,30 @@ gaast_status gaast_batch_wrap_typed(gaast_ctx* ctx, uint32_t n, uint32_t grade_m
     return batch_make(ctx, n, grade_mask, len, stride, broadcast, dtype, grade_ptrs, out);
 }
 
+gaast_status gaast_batch_alloc_sparse(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, int broadcast,
+                                      int dtype, const uint64_t* const* present, gaast_batch** out) {
+    if (!present) {
+        gaast::set_last_error("null presence-bitmap array");
+        return GAAST_ERR_INVALID;
+    }
+    return batch_make(ctx, n, grade_mask, len, 0, broadcast, dtype, nullptr, out, present);
+}
+
+gaast_status gaast_batch_wrap_sparse(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
+                                     int broadcast, int dtype, const uint64_t* const* present, void* const* grade_ptrs,
+                                     gaast_batch** out) {
+    if (!present || !grade_ptrs) {
+        gaast::set_last_error("null presence-bitmap or grade pointer array");
+        return GAAST_ERR_INVALID;
+    }
+    return batch_make(ctx, n, grade_mask, len, stride, broadcast, dtype, grade_ptrs, out, present);
+}
+
+uint32_t gaast_batch_stored_rows(const gaast_batch* b, uint32_t grade) {
+    if (!b || grade > b->n || !(b->mask >> grade & 1)) return 0;
+    return b->stored[grade];
+}
+
 int gaast_batch_dtype(const gaast_batch* b) { return b ? b->dtype : GAAST_F64; }
 
 gaast_status gaast_batch_free(gaast_batch* b) {
@@ -455,7 +509,7 @@ static void batch_copy(const gaast_batch* b, uint32_t grade, void* host, uint64_
     if (grade > b->n || !(b->mask >> grade & 1)) throw Error(GAAST_ERR_SHAPE, "the batch does not hold this grade");
     if (!host) throw Error(GAAST_ERR_INVALID, "null host pointer");
     if (host_stride < b->len) throw Error(GAAST_ERR_INVALID, "host stride smaller than the batch length");
-    const size_t rows = gaast::binomial(b->n, grade);
+    const size_t rows = b->stored[grade];  // (a sparse grade: the stored rows, compact)
     if (!rows || !b->len) return;
     DeviceGuard dg(b->ctx->device);
     double* dev = b->grade_ptr[grade];
@@ -487,7 +541,7 @@ gaast_status gaast_batch_zero(gaast_batch* b) {
         DeviceGuard dg(b->ctx->device);
         for (uint32_t k = 0; k <= b->n; ++k)
             if (b->mask >> k & 1)
-                cuda_check(cudaMemsetAsync(b->grade_ptr[k], 0, gaast::binomial(b->n, k) * b->stride * b->esize(), b->ctx->stream),
+                cuda_check(cudaMemsetAsync(b->grade_ptr[k], 0, size_t(b->stored[k]) * b->stride * b->esize(), b->ctx->stream),
                            "batch zero");
     });
 }
@@ -495,7 +549,8 @@ gaast_status gaast_batch_zero(gaast_batch* b) {
 // ---------------------------------------------------------------- eval ----
 static std::shared_ptr<gaast::JitKernel> get_specialized(gaast_plan* plan, const gaast::CodegenOptions& opt) {
     auto key = std::make_tuple(opt.broadcast_slots, opt.arith, int(opt.with_sum), int(opt.store_out),
-                               opt.elems_per_thread, opt.variant, int(opt.pipelined), int(opt.tma_stage), int(opt.f32));
+                               opt.elems_per_thread, opt.variant, int(opt.pipelined), int(opt.tma_stage), int(opt.f32),
+                               opt.sparse_hash);
     auto it = plan->jit.find(key);
     if (it != plan->jit.end()) {
         // a negative entry: THIS variant failed to build before (other variants of the plan are unaffected)
@@ -531,7 +586,13 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     uint64_t bslots = 0;
     long long n = 0;
     int dtype = GAAST_F64;
-    bind_streams(plan, inputs, n_inputs, out, !with_sum, a, &bslots, &n, &dtype);
+    std::vector<std::vector<uint64_t>> sparse;
+    uint64_t sparse_hash = 0;
+    bind_streams(plan, inputs, n_inputs, out, !with_sum, a, &bslots, &n, &dtype, &sparse, &sparse_hash);
+    const bool any_sparse = !sparse.empty();
+    if (any_sparse && (engine == GAAST_ENGINE_TABLE || engine == GAAST_ENGINE_DENSE_WARP))
+        throw Error(GAAST_ERR_UNSUPPORTED, "sparse batches are evaluated by the specialised engine only (the kernel is "
+                                           "generated for the sparsity pattern): use GAAST_ENGINE_AUTO or GAAST_ENGINE_SPECIALIZED");
     const bool f32 = dtype == GAAST_F32;
     const gaast::DevicePlanHost& h = plan->h;
     const int sum_cols = int(h.buf_cols[0]);
@@ -591,7 +652,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     std::shared_ptr<gaast::JitKernel> jk;
     // AUTO: a handful of elements of a plan never specialised before is not worth generating and
     // compiling a kernel for (0.3-3 s): the table engine evaluates it at once.
-    const bool tiny = engine == GAAST_ENGINE_AUTO && plan->jit.empty() &&
+    const bool tiny = engine == GAAST_ENGINE_AUTO && plan->jit.empty() && !any_sparse &&
                       double(n) * double(h.total_terms > 0 ? h.total_terms : 1) < 2e6;
     if (use_dense_warp) {
         // chosen explicitly
@@ -606,6 +667,8 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                 opt.elems_per_thread = plan->force_ept;
                 opt.variant = plan->variant;
                 opt.f32 = f32;
+                opt.sparse = sparse;
+                opt.sparse_hash = sparse_hash;
                 // 128-bit accesses need even strides and 16-byte aligned rows
                 const long long quantum = f32 ? 4 : 2;  // elements per 16 bytes
                 bool aligned = (n % quantum == 0);
@@ -641,7 +704,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                 // AUTO: this variant cannot be specialised (too large, or no NVRTC and no cached cubin): the table
                 // engine evaluates it.  The failure is remembered per variant (get_specialized), so an odd-length
                 // call that needs another kernel does not take the fast path away from aligned calls.
-                if (engine == GAAST_ENGINE_SPECIALIZED) throw;
+                if (engine == GAAST_ENGINE_SPECIALIZED || any_sparse) throw;  // (no other engine reads a sparse batch)
             }
         }
         // too large / too wide to specialise: a full high-dimensional product still has a fast engine
@@ -718,17 +781,21 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
         if ((with_sum || jk->pipelined || gaast::tuning().force_persistent) && !jk->one_tile_blocks) {
             // persistent grid: the batch-sum epilogue keeps per-block partials, and the TMA-pipelined
             // kernels loop over their tiles; blocks stride over the batch
-            // sum-only kernels: many short-lived blocks overlap better (cfg5 + sum: 6.42 / 6.20 / 5.97 / 5.92 / 5.99 ms at
-            // 4 / 8 / 32 / 64 / 128 blocks per resident slot; the partials are 66 doubles per block)
-            long long mult = jk->pipelined ? 1 : 64;
+            // sum-only kernels: many short-lived blocks overlap better than one long-lived block per resident slot, but
+            // every block pays its epilogue (column sums -> partials), so a block should still see ~8 tiles.  Measured
+            // on cfg5 + sum (ms per step at 4 / 8 / 16 / 32 / 64 blocks per slot): 32 M elements 6.42 / 6.20 / - / 5.97 /
+            // 5.92; 8 M (the 4-GPU shard) 1.577 / 1.535 / 1.505 / 1.501 / 1.558; 4 M (the 8-GPU shard) 0.787 / 0.770 /
+            // 0.770 / 0.793 / 0.857.
+            const long long resident = (long long)ctx->sm_count * jk->blocks_per_sm;
+            long long mult = jk->pipelined ? 1 : std::min(64LL, std::max(4LL, blocks / (8 * resident)));
             if (gaast::tuning().grid_mult > 0) mult = gaast::tuning().grid_mult;
-            const long long cap = (long long)ctx->sm_count * jk->blocks_per_sm * mult;
+            const long long cap = resident * mult;
             if (grid > cap) grid = int(cap);
-            max_grid = size_t(cap);
+            max_grid = size_t(resident * std::max(64LL, mult));  // scratch sized once, for the largest grid of the variant
         }
         if (with_sum) {
             // sized for the largest grid this kernel can get: allocated by the first call, never again
-            ensure(plan->d_partials, plan->partials_cap, std::max(max_grid, size_t(grid)) * sum_cols);
+            ensure(plan->d_partials, plan->partials_cap, (std::max(max_grid, size_t(grid)) + gaast::kReduceStage1Rows) * sum_cols);
             a.partials = plan->d_partials;
         }
         if (jk->n_uniform > 0) {
@@ -764,7 +831,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
             a.ws_global = plan->d_ws;
         }
         if (with_sum) {
-            ensure(plan->d_partials, plan->partials_cap, max_grid * sum_cols);
+            ensure(plan->d_partials, plan->partials_cap, (max_grid + gaast::kReduceStage1Rows) * sum_cols);
             a.partials = plan->d_partials;
         }
         a.micro = plan->d_micro;
@@ -782,7 +849,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     if (with_sum) {
         cuda_check(gaast::reduce_partials_launch(plan->d_partials, grid, sum_cols, dev_sum, ctx->stream),
                    "launch partial-sum reduction");
-        ctx->launches++;
+        ctx->launches += (grid > 2048 && sum_cols <= 256) ? 2 : 1;  // (many partial rows: two-level reduction)
     }
 }
 

@@ -48,6 +48,12 @@ struct CodegenOptions {
     bool tma_stage = false;    // one-tile blocks: parked rows copied to shared memory by TMA bulk copies (aligned rows)
     int extra_parked = 0;      // more input rows parked in shared memory (raised while ptxas reports spills)
     bool f32 = false;          // binary32 batches and arithmetic (the f32 variant); batch sums stay in double
+    // Sparse per-grade storage of the bound inputs: per stream (device_plan.hpp) a bitmap of the components its grade
+    // array stores (empty = dense).  Components that are not stored are zero for every element: their loads become
+    // the constant 0 and every term that reads them is dropped (exactly, in strict arithmetic too: x + 0 * y == x
+    // for finite y); stored rows are addressed by their rank.
+    std::vector<std::vector<uint64_t>> sparse;
+    uint64_t sparse_hash = 0;
 };
 
 struct CodegenResult {
@@ -94,6 +100,8 @@ struct TableLaunch {
 TableLaunch table_engine_shape(const gaast_ctx& ctx, const DevicePlanHost& h, long long n, bool with_sum, bool f32);
 cudaError_t table_engine_launch(const EvalArgs& args, const TableLaunch& shape, bool strict, bool with_sum, bool f32,
                                 cudaStream_t stream);
+// (the partials buffer must have room for kReduceStage1Rows more rows of n_cols doubles: the two-level reduction's scratch)
+constexpr int kReduceStage1Rows = 296;
 cudaError_t reduce_partials_launch(const double* partials, int n_blocks, int n_cols, double* out,
                                    cudaStream_t stream);
 const char* table_engine_arch();
@@ -170,7 +178,12 @@ struct gaast_batch {
     size_t esize() const { return dtype == GAAST_F32 ? 4 : 8; }
     double* base = nullptr;
     double* grade_ptr[GAAST_MAX_DIM + 1] = {};
-    uint32_t rows = 0;
+    uint32_t rows = 0;  // rows stored, over all grades
+    // sparse per-grade storage: present[k] = bitmap of the C(n,k) components grade k stores (empty = all of them);
+    // stored rows are compacted in ascending component order
+    std::vector<uint64_t> present[GAAST_MAX_DIM + 1];
+    uint32_t stored[GAAST_MAX_DIM + 1] = {};  // rows stored per grade
+    bool sparse = false;
 };
 
 struct gaast_plan {
@@ -187,9 +200,10 @@ struct gaast_plan {
     size_t uniform_cap = 0;
     std::string last_kernel;
     // specialised kernels, keyed by (broadcast slots, arith, with_sum, store_out, elems/thread, variant)
-    std::map<std::tuple<uint64_t, int, int, int, int, int, int, int, int>, std::shared_ptr<gaast::JitKernel>> jit;
+    using JitKey = std::tuple<uint64_t, int, int, int, int, int, int, int, int, uint64_t>;
+    std::map<JitKey, std::shared_ptr<gaast::JitKernel>> jit;
     // why a variant could not be built (its entry in `jit` is null): per variant, never sticky for the plan
-    std::map<std::tuple<uint64_t, int, int, int, int, int, int, int, int>, std::string> jit_errors;
+    std::map<JitKey, std::string> jit_errors;
     int variant = 0;
     int force_ept = 0;
     gaast::HostPipe* pipe = nullptr;  // device buffer sets of gaast_eval_host

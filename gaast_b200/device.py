@@ -139,6 +139,47 @@ class DeviceBatch:
         ctx.sync()
         return b
 
+    @staticmethod
+    def from_host_sparse(ctx: Ctx, n: int, data: Dict[int, "tuple"], broadcast: bool = False,
+                         dtype: int = L.F64) -> "DeviceBatch":
+        """Sparse per-grade storage (gaast_batch_alloc_sparse): data[grade] = (stored component indices, array
+        [len(indices), batch]), or a plain [C(n,k), batch] array for a dense grade.  Components that are not
+        stored are zero for every element; the kernel generated for this pattern never loads or multiplies them."""
+        grades = sorted(data)
+        length = None
+        bitmaps, arrays = [], {}
+        for k in grades:
+            item = data[k]
+            if isinstance(item, tuple):
+                idx, arr = item
+                arr = np.ascontiguousarray(np.asarray(arr, dtype=_np_dtype(dtype)))
+                idx = [int(i) for i in idx]
+                assert list(idx) == sorted(set(idx)) and arr.shape[0] == len(idx) and all(0 <= i < comb(n, k) for i in idx)
+                words = (comb(n, k) + 63) // 64
+                bits = (L.u64 * words)()
+                for i in idx:
+                    bits[i // 64] |= 1 << (i % 64)
+                bitmaps.append(bits)
+            else:
+                arr = np.ascontiguousarray(np.asarray(item, dtype=_np_dtype(dtype)))
+                bitmaps.append(None)
+            arrays[k] = arr
+            length = arr.shape[1] if length is None else length
+            assert arr.shape[1] == length
+        ptrs = (C.POINTER(L.u64) * max(1, len(grades)))(*[C.cast(b, C.POINTER(L.u64)) if b is not None else None for b in bitmaps])
+        out = L.vp()
+        L.check(L.lib.gaast_batch_alloc_sparse(ctx._h, n, grade_mask(grades), int(length or 0), int(broadcast), int(dtype), ptrs,
+                                               C.byref(out)))
+        b = DeviceBatch(out, ctx, n, keep=tuple(bitmaps))
+        for k in grades:
+            if arrays[k].shape[0]:
+                b.upload(k, arrays[k])
+        ctx.sync()
+        return b
+
+    def stored_rows(self, k: int) -> int:
+        return L.lib.gaast_batch_stored_rows(self._h, k)
+
     @property
     def length(self) -> int:
         return L.lib.gaast_batch_len(self._h)
@@ -160,14 +201,14 @@ class DeviceBatch:
     def upload(self, k: int, host: np.ndarray):
         f32 = self.dtype == L.F32
         host = np.ascontiguousarray(host, dtype=_np_dtype(self.dtype))
-        assert host.ndim == 2 and host.shape[0] == comb(self.n, k)
+        assert host.ndim == 2 and host.shape[0] == self.stored_rows(k)
         fn = L.lib.gaast_batch_upload_f32 if f32 else L.lib.gaast_batch_upload
         L.check(fn(self._h, k, host.ctypes.data_as(L.vp), host.shape[1]))
         self.ctx.sync()  # `host` may be a temporary
 
     def download(self, k: int) -> np.ndarray:
         f32 = self.dtype == L.F32
-        out = np.empty((comb(self.n, k), self.length), dtype=_np_dtype(self.dtype))
+        out = np.empty((self.stored_rows(k), self.length), dtype=_np_dtype(self.dtype))
         fn = L.lib.gaast_batch_download_f32 if f32 else L.lib.gaast_batch_download
         L.check(fn(self._h, k, out.ctypes.data_as(L.vp), out.shape[1]))
         self.ctx.sync()

@@ -221,6 +221,22 @@ gaast_status gaast_batch_alloc_typed(gaast_ctx* ctx, uint32_t n, uint32_t grade_
                                      int dtype, gaast_batch** out);
 gaast_status gaast_batch_wrap_typed(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
                                     int broadcast, int dtype, void* const* grade_ptrs, gaast_batch** out);
+/* Sparse per-grade storage (the reference's README.md:102-104 caveat: "one array per grade imposes a dense
+ * storage whatever the grade; a sparse storage for some grades would be necessary for higher-dimension
+ * spaces").  A sparse batch stores, for grade k, only SOME of the C(n,k) components; the others are zero for
+ * every element.  present[i] (i-th grade of the mask, ascending) is a bitmap of C(n,k) bits -- bit c of word
+ * c / 64 set = component c is stored -- or NULL for a dense grade; the grade's array is then
+ * [stored rows][stride], rows in ascending component order (uploads / downloads / wrapped pointers use that
+ * compact shape; gaast_batch_stored_rows gives its height).  Input batches only: a kernel is specialised for the
+ * sparsity pattern it is given -- loads of absent components and every term that reads them disappear -- so
+ * sparse batches need the specialised engine (GAAST_ENGINE_AUTO or _SPECIALIZED; GAAST_ERR_UNSUPPORTED on the
+ * table and dense-warp engines), in either arithmetic. */
+gaast_status gaast_batch_alloc_sparse(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, int broadcast,
+                                      int dtype, const uint64_t* const* present, gaast_batch** out);
+gaast_status gaast_batch_wrap_sparse(gaast_ctx* ctx, uint32_t n, uint32_t grade_mask, uint64_t len, uint64_t stride,
+                                     int broadcast, int dtype, const uint64_t* const* present, void* const* grade_ptrs,
+                                     gaast_batch** out);
+uint32_t gaast_batch_stored_rows(const gaast_batch* b, uint32_t grade);
 int gaast_batch_dtype(const gaast_batch* b);
 gaast_status gaast_batch_free(gaast_batch* b);
 uint64_t gaast_batch_len(const gaast_batch* b);

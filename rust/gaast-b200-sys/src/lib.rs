@@ -126,6 +126,9 @@ extern "C" {
     pub fn gaast_batch_wrap(ctx: *mut gaast_ctx, n: u32, grade_mask: u32, len: u64, stride: u64, broadcast: c_int, grade_ptrs: *const *mut c_void, out: *mut *mut gaast_batch) -> c_int;
     pub fn gaast_batch_alloc_typed(ctx: *mut gaast_ctx, n: u32, grade_mask: u32, len: u64, broadcast: c_int, dtype: c_int, out: *mut *mut gaast_batch) -> c_int;
     pub fn gaast_batch_wrap_typed(ctx: *mut gaast_ctx, n: u32, grade_mask: u32, len: u64, stride: u64, broadcast: c_int, dtype: c_int, grade_ptrs: *const *mut c_void, out: *mut *mut gaast_batch) -> c_int;
+    pub fn gaast_batch_alloc_sparse(ctx: *mut gaast_ctx, n: u32, grade_mask: u32, len: u64, broadcast: c_int, dtype: c_int, present: *const *const u64, out: *mut *mut gaast_batch) -> c_int;
+    pub fn gaast_batch_wrap_sparse(ctx: *mut gaast_ctx, n: u32, grade_mask: u32, len: u64, stride: u64, broadcast: c_int, dtype: c_int, present: *const *const u64, grade_ptrs: *const *mut c_void, out: *mut *mut gaast_batch) -> c_int;
+    pub fn gaast_batch_stored_rows(b: *const gaast_batch, grade: u32) -> u32;
     pub fn gaast_batch_dtype(b: *const gaast_batch) -> c_int;
     pub fn gaast_batch_free(b: *mut gaast_batch) -> c_int;
     pub fn gaast_batch_len(b: *const gaast_batch) -> u64;
