@@ -306,6 +306,9 @@ size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int 
         opt.with_sum = with_sum != 0;
         opt.elems_per_thread = plan->force_ept;
         opt.variant = plan->variant;
+        // the kernel gaast_eval launches for an aligned f64 batch (the same choices as eval_impl / precompile)
+        opt.pipelined = (opt.variant & 8) != 0;
+        opt.tma_stage = !opt.pipelined && !opt.with_sum && !(opt.variant & 1024);
         gaast::CodegenResult cg = gaast::generate_kernel(plan->h, opt);
         len = cg.source.size();
         if (buf && cap) {
