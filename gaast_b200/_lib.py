@@ -29,7 +29,7 @@ ENGINE_AUTO, ENGINE_TABLE, ENGINE_SPECIALIZED, ENGINE_DENSE_WARP = 0, 1, 2, 3
 ARITH_FMA, ARITH_STRICT = 0, 1
 F64, F32 = 0, 1  # gaast_dtype
 
-OP_ADD_INPUT, OP_MUL_TERMS, OP_NEG_GRADES, OP_SCALAR_INV, OP_SCALAR_SQRT = range(5)
+OP_ADD_INPUT, OP_MUL_TERMS, OP_NEG_GRADES, OP_SCALAR_INV, OP_SCALAR_SQRT, OP_EXP, OP_LOG = range(7)
 INPUT_BATCH, INPUT_CONST = 0, 1
 PROD_GEOMETRIC, PROD_OUTER, PROD_INNER, PROD_LCONTRACT, PROD_RCONTRACT = range(5)
 

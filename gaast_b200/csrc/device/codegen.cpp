@@ -42,7 +42,11 @@ const char kEvalArgsText[] =
 #include "../eval_args_text.inc"
     ;
 
-enum NodeKind : uint8_t { N_ZERO, N_CONST, N_LOAD, N_ACC, N_ADD, N_INV, N_SQRT };
+enum NodeKind : uint8_t { N_ZERO, N_CONST, N_LOAD, N_ACC, N_ADD, N_INV, N_SQRT, N_EXPC, N_EXPS, N_LOGF };
+// N_EXPC / N_EXPS: the two factors of exp(B) as functions of q = <B B>_0 (a);  N_LOGF: the factor of log(a0 + B) as a
+// function of a0 (a) and q (b).  GAAST_OP_EXP / GAAST_OP_LOG: this library's definition (eval.rs:112-113 is todo!()).
+inline bool is_unary(NodeKind k) { return k == N_INV || k == N_SQRT || k == N_EXPC || k == N_EXPS; }
+inline bool is_binary(NodeKind k) { return k == N_ADD || k == N_LOGF; }
 
 struct Ref {
     int id = 0;
@@ -225,6 +229,43 @@ struct Gen {
                     d = make_unary(op.kind == GAAST_OP_SCALAR_INV ? N_INV : N_SQRT, d);
                     break;
                 }
+                case GAAST_OP_EXP:
+                case GAAST_OP_LOG: {
+                    const uint32_t k = uint32_t(__builtin_ctz(op.mask));
+                    const uint32_t src0 = h.col_of(op.a, k) - h.buf_col[op.a], dst0 = h.col_of(op.dst, k) - h.buf_col[op.dst];
+                    Ref q{0, false};  // <B B>_0, in component order
+                    for (uint32_t i = 0; i < op.term_count; ++i)
+                        q = make_acc(q, buf[op.a][src0 + i], buf[op.a][src0 + i], h.terms[op.term_begin + i].coeff, int(oi));
+                    if (strict && is_zero(q)) q = make_add(q, Ref{0, false});
+                    Ref f;
+                    if (op.kind == GAAST_OP_EXP) {
+                        if (h.buffer_masks[op.dst] & 1) {
+                            Ref& d0 = buf[op.dst][h.col_of(op.dst, 0) - h.buf_col[op.dst]];
+                            d0 = make_add(d0, make_unary(N_EXPC, q));
+                        }
+                        f = make_unary(N_EXPS, q);
+                    } else {
+                        Node nf;
+                        nf.k = N_LOGF;
+                        nf.a = buf[op.a][h.col_of(op.a, 0) - h.buf_col[op.a]];
+                        nf.b = q;
+                        nf.uniform = nodes[nf.a.id].uniform && nodes[q.id].uniform;
+                        f = Ref{add(nf), false};
+                    }
+                    const Ref one = constant(1.0);
+                    (void)one;
+                    for (uint32_t i = 0; i < op.term_count; ++i) {
+                        Ref& d = buf[op.dst][dst0 + i];
+                        const size_t before = nodes.size();
+                        d = make_acc(d, f, buf[op.a][src0 + i], 1.0, int(oi));
+                        if (nodes.size() != before) {
+                            nodes.back().out_slot = dst0 + i;
+                            nodes.back().l_slot = 0;
+                            nodes.back().r_slot = src0 + i;
+                        }
+                    }
+                    break;
+                }
             }
         }
     }
@@ -272,7 +313,13 @@ struct Gen {
                 break;
             case N_INV:
             case N_SQRT:
+            case N_EXPC:
+            case N_EXPS:
                 ok = lin_keys(n.a.id, state, keys) && uni(keys[n.a.id]);
+                if (ok) k.insert(kConstKey);
+                break;
+            case N_LOGF:
+                ok = lin_keys(n.a.id, state, keys) && uni(keys[n.a.id]) && lin_keys(n.b.id, state, keys) && uni(keys[n.b.id]);
                 if (ok) k.insert(kConstKey);
                 break;
         }
@@ -323,7 +370,10 @@ struct Gen {
                 break;
             }
             case N_INV:
-            case N_SQRT: m.emplace(kConstKey, Ref{id, false}); break;  // uniform argument (checked by lin_keys)
+            case N_SQRT:
+            case N_EXPC:
+            case N_EXPS:
+            case N_LOGF: m.emplace(kConstKey, Ref{id, false}); break;  // uniform argument(s) (checked by lin_keys)
         }
         return memo.emplace(id, std::move(m)).first->second;
     }
@@ -343,8 +393,8 @@ struct Gen {
             refs.resize(nodes.size(), 0);
             for (const Node& n : nodes) {
                 if (n.k == N_ACC) { ++refs[n.a.id]; ++refs[n.b.id]; ++refs[n.c.id]; }
-                else if (n.k == N_ADD) { ++refs[n.a.id]; ++refs[n.b.id]; }
-                else if (n.k == N_INV || n.k == N_SQRT) ++refs[n.a.id];
+                else if (is_binary(n.k)) { ++refs[n.a.id]; ++refs[n.b.id]; }
+                else if (is_unary(n.k)) ++refs[n.a.id];
             }
             for (Ref r : buf[0]) ++refs[r.id];  // only the root buffer is read after the symbolic run
         };
@@ -408,9 +458,9 @@ struct Gen {
             for (size_t id = 0; id < nodes.size(); ++id) {
                 Node& n = nodes[id];
                 if (n.k == N_ACC && n.op == int(oi)) { fix(n.b, int(id)); fix(n.c, int(id)); continue; }  // own chain links stay
-                if (n.k == N_ACC || n.k == N_ADD || n.k == N_INV || n.k == N_SQRT) {
+                if (n.k == N_ACC || is_binary(n.k) || is_unary(n.k)) {
                     fix(n.a, int(id));
-                    if (n.k == N_ACC || n.k == N_ADD) fix(n.b, int(id));
+                    if (n.k == N_ACC || is_binary(n.k)) fix(n.b, int(id));
                     if (n.k == N_ACC) fix(n.c, int(id));
                 }
             }
@@ -617,9 +667,9 @@ struct Gen {
             for (size_t id = 0; id < first_new && id < nodes.size(); ++id) {
                 Node& nd = nodes[id];
                 if (nd.k == N_ACC && nd.op == int(oR)) continue;  // the old chain itself (now dead)
-                if (nd.k == N_ACC || nd.k == N_ADD || nd.k == N_INV || nd.k == N_SQRT) {
+                if (nd.k == N_ACC || is_binary(nd.k) || is_unary(nd.k)) {
                     fix(nd.a);
-                    if (nd.k == N_ACC || nd.k == N_ADD) fix(nd.b);
+                    if (nd.k == N_ACC || is_binary(nd.k)) fix(nd.b);
                     if (nd.k == N_ACC) fix(nd.c);
                 }
             }
@@ -643,10 +693,10 @@ struct Gen {
                 stack.push_back(n.a.id);
                 stack.push_back(n.b.id);
                 stack.push_back(n.c.id);
-            } else if (n.k == N_ADD) {
+            } else if (is_binary(n.k)) {
                 stack.push_back(n.a.id);
                 stack.push_back(n.b.id);
-            } else if (n.k == N_INV || n.k == N_SQRT) {
+            } else if (is_unary(n.k)) {
                 stack.push_back(n.a.id);
             }
         }
@@ -668,10 +718,10 @@ struct Gen {
                 want(n.a);
                 want(n.b);
                 want(n.c);
-            } else if (n.k == N_ADD) {
+            } else if (is_binary(n.k)) {
                 want(n.a);
                 want(n.b);
-            } else if (n.k == N_INV || n.k == N_SQRT) {
+            } else if (is_unary(n.k)) {
                 want(n.a);
             }
         }
@@ -746,6 +796,9 @@ struct Gen {
                 return;
             case N_INV: line(ty + v + " = d_inv(" + opnd(n.a, wide) + ");"); return;
             case N_SQRT: line(ty + v + " = d_sqrt(" + opnd(n.a, wide) + ");"); return;
+            case N_EXPC: line(ty + v + " = d_expc(" + opnd(n.a, wide) + ");"); return;
+            case N_EXPS: line(ty + v + " = d_exps(" + opnd(n.a, wide) + ");"); return;
+            case N_LOGF: line(ty + v + " = d_logf(" + opnd(n.a, wide) + ", " + opnd(n.b, wide) + ");"); return;
             case N_ACC: {
                 const std::string ln = use_name(n.b), rn = use_name(n.c);
                 line(ty + v + " = " +
@@ -862,7 +915,7 @@ struct Gen {
             }
             return;
         }
-        if (n.k == N_ADD) {
+        if (is_binary(n.k)) {
             emit(n.a.id);
             emit(n.b.id);
         } else {
@@ -1605,6 +1658,26 @@ struct Gen {
 
 };
 
+const char kPreludeExpLog[] = R"GAAST(
+// exp / log factors of a k-vector with a scalar square q = <B B>_0 (GAAST_OP_EXP / GAAST_OP_LOG; the same functions as
+// in table_engine.cu).  Near q = 0 both branches share one series.
+__device__ __forceinline__ double s_expc(double q) {
+  if (fabs(q) < 1e-8) return 1.0 + 0.5 * q;
+  const double x = sqrt(fabs(q));
+  return q < 0 ? cos(x) : cosh(x);
+}
+__device__ __forceinline__ double s_exps(double q) {
+  if (fabs(q) < 1e-8) return 1.0 + q / 6.0;
+  const double x = sqrt(fabs(q));
+  return q < 0 ? sin(x) / x : sinh(x) / x;
+}
+__device__ __forceinline__ double s_logf(double a, double q) {
+  if (fabs(q) < 1e-8 * a * a && a > 0) return (1.0 + q / (3.0 * a * a)) / a;
+  const double x = sqrt(fabs(q));
+  return q < 0 ? atan2(x, a) / x : atanh(x / a) / x;
+}
+)GAAST";
+
 const char kPrelude[] = R"GAAST(
 #if GAAST_EPT == 2
 typedef double2 D;
@@ -1619,6 +1692,9 @@ __device__ __forceinline__ D d_muls(D a, D b) { return make_double2(__dmul_rn(a.
 __device__ __forceinline__ D d_adds(D a, D b) { return make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y)); }
 __device__ __forceinline__ D d_inv(D a) { return make_double2(__ddiv_rn(1.0, a.x), __ddiv_rn(1.0, a.y)); }
 __device__ __forceinline__ D d_sqrt(D a) { return make_double2(__dsqrt_rn(a.x), __dsqrt_rn(a.y)); }
+__device__ __forceinline__ D d_expc(D a) { return make_double2(s_expc(a.x), s_expc(a.y)); }
+__device__ __forceinline__ D d_exps(D a) { return make_double2(s_exps(a.x), s_exps(a.y)); }
+__device__ __forceinline__ D d_logf(D a, D q) { return make_double2(s_logf(a.x, q.x), s_logf(a.y, q.y)); }
 __device__ __forceinline__ double d_hsum(D a) { return a.x + a.y; }
 #else
 typedef double D;
@@ -1782,6 +1858,9 @@ __device__ __forceinline__ double d_muls(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ double d_adds(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double d_inv(double a) { return __ddiv_rn(1.0, a); }
 __device__ __forceinline__ double d_sqrt(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ double d_expc(double a) { return s_expc(a); }
+__device__ __forceinline__ double d_exps(double a) { return s_exps(a); }
+__device__ __forceinline__ double d_logf(double a, double q) { return s_logf(a, q); }
 )GAAST";
 
 
@@ -1802,6 +1881,9 @@ __device__ __forceinline__ D d_muls(D a, D b) { return make_float2(__fmul_rn(a.x
 __device__ __forceinline__ D d_adds(D a, D b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 __device__ __forceinline__ D d_inv(D a) { return make_float2(__fdiv_rn(1.0f, a.x), __fdiv_rn(1.0f, a.y)); }
 __device__ __forceinline__ D d_sqrt(D a) { return make_float2(__fsqrt_rn(a.x), __fsqrt_rn(a.y)); }
+__device__ __forceinline__ D d_expc(D a) { return make_float2((float)s_expc(a.x), (float)s_expc(a.y)); }
+__device__ __forceinline__ D d_exps(D a) { return make_float2((float)s_exps(a.x), (float)s_exps(a.y)); }
+__device__ __forceinline__ D d_logf(D a, D q) { return make_float2((float)s_logf(a.x, q.x), (float)s_logf(a.y, q.y)); }
 __device__ __forceinline__ double d_hsum(D a) { return (double)a.x + (double)a.y; }
 #else
 typedef float D;
@@ -1843,6 +1925,9 @@ __device__ __forceinline__ float d_muls(float a, float b) { return __fmul_rn(a, 
 __device__ __forceinline__ float d_adds(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float d_inv(float a) { return __fdiv_rn(1.0f, a); }
 __device__ __forceinline__ float d_sqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float d_expc(float a) { return (float)s_expc(a); }
+__device__ __forceinline__ float d_exps(float a) { return (float)s_exps(a); }
+__device__ __forceinline__ float d_logf(float a, float q) { return (float)s_logf(a, q); }
 )GAAST";
 
 }  // namespace
@@ -1937,8 +2022,8 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
             for (const Node& n : g.nodes) {
                 if (!n.live) continue;
                 if (n.k == N_ACC) { ++refcount[n.a.id]; ++refcount[n.b.id]; ++refcount[n.c.id]; }
-                else if (n.k == N_ADD) { ++refcount[n.a.id]; ++refcount[n.b.id]; }
-                else if (n.k == N_INV || n.k == N_SQRT) ++refcount[n.a.id];
+                else if (is_binary(n.k)) { ++refcount[n.a.id]; ++refcount[n.b.id]; }
+                else if (is_unary(n.k)) ++refcount[n.a.id];
             }
             if (g.plan_dense(int(oi), refcount)) pol = P_DENSE;
         }
@@ -2096,7 +2181,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     res.min_blocks = min_blocks;
     src << "#define GAAST_EPT " << ept << "\n#define GAAST_THREADS " << threads << "\n#define GAAST_MIN_BLOCKS "
         << min_blocks << "\n";
-    src << kEvalArgsText << "\nusing gaast::EvalArgs;\n" << (opt.f32 ? kPreludeF32Head : kPrelude) << kPreludeShared << (opt.f32 ? kPreludeF32Tail : kPreludeTail) << "\n";
+    src << kEvalArgsText << "\nusing gaast::EvalArgs;\n" << kPreludeExpLog << (opt.f32 ? kPreludeF32Head : kPrelude) << kPreludeShared << (opt.f32 ? kPreludeF32Tail : kPreludeTail) << "\n";
 
     std::ostringstream loop_strides;
     auto stream_decls = [&](std::ostringstream& o, bool prologue) {

@@ -73,6 +73,25 @@ __device__ __forceinline__ float inv_rn(float a) { return __fdiv_rn(1.0f, a); }
 __device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
 __device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
 
+// exp / log of a k-vector with a scalar square (GAAST_OP_EXP / GAAST_OP_LOG: this library's definition, the reference
+// has todo!() there).  q = <B B>_0.  Near q = 0 both branches share one series: sin x / x = sinh x / x = 1 + q / 6,
+// cos x = cosh x = 1 + q / 2, atan(x / a) / x = atanh(x / a) / x = (1 + q / (3 a^2)) / a  (q = -+ x^2).
+template <class T>
+__device__ __forceinline__ void exp_factors(T q, T* c, T* s) {
+    const double qq = double(q);
+    if (fabs(qq) < 1e-8) { *c = T(1.0 + 0.5 * qq); *s = T(1.0 + qq / 6.0); return; }
+    const double x = sqrt(fabs(qq));
+    if (qq < 0) { *c = T(cos(x)); *s = T(sin(x) / x); }
+    else { *c = T(cosh(x)); *s = T(sinh(x) / x); }
+}
+template <class T>
+__device__ __forceinline__ T log_factor(T a0, T q) {
+    const double a = double(a0), qq = double(q);
+    if (fabs(qq) < 1e-8 * a * a && a > 0) return T((1.0 + qq / (3.0 * a * a)) / a);
+    const double x = sqrt(fabs(qq));
+    return T(qq < 0 ? atan2(x, a) / x : atanh(x / a) / x);
+}
+
 // Thread layout: lane = batch element (32 per block and tile), warp = work group.  The
 // element's workspace is shared by the block's warps: inside a micro-op they split the rows
 // (loads, sign flips, stores) or the output runs of a term chunk (products), so a block
@@ -203,6 +222,29 @@ __global__ void __launch_bounds__(256) table_engine_kernel(const __grid_constant
                     if (grp == 0) {
                         T* d = &w[size_t(op.dst_col) * kLanes];
                         *d = sqrt_rn(*d);
+                    }
+                    break;
+                case MK_EXP:    // dst += exp(B): grade 0 += c(q), grade k += s(q) B
+                case MK_LOG:    // dst += log(a0 + B): grade k += t(a0, q) B
+                    if (grp == 0) {  // (rare ops on C(n,k) components: one warp, in component order)
+                        const T* src = w + size_t(op.a) * kLanes;
+                        T q = T(0);
+                        for (uint32_t r = 0; r < op.count; ++r) q = term_acc<kStrict>(q, src[size_t(r) * kLanes], src[size_t(r) * kLanes], T(a.consts[op.chunk0 + r]));
+                        T f;
+                        if (op.kind == MK_EXP) {
+                            T c;
+                            exp_factors(q, &c, &f);
+                            if (op.b != 0xFFFFFFFFu) {
+                                T* d0 = &w[size_t(op.b) * kLanes];
+                                *d0 = kStrict ? add_rn(*d0, c) : (*d0 + c);
+                            }
+                        } else {
+                            f = log_factor(w[size_t(op.b) * kLanes], q);
+                        }
+                        for (uint32_t r = 0; r < op.count; ++r) {
+                            T* d = &w[size_t(op.dst_col + r) * kLanes];
+                            *d = term_acc<kStrict>(*d, f, src[size_t(r) * kLanes], T(1));
+                        }
                     }
                     break;
                 case MK_STORE: {

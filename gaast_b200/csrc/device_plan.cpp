@@ -113,6 +113,25 @@ void DevicePlanHost::build(const gaast_plan_desc& d) {
             case GAAST_OP_SCALAR_SQRT:
                 if (!(buffer_masks[op.dst] & 1)) bad("scalar op on a buffer without grade 0");
                 break;
+            case GAAST_OP_EXP:
+            case GAAST_OP_LOG: {
+                if (op.a >= d.n_buffers || op.a == op.dst) bad("EXP / LOG: source buffer out of range or aliasing the destination");
+                if (!op.mask || (op.mask & (op.mask - 1)) || (op.mask & ~full)) bad("EXP / LOG: `mask` must name one grade");
+                const uint32_t k = uint32_t(__builtin_ctz(op.mask));
+                if (k == 0) bad("EXP / LOG: the k-vector part cannot be grade 0");
+                if (!(buffer_masks[op.a] >> k & 1) || !(buffer_masks[op.dst] >> k & 1))
+                    bad("EXP / LOG: grade k must be held by the source and by the destination");
+                if (op.kind == GAAST_OP_LOG && !(buffer_masks[op.a] & 1)) bad("LOG: the source lacks grade 0");
+                if (uint64_t(op.term_begin) + op.term_count > terms.size() || op.term_count != gdim[k])
+                    bad("EXP / LOG: needs one term (blade square) per component of grade k");
+                const uint32_t first = col_of(op.a, k) - buf_col[op.a];
+                for (uint32_t i = 0; i < op.term_count; ++i) {
+                    const gaast_term& tm = terms[op.term_begin + i];
+                    if (tm.a != first + i || tm.b != first + i) bad("EXP / LOG: term i must address component i of grade k");
+                }
+                total_terms += 2 * uint64_t(op.term_count);  // the square and the scaling, per component
+                break;
+            }
             default: bad("unknown op kind");
         }
     }
@@ -178,6 +197,16 @@ void DevicePlanHost::build(const gaast_plan_desc& d) {
                 break;
             case GAAST_OP_SCALAR_INV: push(MK_INV, col_of(op.dst, 0), 0, 0, 1); break;
             case GAAST_OP_SCALAR_SQRT: push(MK_SQRT, col_of(op.dst, 0), 0, 0, 1); break;
+            case GAAST_OP_EXP:
+            case GAAST_OP_LOG: {
+                const uint32_t k = uint32_t(__builtin_ctz(op.mask));
+                const uint32_t coff = uint32_t(const_values.size());  // the blade squares join the plan's constants
+                for (uint32_t i = 0; i < op.term_count; ++i) const_values.push_back(terms[op.term_begin + i].coeff);
+                push(op.kind == GAAST_OP_EXP ? MK_EXP : MK_LOG, col_of(op.dst, k), col_of(op.a, k),
+                     op.kind == GAAST_OP_LOG ? col_of(op.a, 0) : (buffer_masks[op.dst] & 1) ? col_of(op.dst, 0) : 0xFFFFFFFFu,
+                     gdim[k], coff);  // (EXP into an accumulator without grade 0 -- a projection pruned it: no scalar part)
+                break;
+            }
         }
     }
     for (uint32_t i = n_in_streams; i < streams.size(); ++i)

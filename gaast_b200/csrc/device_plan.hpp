@@ -23,7 +23,10 @@ struct Stream {
 };
 
 // What the table engine executes; one per contiguous run of rows.
-enum MicroKind : uint32_t { MK_LOAD_ADD = 0, MK_CONST_ADD, MK_MUL, MK_NEG, MK_INV, MK_SQRT, MK_STORE };
+enum MicroKind : uint32_t { MK_LOAD_ADD = 0, MK_CONST_ADD, MK_MUL, MK_NEG, MK_INV, MK_SQRT, MK_STORE, MK_EXP, MK_LOG };
+// MK_EXP / MK_LOG: dst_col = first column of grade k in the destination, a = first column of grade k in the source,
+// b = column of grade 0 (EXP: in the destination, LOG: in the source), count = C(n,k), chunk0 = offset of the
+// components' blade squares in the plan's constants.
 struct MicroOp {
     uint32_t kind;
     uint32_t dst_col;  // first workspace column written (MK_STORE: read)

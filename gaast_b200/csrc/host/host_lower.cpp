@@ -163,8 +163,54 @@ struct Lowerer {
             }
             case GAAST_NODE_GRADE_PROJECTION: add_to_res(buf, nd.c0); return;  // :111
             case GAAST_NODE_EXPONENTIAL:
-            case GAAST_NODE_LOGARITHM:  // :112-113 todo!()
-                throw Error(GAAST_ERR_UNSUPPORTED, "Exponential / Logarithm evaluation is todo!() in gaast (eval.rs:112-113)");
+            case GAAST_NODE_LOGARITHM: {
+                // :112-113 is todo!() in the reference.  This library's definition (gaast_b200.h, GAAST_OP_EXP / _LOG):
+                // the operand is evaluated into its own buffer like a product operand (:67-68) and
+                //     res += c(q) + s(q) B          (exp of a single-graded k-vector B, q = <B B>_0)
+                //     res += t(a0, q) B             (log of a0 + B)
+                // for a k-vector with a scalar square.  The grade rules are the reference's (grade_set.rs:181-197).
+                const bool is_exp = nd.kind == GAAST_NODE_EXPONENTIAL;
+                const uint32_t src = store_in_cache(nd.c0);
+                const GradeMask sm = out.buffer_masks[src];
+                const GradeMask kv = sm & ~GradeMask(1) & (is_exp ? ~GradeMask(0) : ~GradeMask(0));
+                GradeMask bpart = is_exp ? sm : kv;
+                if (!gs_is_single(bpart) || (bpart & 1)) {
+                    if (bpart == 0 || bpart == 1) {
+                        // exp(0) = 1 / exp of a scalar, log of a scalar: no k-vector part survives specialization
+                        throw Error(GAAST_ERR_UNSUPPORTED, "exp / log of an operand without a k-vector part (k >= 1) is not supported");
+                    }
+                    throw Error(GAAST_ERR_PANIC, "the reference panics here: exp / log need a single-graded k-vector part");
+                }
+                unsigned k = 0;
+                while (!(bpart >> k & 1)) ++k;
+                if (!is_exp && !(sm & 1))
+                    throw Error(GAAST_ERR_UNSUPPORTED, "log of a k-vector without a scalar part (the result would be infinite)");
+                require_grades(buf, GradeMask(1) << k, is_exp ? "exp" : "log");
+                gaast_op op{};
+                op.kind = is_exp ? GAAST_OP_EXP : GAAST_OP_LOG;
+                op.dst = buf;
+                op.a = src;
+                op.mask = uint32_t(1) << k;
+                op.term_begin = uint32_t(out.terms.size());
+                // one term per component: the square of its basis blade, (-1)^(k(k-1)/2) times the metric of its vectors
+                const BladeTable bt(ast.n);
+                const double rev = (k * (k - 1) / 2) % 2 ? -1.0 : 1.0;
+                uint32_t idx = 0;
+                for (Blade b : bt.of_grade[k]) {
+                    double sq = rev;
+                    for (unsigned i = 0; i < ast.n; ++i)
+                        if (b >> i & 1) sq *= ast.metric[i];
+                    gaast_term t{};
+                    t.out = 0;
+                    t.a = t.b = uint16_t(slot_of(ast.n, sm, k, idx));
+                    t.coeff = sq;
+                    out.terms.push_back(t);
+                    ++idx;
+                }
+                op.term_count = idx;
+                out.ops.push_back(op);
+                return;
+            }
         }
     }
 };

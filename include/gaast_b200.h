@@ -84,7 +84,21 @@ typedef enum gaast_op_kind {
     GAAST_OP_MUL_TERMS = 1,  /* dst += sum terms(left=a, right=b)     eval.rs:61-86 */
     GAAST_OP_NEG_GRADES = 2, /* dst = -dst on grades `mask`           eval.rs:55-60,87-102 */
     GAAST_OP_SCALAR_INV = 3, /* dst[grade 0] = 1/dst[grade 0]         eval.rs:103-110 */
-    GAAST_OP_SCALAR_SQRT = 4 /* dst[grade 0] = sqrt(dst[grade 0])     eval.rs:103-110 */
+    GAAST_OP_SCALAR_SQRT = 4,/* dst[grade 0] = sqrt(dst[grade 0])     eval.rs:103-110 */
+    /* The two ops below have NO reference evaluation: eval.rs:112-113 is `todo!()` for Exponential / Logarithm
+     * (README.md:79 "versor exponentiation & logarithm" is on gaast's roadmap).  They implement this library's
+     * own definition, consistent with the grade rules the reference already has (grade_set.rs:181-197: exp of
+     * a single-graded k-vector holds grades {0, k}; log of <A>_0 + <A>_k holds grade k), for a k-vector B whose
+     * square is a scalar (every blade: any vector, any bivector in dimension <= 3, the bivector of a simple
+     * rotor ...), with q = <B B>_0 = sum_i (e_i)^2 B_i^2 over B's components:
+     *     exp(B)     = c(q) + s(q) B     q < 0: cos x, sin x / x   q > 0: cosh x, sinh x / x   (x = sqrt|q|)   q = 0: 1, 1
+     *     log(a + B) = t(a, q) B         q < 0: atan2(x, a) / x    q > 0: atanh(x / a) / x                     q = 0: 1 / a
+     * (the scalar part ln|a + B| is not part of the reference's grade rule for log: 0 for a unit rotor).
+     * `a` = source buffer (evaluated like a product operand, eval.rs:67-68), `mask` = the single grade k,
+     * terms [term_begin, term_begin + term_count) = one per component of grade k in slot order with
+     * a == b == that component's slot in the source buffer and coeff == the square of its basis blade. */
+    GAAST_OP_EXP = 5,        /* dst += exp(B),      B = grade k of buffer a (the scalar part only if dst holds grade 0) */
+    GAAST_OP_LOG = 6         /* dst += log(a0 + B), a0 = grade 0, B = grade k of buffer a */
 } gaast_op_kind;
 
 typedef struct gaast_op {

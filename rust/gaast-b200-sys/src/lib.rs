@@ -27,6 +27,10 @@ pub const GAAST_OP_MUL_TERMS: u32 = 1; // eval.rs:61-86
 pub const GAAST_OP_NEG_GRADES: u32 = 2; // eval.rs:55-60, 87-102
 pub const GAAST_OP_SCALAR_INV: u32 = 3; // eval.rs:103-110
 pub const GAAST_OP_SCALAR_SQRT: u32 = 4;
+// exp / log of a k-vector with a scalar square: this library's definition (eval.rs:112-113 is todo!() in gaast; the
+// emitter of rust/patches/0002 keeps returning LowerError::Unsupported for those nodes until gaast defines them)
+pub const GAAST_OP_EXP: u32 = 5;
+pub const GAAST_OP_LOG: u32 = 6;
 
 /// gaast_input_kind
 pub const GAAST_INPUT_BATCH: u32 = 0;

@@ -143,6 +143,22 @@ def run_plan_numpy(plan: Dict, inputs: Sequence[Dict[int, np.ndarray]], batch: i
             c0 = col0(plan["buffer_masks"][dst], 0)
             with np.errstate(divide="ignore", invalid="ignore"):
                 bufs[dst][c0] = one / bufs[dst][c0] if kind == 3 else np.sqrt(bufs[dst][c0])
+        elif kind in (5, 6):  # GAAST_OP_EXP / GAAST_OP_LOG: this library's definition (oracle/explog_extension.py)
+            from oracle.explog_extension import exp_factors, log_factor
+            k = grades(mask)[0]
+            s0, d0 = col0(plan["buffer_masks"][a], k), col0(plan["buffer_masks"][dst], k)
+            q = np.zeros(batch, dtype=dtype)
+            for i, (_, ta, _, coeff) in enumerate(plan["terms"][tb:tb + tc]):
+                q = q + bufs[a][ta] * bufs[a][ta] * dtype(coeff)
+            if kind == 5:
+                c, f = exp_factors(q)
+                if plan["buffer_masks"][dst] & 1:
+                    z = col0(plan["buffer_masks"][dst], 0)
+                    bufs[dst][z] = bufs[dst][z] + c.astype(dtype)
+            else:
+                f = log_factor(bufs[a][col0(plan["buffer_masks"][a], 0)], q)
+            for i in range(gd[k]):
+                bufs[dst][d0 + i] = bufs[dst][d0 + i] + f.astype(dtype) * bufs[a][s0 + i]
     out, c = {}, 0
     for k in grades(plan["buffer_masks"][0]):
         out[k] = bufs[0][c:c + gd[k]]
