@@ -342,6 +342,22 @@ gaast_status gaast_plan_precompile_typed(gaast_plan* plan, uint64_t broadcast_sl
         std::string key, origin;
         try {
             gaast::build_specialized(plan->h, opt, &cg, &key, &origin);
+            // ... and the variant gaast_eval takes for a batch it cannot address with 128-bit accesses / TMA row copies (an
+            // odd length or a misaligned pointer in caller-owned memory): one element per thread, no TMA staging.  With both
+            // in the cache no shape of a shipped workload compiles at run time.
+            {
+                gaast::CodegenOptions un = opt;
+                un.elems_per_thread = 1;
+                un.pipelined = false;
+                un.tma_stage = false;
+                gaast::CodegenResult cg2;
+                std::string key2, origin2;
+                try {
+                    gaast::build_specialized(plan->h, un, &cg2, &key2, &origin2);
+                } catch (const Error&) {
+                    // (a plan whose unaligned form does not fit is evaluated by the table engine for such batches)
+                }
+            }
         } catch (const Error&) {
             // too large / too wide to specialise: a full high-dimensional product gets its dense-warp kernel instead
             gaast::DenseWarpHost dw;

@@ -192,6 +192,30 @@ def test_wrap_torch_tensors(ctx):
     assert_close({2: out_t.cpu().numpy()}, want, scale)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg5"])
+def test_odd_length_caller_owned_batches_need_no_runtime_compile(ctx, name):
+    """A batch of odd length in caller-owned memory (row stride == length: no padding to launch into) cannot use
+    128-bit accesses or TMA row copies: gaast_eval takes the one-element-per-thread variant of the kernel.  The build
+    step precompiles that variant too, so nothing compiles at run time, and the result is the oracle's."""
+    import torch
+    w = W.WORKLOADS[name]
+    batch = 1001
+    tin = W.torch_inputs(w, batch, "cuda:0")
+    torch.cuda.synchronize()
+    plan = g.Plan(ctx, W.specialize(w))
+    bcs = [bc for _, bc in w.inputs]
+    dev = [g.DeviceBatch.wrap_torch(ctx, w.n, t, broadcast=bc) for t, bc in zip(tin, bcs)]
+    out_t = {k: torch.empty((comb(w.n, k), batch), dtype=torch.float64, device="cuda:0") for k in plan.root_grades()}
+    plan.eval(dev, out=g.DeviceBatch.wrap_torch(ctx, w.n, out_t), engine=L.ENGINE_AUTO)
+    ctx.sync()
+    kern = plan.last_kernel()
+    assert "engine=specialized" in kern and "origin=cache" in kern and "elems/thread=1" in kern, kern
+    host = [{k: v.cpu().numpy() for k, v in t.items()} for t in tin]
+    want = oracle_eval(w.build, w.metric, host, bcs, batch)
+    scale = oracle_abs_scale(w.build, w.metric, host, bcs, batch)
+    assert_close({k: v.cpu().numpy() for k, v in out_t.items()}, want, scale, what=f"{name} odd wrapped batch")
+
+
 def test_wide_plan_auto_engine_uses_table_engine_with_global_workspace(ctx):
     """G(9,0) full product: 262 144 terms and 1 536 workspace columns -- too large to
     specialise and too wide for shared memory: AUTO runs the table engine with its
