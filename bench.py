@@ -98,6 +98,10 @@ def _ncu_traffic(kernel_desc: str, elements: int):
         return None, f"no ncu capture committed for cubin {key}"
     scale = elements / float(ent["elements"])
     note = ent["source"] + (f" (captured at {ent['elements']} elements, scaled x{scale:g})" if scale != 1.0 else "")
+    if "dram_pct_of_peak" in ent:
+        # the second denominator: what ncu itself calls DRAM throughput in that capture (% of the device's DRAM peak;
+        # MEASURED_PEAKS' copy bandwidth is ~80 % of it)
+        note += f"; gpu__dram_throughput {ent['dram_pct_of_peak']:.1f} % of peak in that capture ({ent.get('ncu_ms', '?')} ms under ncu)"
     return int(ent["dram_bytes"] * scale), note
 
 
