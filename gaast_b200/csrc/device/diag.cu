@@ -43,8 +43,9 @@ extern "C" gaast_status gaast_diag_fp64_peak(gaast_ctx* ctx, double seconds, dou
             }
         } restore{prev, ctx->device};
         constexpr int kIlp = 8, kThreads = 1024;
-        // one launch is ~5 ms at 37 TFLOP/s (a few launches per call: the launch list of a bench run stays readable)
-        const int kIters = seconds >= 0.1 ? 4096 * 20 : 4096;
+        // one launch is ~50 ms at 37 TFLOP/s for a long call (a few launches per call: the launch list of a bench run
+        // stays readable), 0.27 ms for a burst
+        const int kIters = seconds >= 0.1 ? 4096 * 200 : 4096;
         const int grid = ctx->sm_count * 2;
         double* d_out = nullptr;
         if (cudaMalloc(&d_out, 8) != cudaSuccess) throw gaast::Error(GAAST_ERR_OOM, "diag_fp64_peak: cudaMalloc");
