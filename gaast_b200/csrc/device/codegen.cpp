@@ -2176,7 +2176,7 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     // (ptxas treats the hint as a register budget to spend: only give it when it is a tight one)
     // (rolled dense product in f32: 64 left components + a 16 x 16 tile = ~110 registers, 4 blocks per SM)
     const int min_blocks = g.dense_tmem ? 3
-                           : g.dense.op >= 0 ? (opt.f32 ? 4 : 1)
+                           : g.dense.op >= 0 ? (opt.f32 ? 4 : (opt.variant & 524288) ? 3 : 1)  // (bit 19: experiment, 168 registers)
                            : live_regs <= (opt.f32 ? 80u : 40u) ? 8 : live_regs <= (opt.f32 ? 128u : 64u) ? 4 : 1;
     res.min_blocks = min_blocks;
     src << "#define GAAST_EPT " << ept << "\n#define GAAST_THREADS " << threads << "\n#define GAAST_MIN_BLOCKS "
