@@ -109,6 +109,8 @@ PROTOTYPES = {
     "gaast_plan_set_tuning": (C.c_int, vp, C.c_int, C.c_int),
     "gaast_plan_last_kernel": (C.c_char_p, vp),
     "gaast_diag_fp64_peak": (C.c_int, vp, C.c_double, C.POINTER(C.c_double)),
+    "gaast_diag_matrix_rep": (C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                              C.POINTER(C.c_double), C.POINTER(C.c_double)),
     "gaast_batch_alloc": (C.c_int, vp, u32, u32, u64, C.c_int, C.POINTER(vp)),
     "gaast_batch_wrap": (C.c_int, vp, u32, u32, u64, u64, C.c_int, C.POINTER(vp), C.POINTER(vp)),
     "gaast_batch_alloc_typed": (C.c_int, vp, u32, u32, u64, C.c_int, C.c_int, C.POINTER(vp)),

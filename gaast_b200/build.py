@@ -35,11 +35,12 @@ SOURCES = [
     "device/comm.cpp",
     "device/table_engine.cu",
     "device/dense_warp.cu",
+    "device/dense_matrix.cu",
     "device/runtime.cu",
     "device/host_pipeline.cu",
     "device/diag.cu",
 ]
-HEADERS = ["common.hpp", "device_plan.hpp", "runtime.hpp", "eval_args.h", "host/host.hpp", "device/dense_warp_kernel.h",
+HEADERS = ["common.hpp", "device_plan.hpp", "runtime.hpp", "eval_args.h", "host/host.hpp", "device/dense_warp_kernel.h", "device/dense_matrix_kernel.h",
            "../../include/gaast_b200.h", "../../include/gaast_b200_host.h"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -59,6 +60,13 @@ def _write_args_text():
     src = os.path.join(CSRC, "device", "dense_warp_kernel.h")
     dst = os.path.join(CSRC, "device", "dense_warp_kernel_text.inc")
     text = 'R"GAASTDW(' + open(src).read() + ')GAASTDW"\n'
+    if not os.path.exists(dst) or open(dst).read() != text:
+        with open(dst, "w") as f:
+            f.write(text)
+    # ... and the matrix-representation kernel of the same engine (one NVRTC build per tile shape)
+    src = os.path.join(CSRC, "device", "dense_matrix_kernel.h")
+    dst = os.path.join(CSRC, "device", "dense_matrix_kernel_text.inc")
+    text = 'R"GAASTDM(' + open(src).read() + ')GAASTDM"\n'
     if not os.path.exists(dst) or open(dst).read() != text:
         with open(dst, "w") as f:
             f.write(text)

@@ -72,7 +72,10 @@ std::vector<uint16_t> blades_of_mask(uint32_t n, uint32_t mask) {
 // Tables of ONE product op: which pairs it keeps and with which sign, factorised over (high, low) parts.
 // maskL / maskR / maskO: grade sets of the operand buffers and of the destination buffer.
 bool analyse_product(const DevicePlanHost& h, const gaast_op& mul, uint32_t maskL, uint32_t maskR, uint32_t maskO,
-                     DenseWarpProduct* out) {
+                     DenseWarpProduct* out, bool* is_geometric, uint32_t* metric_neg) {
+    *is_geometric = false;
+    *metric_neg = 0;
+    bool geometric = false;
     const uint32_t n = h.n, NB = 1u << n, J = NB / 32, full = (2u << n) - 1;
     if (mul.term_count > uint64_t(NB) * NB || mul.term_count < 1) return false;
     const std::vector<uint16_t> bl_of = blades_of_mask(n, maskL), br_of = blades_of_mask(n, maskR), bo_of = blades_of_mask(n, maskO);
@@ -127,7 +130,9 @@ bool analyse_product(const DevicePlanHost& h, const gaast_op& mul, uint32_t mask
                 const bool want = bool(sigma[ah * J + bh] == 1) ^ chi(ah, bl) ^ bool(lambda_words[al] >> bl & 1);
                 if (want != is_neg(ab, bb)) return false;
             }
+        geometric = complete;
     } else {
+        geometric = true;
         // Grade-restricted buffers (rotors: even grades only, ...).  The kernel runs the COMPLETE product on operands
         // padded with zeros and stores the destination's grades only, so the pairs the plan lacks must be
         // exactly those a grade set explains (a geometric product restricted by its buffers) ...
@@ -191,6 +196,34 @@ bool analyse_product(const DevicePlanHost& h, const gaast_op& mul, uint32_t mask
                 if (lm[al * 32 + bl] > 0) lambda_words[al] |= 1u << bl;
         }
     }
+    // Is it a geometric product under a +-1 metric (every pair the grade sets allow, the signs of algebra.rs:73-83)?
+    // Then the matrix-representation kernel applies (dense_matrix.cu).  The metric is read off pairs that share
+    // exactly one generator and the whole table is verified against it.
+    if (geometric) {
+        uint32_t neg_mask = 0, known = 0;
+        auto reorder = [](uint32_t a, uint32_t b) {
+            int c = 0;
+            for (uint32_t t = a >> 1; t; t >>= 1) c += __builtin_popcount(t & b);
+            return (c & 1) != 0;
+        };
+        for (uint32_t ab = 0; ab < NB && known != NB - 1; ++ab)
+            for (uint32_t bb = 0; bb < NB; ++bb) {
+                const uint32_t common = ab & bb;
+                if (__builtin_popcount(common) != 1 || (known & common) || !present(ab, bb)) continue;
+                known |= common;
+                if (is_neg(ab, bb) != reorder(ab, bb)) neg_mask |= common;
+            }
+        bool ok = known == NB - 1;
+        for (uint32_t ab = 0; ab < NB && ok; ++ab)
+            for (uint32_t bb = 0; bb < NB; ++bb)
+                if (present(ab, bb) &&
+                    is_neg(ab, bb) != (reorder(ab, bb) != bool(__builtin_popcount(ab & bb & neg_mask) & 1))) {
+                    ok = false;
+                    break;
+                }
+        *is_geometric = ok;
+        *metric_neg = neg_mask;
+    }
     out->lambda_words = std::move(lambda_words);
     out->present_words = std::move(present_words);
     out->sigma = sigma;
@@ -210,7 +243,7 @@ bool analyse_product(const DevicePlanHost& h, const gaast_op& mul, uint32_t mask
 // product -- on success.
 bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
     const uint32_t n = h.n;
-    if (n < 7 || n > 10) return false;
+    if (n < 7 || n > 12) return false;  // (n = 11, 12: through the matrix-representation kernel only)
     const uint32_t NB = 1u << n;
     std::vector<uint16_t> blade_of = blades_of_mask(n, (2u << n) - 1);
     std::vector<int> gstart(n + 2, 0);
@@ -271,7 +304,9 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
                 l.frozen = r.frozen = true;
                 DenseWarpStep step;
                 // (an input-backed buffer may hold fewer grades than it declares: the missing ones are zeros either way)
-                if (!analyse_product(h, op, h.buffer_masks[op.a], h.buffer_masks[op.b], bm, &step.prod)) return false;
+                if (!analyse_product(h, op, h.buffer_masks[op.a], h.buffer_masks[op.b], bm, &step.prod, &step.geometric,
+                                     &step.neg_mask))
+                    return false;
                 auto source = [&](const State& s) {
                     DenseWarpOperand o;
                     o.grade_mask = s.mask;
@@ -320,6 +355,16 @@ bool dense_warp_analyse(const DevicePlanHost& h, DenseWarpHost* out) {
     prog.n_scratch = n_scratch;
     prog.complete = true;
     for (const DenseWarpStep& s : prog.steps) prog.complete = prog.complete && s.prod.complete;
+    // one +-1 metric behind every product, all of them geometric: the matrix-representation kernel can run the chain
+    bool all_geometric = true;
+    for (const DenseWarpStep& s : prog.steps)
+        all_geometric = all_geometric && s.geometric && s.neg_mask == prog.steps.front().neg_mask;
+    if (all_geometric) {
+        auto rep = std::make_shared<MatrixRep>();
+        if (matrix_rep_plan(n, prog.steps.front().neg_mask, rep.get()) && rep->mx >= 3 && rep->db + rep->dl >= 3)
+            prog.mat = std::move(rep);
+    }
+    if (n > 10 && !prog.mat) return false;  // the term-by-term kernel holds 2^n / 32 <= 32 accumulators per lane
     prog.blade_of_slot = std::move(blade_of);
     prog.gstart = std::move(gstart);
     (void)NB;

@@ -73,3 +73,23 @@ extern "C" gaast_status gaast_diag_fp64_peak(gaast_ctx* ctx, double seconds, dou
         return e.status;
     }
 }
+
+extern "C" gaast_status gaast_diag_matrix_rep(uint32_t n, uint32_t neg_mask, int32_t* shape, const double* a, const double* b,
+                                              double* c) {
+    try {
+        gaast::MatrixRep rep;
+        if (n < 7 || n > 12 || !gaast::matrix_rep_plan(n, neg_mask, &rep))
+            throw gaast::Error(GAAST_ERR_UNSUPPORTED, "no matrix representation the dense engine can use for this algebra");
+        if (shape) {
+            shape[0] = rep.mx;
+            shape[1] = rep.db;
+            shape[2] = rep.dl;
+            shape[3] = rep.has_lx ? 1 : 0;
+        }
+        if (a && b && c) gaast::matrix_rep_apply(rep, a, b, c);
+        return GAAST_OK;
+    } catch (const gaast::Error& e) {
+        gaast::set_last_error(e.what());
+        return e.status;
+    }
+}

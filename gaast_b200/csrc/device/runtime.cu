@@ -257,6 +257,9 @@ gaast_status gaast_plan_destroy(gaast_plan* plan) {
             cudaFree(plan->d_ws);
             cudaFree(plan->d_uniform);
             cudaFree(plan->d_dw_blades);
+            cudaFree(plan->d_dm_src);
+            cudaFree(plan->d_dm_lx);
+            plan->dm_jit.clear();
             plan->dw_jit.clear();
             for (double* p : plan->d_dw_scratch) cudaFree(p);
         }
@@ -372,6 +375,15 @@ gaast_status gaast_plan_precompile_typed(gaast_plan* plan, uint64_t broadcast_sl
                 gaast::jit_cubin(cg, &key, &origin, &log);
             }
             cg.notes += " x" + std::to_string(dw.steps.size()) + " product(s)";
+            if (dw.mat && !(plan->variant & 1048576)) {  // a chain of geometric products: its matrix-representation kernel
+                cg = gaast::dense_matrix_codegen(*dw.mat, gaast::dense_matrix_shape(fake, *dw.mat, 1 << 20));
+                std::string log;
+                gaast::jit_cubin(cg, &key, &origin, &log);
+                const size_t used = log.find("Used ", log.find("Function properties for " + cg.kernel_name));
+                if (used != std::string::npos)
+                    cg.notes += " regs=" + std::to_string(std::atoi(log.c_str() + used + 5)) +
+                                " spill=" + std::to_string(gaast::spill_bytes_from_log(log, cg.kernel_name)) + "B";
+            }
         }
         plan->last_kernel = cg.kernel_name + " key=" + key + " origin=" + origin + " fma/elem=" + std::to_string(cg.fma_per_elem) +
                             " " + cg.notes;
@@ -642,14 +654,44 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
             return nullptr;
         }
     };
+    // ... and the matrix-representation kernel of a chain of geometric products (dense_matrix.cu): one per tile shape,
+    // shared by every signature of that shape; null when it is switched off (variant bit 20) or cannot be built
+    auto dense_matrix_kernel_for = [&](const gaast::DenseMatLaunch& shape) -> std::shared_ptr<gaast::JitKernel> {
+        if (!plan->dense_warp.mat || plan->dm_jit_failed || (plan->variant & 1048576)) return nullptr;
+        auto it = plan->dm_jit.find(shape.T);
+        if (it != plan->dm_jit.end()) return it->second;
+        try {
+            gaast::CodegenResult cg = gaast::dense_matrix_codegen(*plan->dense_warp.mat, shape);
+            std::string key, origin, log;
+            std::vector<char> cubin = gaast::jit_cubin(cg, &key, &origin, &log);
+            auto k = gaast::jit_load(cg, cubin);
+            k->key = key;
+            k->origin = origin;
+            k->fma_per_elem = cg.fma_per_elem;
+            plan->dm_jit.emplace(shape.T, k);
+            return k;
+        } catch (const Error&) {
+            plan->dm_jit_failed = true;
+            return nullptr;
+        }
+    };
     // usable for this call?  (a chain of dense products, f64, FMA arithmetic, per-element operands)
     auto dense_warp_ready = [&]() {
         if (with_sum || f32 || arith != GAAST_ARITH_FMA || !out) return false;
         if (plan->dense_warp_state == 0) {
             plan->dense_warp_state = gaast::dense_warp_analyse(h, &plan->dense_warp) ? 1 : -1;
-            if (plan->dense_warp_state == 1) upload(plan->d_dw_blades, plan->dense_warp.blade_of_slot, ctx->stream);
+            if (plan->dense_warp_state == 1) {
+                upload(plan->d_dw_blades, plan->dense_warp.blade_of_slot, ctx->stream);
+                if (plan->dense_warp.mat) {
+                    upload(plan->d_dm_src, gaast::matrix_rep_device_table(*plan->dense_warp.mat), ctx->stream);
+                    upload(plan->d_dm_lx, plan->dense_warp.mat->lx, ctx->stream);
+                }
+            }
         }
         if (plan->dense_warp_state != 1) return false;
+        if (h.n > 10 &&  // no term-by-term kernel above n = 10: the matrix kernel or nothing
+            !(plan->dense_warp.mat && dense_matrix_kernel_for(gaast::dense_matrix_shape(*ctx, *plan->dense_warp.mat, n))))
+            return false;
         // products that drop pairs (outer products, contractions) need their per-plan kernel
         if (!plan->dense_warp.complete) {
             const gaast::DenseWarpLaunch shape = gaast::dense_warp_shape(*ctx, h.n, n);
@@ -776,7 +818,33 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
             return b;
         };
         std::shared_ptr<gaast::JitKernel> dwk;
-        for (size_t i = 0; i < prog.steps.size(); ++i) {
+        gaast::DenseMatLaunch mshape;
+        std::shared_ptr<gaast::JitKernel> dmk;
+        if (prog.mat) {
+            mshape = gaast::dense_matrix_shape(*ctx, *prog.mat, n);
+            dmk = dense_matrix_kernel_for(mshape);
+        }
+        for (size_t i = 0; i < prog.steps.size() && dmk; ++i) {
+            const gaast::DenseWarpStep& step = prog.steps[i];
+            cuda_check(gaast::dense_matrix_launch(prog, step, buffers_of(step.L), buffers_of(step.R), buffers_of(step.O),
+                                                  step.C.slot >= 0 ? buffers_of(step.C) : gaast::DenseWarpBuffers(), n,
+                                                  plan->d_dm_src, prog.mat->has_lx ? plan->d_dm_lx : nullptr, mshape,
+                                                  dmk->kernel, ctx->stream),
+                       "launch dense-matrix kernel");
+            ctx->launches++;
+        }
+        if (dmk) {
+            grid = mshape.grid;
+            char desc[400];
+            std::snprintf(desc, sizeof desc,
+                          "gaast_dense_matrix engine=dense_warp kernel=matrix origin=%s products=%zu grid=%d block=%d smem=%zu "
+                          "tile=%d elements regs=%d spill=%zuB blocks/SM=%d fma/elem=%d key=%s M%d x%d cols=%d",
+                          dmk->origin.c_str(), prog.steps.size(), grid, mshape.threads, mshape.smem, mshape.T, dmk->regs,
+                          dmk->local_bytes, mshape.blocks_per_sm, dmk->fma_per_elem, dmk->key.c_str(), 1 << prog.mat->mx,
+                          1 << prog.mat->db, 1 << prog.mat->dl);
+            plan->last_kernel = desc;
+        }
+        for (size_t i = 0; i < prog.steps.size() && !dmk; ++i) {
             const gaast::DenseWarpStep& step = prog.steps[i];
             dwk = dense_warp_kernel_for(int(i), shape);
             cuda_check(gaast::dense_warp_launch(prog, step, buffers_of(step.L), buffers_of(step.R), buffers_of(step.O),
@@ -785,12 +853,14 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                        "launch dense-warp engine");
             ctx->launches++;
         }
-        char desc[320];
-        std::snprintf(desc, sizeof desc,
-                      "%s engine=dense_warp origin=%s products=%zu grid=%d block=%d smem=%zu tile=%d elements regs=%d",
-                      dwk ? "gaast_dense_warp" : "dense_warp_kernel", dwk ? dwk->origin.c_str() : "library", prog.steps.size(),
-                      grid, shape.threads, shape.smem, shape.T, dwk ? dwk->regs : 0);
-        plan->last_kernel = desc;
+        if (!dmk) {
+            char desc[320];
+            std::snprintf(desc, sizeof desc,
+                          "%s engine=dense_warp origin=%s products=%zu grid=%d block=%d smem=%zu tile=%d elements regs=%d",
+                          dwk ? "gaast_dense_warp" : "dense_warp_kernel", dwk ? dwk->origin.c_str() : "library",
+                          prog.steps.size(), grid, shape.threads, shape.smem, shape.T, dwk ? dwk->regs : 0);
+            plan->last_kernel = desc;
+        }
     } else if (jk) {
         const long long per_block = (long long)jk->threads * jk->elems_per_thread;
         const long long blocks = (n + per_block - 1) / per_block;

@@ -123,12 +123,27 @@ struct DenseWarpOperand {   // where a full-grade buffer lives when a product re
 };
 struct DenseWarpStep {
     DenseWarpProduct prod;
+    bool geometric = false;   // keeps every pair its buffers' grades allow, signs of a +-1 metric: the matrix kernel applies
+    uint32_t neg_mask = 0;    // that metric (bit i: e_i^2 = -1)
     DenseWarpOperand L, R, O;
     bool accumulate = false;  // O already holds an earlier product of the same sum: add to it
     DenseWarpOperand C;       // optional addend (slot >= 0): a batch input summed into the same buffer
 };
+// dense_matrix.cu: the real matrix representation of G(p,q) the matrix kernel of the dense engine multiplies in
+struct MatrixRep {
+    uint32_t n = 0, neg_mask = 0;  // bit i of neg_mask: e_i^2 = -1
+    int mx = 0, db = 0, dl = 0;    // 2^db products of 2^mx x 2^mx by 2^mx x 2^dl matrices per element
+    std::vector<uint32_t> entry;   // [2^n], index x * 2^(db+dl) + t: blade bitmask | sign << 31
+    std::vector<uint8_t> lx;       // [2^mx]: sign mask of the left matrix, M(a)[i][l] *= (-1)^popc(lx[i ^ l] & l)
+    bool has_lx = false;
+};
+struct DenseMatLaunch {
+    int T = 0, RC = 1, threads = 0, grid = 0, blocks_per_sm = 1;
+    size_t smem = 0;
+};
 struct DenseWarpHost {
     uint32_t n = 0;
+    std::shared_ptr<MatrixRep> mat;       // set when every product is a geometric product under one +-1 metric
     std::vector<uint16_t> blade_of_slot;  // [2^n]
     std::vector<int> gstart;              // first slot of grade k
     std::vector<DenseWarpStep> steps;     // one per product, in the plan's order
@@ -151,6 +166,15 @@ cudaError_t dense_warp_launch(const DenseWarpHost& prog, const DenseWarpStep& st
                               const uint16_t* d_blade_of_slot, const DenseWarpLaunch& shape, cudaKernel_t jit_kernel,
                               cudaStream_t stream);
 CodegenResult dense_warp_codegen(uint32_t n, const DenseWarpProduct& prod, const DenseWarpLaunch& shape);
+bool matrix_rep_plan(uint32_t n, uint32_t neg_mask, MatrixRep* out);
+void matrix_rep_apply(const MatrixRep& rep, const double* a, const double* b, double* c);
+std::vector<uint32_t> matrix_rep_device_table(const MatrixRep& rep);
+DenseMatLaunch dense_matrix_shape(const gaast_ctx& ctx, const MatrixRep& rep, long long batch);
+CodegenResult dense_matrix_codegen(const MatrixRep& rep, const DenseMatLaunch& shape);
+cudaError_t dense_matrix_launch(const DenseWarpHost& prog, const DenseWarpStep& step, const DenseWarpBuffers& L,
+                                const DenseWarpBuffers& R, const DenseWarpBuffers& O, const DenseWarpBuffers& C, long long batch,
+                                const uint32_t* d_src, const uint8_t* d_lx, const DenseMatLaunch& shape, cudaKernel_t kernel,
+                                cudaStream_t stream);
 
 // host_pipeline.cu
 struct HostPipe;
@@ -215,4 +239,9 @@ struct gaast_plan {
     std::vector<double*> d_dw_scratch;  // intermediate products: [2^n][stride] each
     size_t dw_scratch_stride = 0;
     bool dw_jit_failed = false;  // NVRTC unavailable: keep using the generic kernel
+    // ... its matrix-representation kernel (dense_matrix.cu): tables of the algebra, one kernel per tile shape
+    uint32_t* d_dm_src = nullptr;
+    uint8_t* d_dm_lx = nullptr;
+    std::map<int, std::shared_ptr<gaast::JitKernel>> dm_jit;  // by elements per tile
+    bool dm_jit_failed = false;
 };

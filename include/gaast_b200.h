@@ -330,6 +330,15 @@ gaast_status gaast_comm_destroy(gaast_comm* comm);
  * power-capped one.  Synchronous. */
 gaast_status gaast_diag_fp64_peak(gaast_ctx* ctx, double seconds, double* tflops);
 
+/* Diagnostic, no device needed: the real matrix representation the dense engine's matrix kernel uses for the
+ * geometric product of G(n) with a +-1 metric (bit i of neg_mask set: e_i^2 = -1; csrc/device/dense_matrix.cu).
+ * shape[0..3] receive MX, DB, DL, has_lx: 2^DB products of 2^MX x 2^MX by 2^MX x 2^DL matrices per element, i.e.
+ * 2^(n + MX) multiplications instead of 4^n.  When a, b, c are non-null, c = a b is computed ON THE HOST through
+ * that representation (2^n doubles each, indexed by blade bitmask) -- the mirror of the kernel the tests compare
+ * with the reference's term tables.  GAAST_ERR_UNSUPPORTED when the algebra has no representation the kernel
+ * can use (n < 7, n > 12, degenerate metric). */
+gaast_status gaast_diag_matrix_rep(uint32_t n, uint32_t neg_mask, int32_t* shape, const double* a, const double* b, double* c);
+
 /* Name and launch shape of the kernel the last gaast_eval on this plan used. */
 const char* gaast_plan_last_kernel(const gaast_plan* plan);
 
