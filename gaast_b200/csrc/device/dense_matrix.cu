@@ -50,6 +50,11 @@ namespace {
 
 #include "dense_matrix_kernel.h"
 
+// the prologue of every launch: row addresses of the three multivectors (see DenseMatArgs)
+__global__ void __launch_bounds__(256) dense_matrix_rows_kernel(const __grid_constant__ DenseMatArgs d) {
+    dense_matrix_rows_body(d);
+}
+
 // compile check of the device code inside the library (the kernels that run are built by NVRTC per shape)
 __global__ void __launch_bounds__(GAAST_DM_THREADS) dense_matrix_check_kernel(const __grid_constant__ DenseMatArgs d) {
     dense_matrix_body<4, 0, 4, 16, 1, false>(d);
@@ -343,9 +348,9 @@ DenseMatLaunch dense_matrix_shape(const gaast_ctx& ctx, const MatrixRep& rep, lo
     const size_t budget = (size_t(ctx.smem_optin) - 1024);
     int T = 32;
     const int want_blocks = n >= 12 ? 1 : n >= 10 ? 2 : 3;
-    while (T > 1 && (2 * NW * size_t(T | 1) * sizeof(double) + 1024) * size_t(want_blocks) > budget) T /= 2;
+    while (T > 1 && (2 * NW * size_t(T) * sizeof(double) + 1024) * size_t(want_blocks) > budget) T /= 2;
     s.T = T;
-    s.smem = 2 * NW * size_t(T | 1) * sizeof(double);
+    s.smem = 2 * NW * size_t(T) * sizeof(double);
     s.threads = 256;
     s.blocks_per_sm = std::max(1, std::min(int(budget / (s.smem + 1024)), 2048 / s.threads));
     if (rep.db + rep.dl >= 5) s.blocks_per_sm = std::min(s.blocks_per_sm, 2);  // 32 transform values per thread: 128 registers
@@ -383,12 +388,16 @@ CodegenResult dense_matrix_codegen(const MatrixRep& rep, const DenseMatLaunch& s
 
 cudaError_t dense_matrix_launch(const DenseWarpHost& prog, const DenseWarpStep& step, const DenseWarpBuffers& L,
                                 const DenseWarpBuffers& R, const DenseWarpBuffers& O, const DenseWarpBuffers& C, long long batch,
-                                const uint32_t* d_src, const uint8_t* d_lx, const DenseMatLaunch& shape, cudaKernel_t kernel,
-                                cudaStream_t stream) {
+                                const uint32_t* d_src, const uint8_t* d_lx, unsigned long long* d_rows, const DenseMatLaunch& shape,
+                                cudaKernel_t kernel, cudaStream_t stream) {
     DenseMatArgs d;
     std::memset(&d, 0, sizeof d);
     d.src = d_src;
     d.lx = d_lx;
+    d.rowsL = d_rows;
+    d.rowsR = d_rows + (size_t(1) << prog.n);
+    d.rowsO = d_rows + (size_t(2) << prog.n);
+    d.n = int(prog.n);
     d.batch = batch;
     for (uint32_t k = 0; k <= prog.n; ++k) {
         d.Lp[k] = L.ptr[k];
@@ -412,6 +421,9 @@ cudaError_t dense_matrix_launch(const DenseWarpHost& prog, const DenseWarpStep& 
     d.Lneg = step.L.neg_mask;
     d.Rneg = step.R.neg_mask;
     d.Oneg = step.O.neg_mask;
+    dense_matrix_rows_kernel<<<((1u << prog.n) + 255) / 256, 256, 0, stream>>>(d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     void* params[] = {&d};
     return cudaLaunchKernel(reinterpret_cast<const void*>(kernel), dim3(shape.grid), dim3(shape.threads), params, shape.smem,
                             stream);

@@ -259,6 +259,7 @@ gaast_status gaast_plan_destroy(gaast_plan* plan) {
             cudaFree(plan->d_dw_blades);
             cudaFree(plan->d_dm_src);
             cudaFree(plan->d_dm_lx);
+            cudaFree(plan->d_dm_rows);
             plan->dm_jit.clear();
             plan->dw_jit.clear();
             for (double* p : plan->d_dw_scratch) cudaFree(p);
@@ -685,6 +686,8 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                 if (plan->dense_warp.mat) {
                     upload(plan->d_dm_src, gaast::matrix_rep_device_table(*plan->dense_warp.mat), ctx->stream);
                     upload(plan->d_dm_lx, plan->dense_warp.mat->lx, ctx->stream);
+                    cuda_check(cudaMalloc(&plan->d_dm_rows, (size_t(3) << h.n) * sizeof(unsigned long long)),
+                               "cudaMalloc(dense-matrix row tables)");
                 }
             }
         }
@@ -828,10 +831,10 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
             const gaast::DenseWarpStep& step = prog.steps[i];
             cuda_check(gaast::dense_matrix_launch(prog, step, buffers_of(step.L), buffers_of(step.R), buffers_of(step.O),
                                                   step.C.slot >= 0 ? buffers_of(step.C) : gaast::DenseWarpBuffers(), n,
-                                                  plan->d_dm_src, prog.mat->has_lx ? plan->d_dm_lx : nullptr, mshape,
+                                                  plan->d_dm_src, plan->d_dm_lx, plan->d_dm_rows, mshape,
                                                   dmk->kernel, ctx->stream),
                        "launch dense-matrix kernel");
-            ctx->launches++;
+            ctx->launches += 2;  // the row-address prologue and the product
         }
         if (dmk) {
             grid = mshape.grid;

@@ -173,8 +173,8 @@ DenseMatLaunch dense_matrix_shape(const gaast_ctx& ctx, const MatrixRep& rep, lo
 CodegenResult dense_matrix_codegen(const MatrixRep& rep, const DenseMatLaunch& shape);
 cudaError_t dense_matrix_launch(const DenseWarpHost& prog, const DenseWarpStep& step, const DenseWarpBuffers& L,
                                 const DenseWarpBuffers& R, const DenseWarpBuffers& O, const DenseWarpBuffers& C, long long batch,
-                                const uint32_t* d_src, const uint8_t* d_lx, const DenseMatLaunch& shape, cudaKernel_t kernel,
-                                cudaStream_t stream);
+                                const uint32_t* d_src, const uint8_t* d_lx, unsigned long long* d_rows, const DenseMatLaunch& shape,
+                                cudaKernel_t kernel, cudaStream_t stream);
 
 // host_pipeline.cu
 struct HostPipe;
@@ -242,6 +242,7 @@ struct gaast_plan {
     // ... its matrix-representation kernel (dense_matrix.cu): tables of the algebra, one kernel per tile shape
     uint32_t* d_dm_src = nullptr;
     uint8_t* d_dm_lx = nullptr;
+    unsigned long long* d_dm_rows = nullptr;  // per-launch row address tables: 3 x 2^n
     std::map<int, std::shared_ptr<gaast::JitKernel>> dm_jit;  // by elements per tile
     bool dm_jit_failed = false;
 };
