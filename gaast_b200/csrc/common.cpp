@@ -33,6 +33,9 @@ static Tuning read_tuning() {
         v.host_chunk_mib = std::max(1, num("GAAST_HOST_CHUNK_MIB", 32));
         v.no_kernel_cache = flag("GAAST_NO_KERNEL_CACHE");
         v.dense_table_rows = flag("GAAST_DENSE_TABLE_ROWS");
+        v.dm_tile = std::max(0, num("GAAST_DM_TILE", 0));
+        v.dm_blocks = std::max(0, num("GAAST_DM_BLOCKS", 0));
+        v.dm_threads = std::max(0, num("GAAST_DM_THREADS", 0));
         v.codegen_debug = flag("GAAST_CODEGEN_DEBUG");
         v.test_hooks = flag("GAAST_TEST_HOOKS");
         if (v.test_hooks) v.kernel_cache_override = str("GAAST_KERNEL_CACHE");

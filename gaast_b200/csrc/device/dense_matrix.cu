@@ -341,23 +341,32 @@ std::vector<uint32_t> matrix_rep_device_table(const MatrixRep& rep) {
 }
 
 DenseMatLaunch dense_matrix_shape(const gaast_ctx& ctx, const MatrixRep& rep, long long batch) {
+    // Measured on B200 (profiles/r2_dense_matrix_tuning.txt): the kernel is bound by the latency of its gathers -- 2^(n+1)
+    // rows, T * 8 bytes of each per tile -- so what pays is (i) ONE (element, x) pair per thread with all of its
+    // 2 * 2^D0 loads in flight at once (128 registers per thread or more), (ii) row pieces of at least 64 bytes
+    // (T >= 8) where shared memory allows, (iii) two blocks per SM rather than one when both still satisfy (i), (ii).
     DenseMatLaunch s;
-    const int n = int(rep.n);
-    const size_t NW = size_t(1) << n;
-    // elements per tile: as many as keep three blocks (two for n >= 10) on an SM
-    const size_t budget = (size_t(ctx.smem_optin) - 1024);
-    int T = 32;
-    const int want_blocks = n >= 12 ? 1 : n >= 10 ? 2 : 3;
-    while (T > 1 && (2 * NW * size_t(T) * sizeof(double) + 1024) * size_t(want_blocks) > budget) T /= 2;
+    const size_t NW = size_t(1) << rep.n;
+    const int K = 1 << rep.mx, NT = 1 << (rep.db + rep.dl);
+    const size_t budget = size_t(ctx.smem_optin) - 1024;
+    auto smem_of = [&](int t) { return 2 * NW * size_t(t) * sizeof(double); };
+    int T = std::max(1, (NT <= 8 ? 512 : 256) / K);  // (8 coefficients per operand and pair: two pairs per thread)
+    while (T > 1 && smem_of(T) + 1024 > budget) T /= 2;
+    if (NT >= 32 && T >= 16 && (smem_of(T) + 1024) * 2 > budget) T /= 2;  // n = 9: two blocks of 8 elements
+    if (tuning().dm_tile && smem_of(tuning().dm_tile) + 1024 <= budget) T = tuning().dm_tile;
     s.T = T;
-    s.smem = 2 * NW * size_t(T) * sizeof(double);
-    s.threads = 256;
-    s.blocks_per_sm = std::max(1, std::min(int(budget / (s.smem + 1024)), 2048 / s.threads));
-    if (rep.db + rep.dl >= 5) s.blocks_per_sm = std::min(s.blocks_per_sm, 2);  // 32 transform values per thread: 128 registers
+    s.smem = smem_of(T);
+    s.threads = std::min(256, std::max(64, K * T));
+    const int pairs = (K * T + s.threads - 1) / s.threads;
+    if (tuning().dm_threads) s.threads = tuning().dm_threads;
+    // registers: 2 * pairs * 2^D0 loaded doubles per thread, all live at once
+    const int by_regs = std::max(1, 65536 / (s.threads * (pairs * NT >= 32 ? 256 : pairs * NT >= 16 ? 128 : 80)));
+    s.blocks_per_sm = std::max(1, std::min(int(budget / (s.smem + 1024)), by_regs));
+    if (tuning().dm_blocks) s.blocks_per_sm = std::max(1, std::min(int(budget / (s.smem + 1024)), tuning().dm_blocks));
     // row chunks: at least one item per warp, at most 32 accumulator doubles per item
-    const int K = 1 << rep.mx, NTI = std::max(1, (1 << rep.dl) / 8);
+    const int NTI = std::max(1, (1 << rep.dl) / 8);
     int RC = 1;
-    while ((T << rep.db) * RC < 8 && K / (RC * 2) >= 8) RC *= 2;
+    while ((T << rep.db) * RC < s.threads / 32 && K / (RC * 2) >= 8) RC *= 2;
     while ((K / RC / 8) * NTI * 2 > 32 && K / (RC * 2) >= 8) RC *= 2;
     s.RC = RC;
     const long long tiles = (batch + T - 1) / T;
@@ -369,6 +378,7 @@ CodegenResult dense_matrix_codegen(const MatrixRep& rep, const DenseMatLaunch& s
     std::string src = "// generated by gaast_b200: matrix-representation kernel of the dense engine, shape MX=" +
                       std::to_string(rep.mx) + " DB=" + std::to_string(rep.db) + " DL=" + std::to_string(rep.dl) +
                       " T=" + std::to_string(shape.T) + " RC=" + std::to_string(shape.RC) + "\n";
+    src += "#define GAAST_DM_THREADS " + std::to_string(shape.threads) + "\n";
     src += kDenseMatrixKernelText;
     src += "\nextern \"C\" __global__ void __launch_bounds__(GAAST_DM_THREADS, " + std::to_string(shape.blocks_per_sm) +
            ") gaast_dense_matrix(const __grid_constant__ DenseMatArgs d) {\n  dense_matrix_body<" + std::to_string(rep.mx) +
