@@ -350,7 +350,7 @@ DenseMatLaunch dense_matrix_shape(const gaast_ctx& ctx, const MatrixRep& rep, lo
     const int K = 1 << rep.mx, NT = 1 << (rep.db + rep.dl);
     const size_t budget = size_t(ctx.smem_optin) - 1024;
     auto smem_of = [&](int t) { return 2 * NW * size_t(t) * sizeof(double); };
-    int T = std::max(1, (NT <= 8 ? 512 : 256) / K);  // (8 coefficients per operand and pair: two pairs per thread)
+    int T = std::max(1, 256 / K);
     while (T > 1 && smem_of(T) + 1024 > budget) T /= 2;
     if (NT >= 32 && T >= 16 && (smem_of(T) + 1024) * 2 > budget) T /= 2;  // n = 9: two blocks of 8 elements
     if (tuning().dm_tile && smem_of(tuning().dm_tile) + 1024 <= budget) T = tuning().dm_tile;
@@ -360,7 +360,7 @@ DenseMatLaunch dense_matrix_shape(const gaast_ctx& ctx, const MatrixRep& rep, lo
     const int pairs = (K * T + s.threads - 1) / s.threads;
     if (tuning().dm_threads) s.threads = tuning().dm_threads;
     // registers: 2 * pairs * 2^D0 loaded doubles per thread, all live at once
-    const int by_regs = std::max(1, 65536 / (s.threads * (pairs * NT >= 32 ? 256 : pairs * NT >= 16 ? 128 : 80)));
+    const int by_regs = std::max(1, 65536 / (s.threads * (pairs * NT >= 32 ? 256 : NT >= 16 ? 128 : 80)));
     s.blocks_per_sm = std::max(1, std::min(int(budget / (s.smem + 1024)), by_regs));
     if (tuning().dm_blocks) s.blocks_per_sm = std::max(1, std::min(int(budget / (s.smem + 1024)), tuning().dm_blocks));
     // row chunks: at least one item per warp, at most 32 accumulator doubles per item

@@ -377,7 +377,9 @@ gaast_status gaast_plan_precompile_typed(gaast_plan* plan, uint64_t broadcast_sl
             }
             cg.notes += " x" + std::to_string(dw.steps.size()) + " product(s)";
             if (dw.mat && !(plan->variant & 1048576)) {  // a chain of geometric products: its matrix-representation kernel
+                const std::string dw_notes = cg.notes;
                 cg = gaast::dense_matrix_codegen(*dw.mat, gaast::dense_matrix_shape(fake, *dw.mat, 1 << 20));
+                cg.notes = dw_notes + " " + cg.notes;
                 std::string log;
                 gaast::jit_cubin(cg, &key, &origin, &log);
                 const size_t used = log.find("Used ", log.find("Function properties for " + cg.kernel_name));

@@ -246,4 +246,22 @@ def precompile_all(verbose: bool = False, fresh: bool = True) -> int:
         if verbose:
             print(f"  {name:10s} f64 arith=fma    sum={int(with_sum)} store=1 variant={variant}: {info}")
         plan.free()
+    # the dense engine's kernels for full products (bench.py's dense entries, tests/test_gpu_dense_matrix.py): one
+    # matrix-representation kernel per SHAPE of the representation (csrc/device/dense_matrix.cu), shared by every
+    # signature of that shape, plus the term-by-term kernel of the benchmarked G(8,0) product
+    from .expr import Input, mv as pmv
+    dense = [([1.0] * 7, None, 0), ([1.0] * 6 + [-1.0], None, 0), ([1.0] * 4 + [-1.0] * 3, None, 0), ([1.0] * 8, None, 0),
+             ([1.0] * 8, None, 1048576), ([1.0] * 9, None, 0), ([1.0] * 10, None, 0), ([1.0] * 11, None, 0),
+             ([1.0] * 8 + [-1.0] * 4, tuple(range(0, 13, 2)), 0)]
+    for metric, grades, variant in dense:
+        n = len(metric)
+        gr = tuple(range(n + 1)) if grades is None else grades
+        plan = Plan(None, (pmv(Input(0, gr)) * pmv(Input(1, gr))).specialize(metric))
+        if variant:
+            plan.set_tuning(0, variant)
+        info = plan.precompile(0, L.ARITH_FMA, False, True, L.F64)
+        count += 1
+        if verbose:
+            print(f"  dense G({sum(m > 0 for m in metric)},{sum(m < 0 for m in metric)}) variant={variant}: {info}")
+        plan.free()
     return count

@@ -158,5 +158,6 @@ extern "C" {
     pub fn gaast_comm_destroy(comm: *mut gaast_comm) -> c_int;
 
     pub fn gaast_diag_fp64_peak(ctx: *mut gaast_ctx, seconds: f64, tflops: *mut f64) -> c_int;
+    pub fn gaast_diag_matrix_rep(n: u32, neg_mask: u32, shape: *mut i32, a: *const f64, b: *const f64, c: *mut f64) -> c_int;
     pub fn gaast_plan_last_kernel(plan: *const gaast_plan) -> *const c_char;
 }

@@ -169,6 +169,10 @@ def test_offline_precompile_of_a_dense_warp_plan():
     a, b = pmv(Input(0, full)), pmv(Input(1, full))
     plan = Plan(None, (a * b).specialize([1.0, 1.0, 1.0, 1.0, -1.0, -1.0, 1.0]))
     info = plan.precompile(0, L.ARITH_FMA, False, True)
+    # a geometric product under a +-1 metric: the matrix-representation kernel of that engine (G(5,2) = M8(C))
+    assert "gaast_dense_matrix" in info and "dense-matrix(n=7 M16 x1 cols=8)" in info and "fma/elem=2048" in info
+    plan.set_tuning(0, 1048576)  # ... and the term-by-term kernel on request
+    info = plan.precompile(0, L.ARITH_FMA, False, True)
     assert "gaast_dense_warp" in info and "dense-warp(n=7)" in info
     bad = Plan(None, (a * b).specialize([1.0] * 6 + [0.0]))
     with pytest.raises(L.GaastError) as ei:
@@ -185,11 +189,15 @@ def test_offline_analysis_of_dense_warp_chains_and_grade_restricted_plans():
     metric = [1.0] * 6 + [-1.0] * 2
     full, even = tuple(range(n + 1)), tuple(range(0, n + 1, 2))
     a, b, r = pmv(Input(0, full)), pmv(Input(1, full)), pmv(Input(2, even))
-    for expr, products in ((a * b, 1), (r * a * r.rev(), 2), ((a ^ b) * r, 2), (-(a * b), 1)):
+    # chains of geometric products get the matrix-representation kernel (G(6,2) = M8(H): 2^(8+5) multiplications), a
+    # chain with an outer product keeps the term-by-term kernel
+    for expr, products, kernel in ((a * b, 1, "gaast_dense_matrix"), (r * a * r.rev(), 2, "gaast_dense_matrix"),
+                                   ((a ^ b) * r, 2, "gaast_dense_warp"), (-(a * b), 1, "gaast_dense_matrix")):
         info = Plan(None, expr.specialize(metric)).precompile(0, L.ARITH_FMA, False, True)
-        assert "gaast_dense_warp" in info and f"x{products} product(s)" in info, info
+        assert kernel in info and f"x{products} product(s)" in info, info
+        assert ("fma/elem=8192" in info) == (kernel == "gaast_dense_matrix"), info
     info = Plan(None, (a * b + a).specialize(metric)).precompile(0, L.ARITH_FMA, False, True)
-    assert "gaast_dense_warp" in info  # an input added into the product's buffer joins the product's store
+    assert "gaast_dense_matrix" in info  # an input added into the product's buffer joins the product's store
     for expr in ((a * b).norm_sq().sqrt() * a, (a * b) * 2.5):  # a scalar op; a literal operand
         with pytest.raises(L.GaastError):
             Plan(None, expr.specialize(metric)).precompile(0, L.ARITH_FMA, False, True)

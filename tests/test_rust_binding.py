@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "gaast_b200.h")
 LIB_RS = os.path.join(ROOT, "rust", "gaast-b200-sys", "src", "lib.rs")
 PATCHES = os.path.join(ROOT, "rust", "patches")
 
-SCALARS = {"int": "c_int", "uint32_t": "u32", "uint64_t": "u64", "uint16_t": "u16", "size_t": "usize", "double": "f64",
+SCALARS = {"int": "c_int", "int32_t": "i32", "uint32_t": "u32", "uint64_t": "u64", "uint16_t": "u16", "size_t": "usize", "double": "f64",
            "float": "f32", "void": "c_void", "char": "c_char", "unsigned char": "u8", "gaast_status": "c_int"}
 
 
