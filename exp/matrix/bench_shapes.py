@@ -20,8 +20,9 @@ for p, q, batch in cases:
     for T, B, nopf, *rest in knobs:
         os.environ["GAAST_DM_THREADS"] = str(rest[0]) if rest else "0"
         os.environ["GAAST_DM_TILE"] = str(T); os.environ["GAAST_DM_BLOCKS"] = str(B)
-        os.environ["GAAST_DM_PREFETCH"] = "0" if nopf else "1"
-        os.environ["GAAST_DM_CLUSTER"] = str(rest[1]) if len(rest) > 1 else "0"
+        os.environ["GAAST_DM_PIPE"] = str(rest[1]) if len(rest) > 1 else "-1"
+        os.environ["GAAST_DM_RC"] = str(rest[2]) if len(rest) > 2 else "0"
+        os.environ["GAAST_DM_CSEP"] = str(rest[3]) if len(rest) > 3 else "-1"
         L.lib.gaast_reload_env()
         plan = g.Plan(ctx, ast)
         out = plan.alloc_output(batch)
@@ -38,7 +39,7 @@ for p, q, batch in cases:
             ms = s.elapsed_time(e) / reps
             k = plan.last_kernel()
             info = " ".join(w for w in k.split() if w.split("=")[0] in ("tile", "regs", "spill", "blocks/SM", "grid", "block"))
-            print(f"G({p},{q}) batch={batch} T={T} B={B} nopf={nopf} thr={rest[0] if rest else 256} cluster={rest[1] if len(rest) > 1 else 1}: {ms:.3f} ms, {batch/ms/1e3:.1f} M products/s, "
+            print(f"G({p},{q}) batch={batch} T={T} B={B} nopf={nopf} thr={rest[0] if rest else 256} pipe={rest[1] if len(rest) > 1 else -1} rc={rest[2] if len(rest) > 2 else 0} csep={rest[3] if len(rest) > 3 else -1}: {ms:.3f} ms, {batch/ms/1e3:.1f} M products/s, "
                   f"{3*(1<<n)*8*batch/ms/1e6:.0f} GB/s  [{info}]", flush=True)
         except Exception as ex:
             print(f"G({p},{q}) T={T} B={B}: {ex}", flush=True)

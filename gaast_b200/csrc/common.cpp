@@ -36,6 +36,9 @@ static Tuning read_tuning() {
         v.dm_tile = std::max(0, num("GAAST_DM_TILE", 0));
         v.dm_blocks = std::max(0, num("GAAST_DM_BLOCKS", 0));
         v.dm_threads = std::max(0, num("GAAST_DM_THREADS", 0));
+        v.dm_pipe = num("GAAST_DM_PIPE", -1);
+        v.dm_csep = num("GAAST_DM_CSEP", -1);
+        v.dm_rc = std::max(0, num("GAAST_DM_RC", 0));
         v.codegen_debug = flag("GAAST_CODEGEN_DEBUG");
         v.test_hooks = flag("GAAST_TEST_HOOKS");
         if (v.test_hooks) v.kernel_cache_override = str("GAAST_KERNEL_CACHE");

@@ -25,6 +25,9 @@ struct Tuning {
     bool no_kernel_cache = false;     // GAAST_NO_KERNEL_CACHE: always compile with NVRTC
     bool dense_table_rows = false;    // GAAST_DENSE_TABLE_ROWS: rolled dense product looks its rows up in a table (A/B runs)
     int dm_threads = 0;               // GAAST_DM_THREADS: block size of that kernel (A/B runs)
+    int dm_rc = 0;                    // GAAST_DM_RC: row chunks per (element, block) of that kernel (A/B runs)
+    int dm_csep = -1;                 // GAAST_DM_CSEP: 0 / 1 = results in their own shared-memory buffer (A/B runs)
+    int dm_pipe = -1;                 // GAAST_DM_PIPE: 0 / 1 = gathers of the next tile in flight across the product (A/B runs)
     int dm_tile = 0, dm_blocks = 0;   // GAAST_DM_TILE / GAAST_DM_BLOCKS: tile and blocks per SM of the dense-matrix kernel (A/B runs)
     bool codegen_debug = false;       // GAAST_CODEGEN_DEBUG
     bool test_hooks = false;          // GAAST_TEST_HOOKS=1: enables kernel_cache_override (tests and timing experiments only)

@@ -349,7 +349,10 @@ DenseMatLaunch dense_matrix_shape(const gaast_ctx& ctx, const MatrixRep& rep, lo
     const size_t NW = size_t(1) << rep.n;
     const int K = 1 << rep.mx, NT = 1 << (rep.db + rep.dl);
     const size_t budget = size_t(ctx.smem_optin) - 1024;
-    auto smem_of = [&](int t) { return 2 * NW * size_t(t) * sizeof(double); };
+    // the results in a third buffer (one barrier and IPW - 1 accumulator sets less) -- measured faster at n = 7, 12, equal
+    // at n = 8, 11, slower at n = 9, 10 (192 KB of shared memory leave 64 KB of L1 for the gathers)
+    s.csep = tuning().dm_csep >= 0 ? tuning().dm_csep != 0 : (rep.n <= 8 || rep.n >= 11);
+    auto smem_of = [&](int t) { return (s.csep ? 3 : 2) * NW * size_t(t) * sizeof(double); };
     int T = std::max(1, 256 / K);
     while (T > 1 && smem_of(T) + 1024 > budget) T /= 2;
     if (NT >= 32 && T >= 16 && (smem_of(T) + 1024) * 2 > budget) T /= 2;  // n = 9: two blocks of 8 elements
@@ -362,13 +365,17 @@ DenseMatLaunch dense_matrix_shape(const gaast_ctx& ctx, const MatrixRep& rep, lo
     // registers: 2 * pairs * 2^D0 loaded doubles per thread, all live at once
     const int by_regs = std::max(1, 65536 / (s.threads * (pairs * NT >= 32 ? 256 : NT >= 16 ? 128 : 80)));
     s.blocks_per_sm = std::max(1, std::min(int(budget / (s.smem + 1024)), by_regs));
+    if (NT == 16 && s.threads == 256) s.blocks_per_sm = 1;  // (n = 8: 32 + 32 doubles in flight want the whole register file)
     if (tuning().dm_blocks) s.blocks_per_sm = std::max(1, std::min(int(budget / (s.smem + 1024)), tuning().dm_blocks));
-    // row chunks: at least one item per warp, at most 32 accumulator doubles per item
+    // row chunks: at least one item per warp, at most 16 accumulator doubles per item (a warp runs its items in turn)
     const int NTI = std::max(1, (1 << rep.dl) / 8);
     int RC = 1;
     while ((T << rep.db) * RC < s.threads / 32 && K / (RC * 2) >= 8) RC *= 2;
-    while ((K / RC / 8) * NTI * 2 > 32 && K / (RC * 2) >= 8) RC *= 2;
+    while ((K / RC / 8) * NTI * 2 > (s.csep ? 16 : 32) && K / (RC * 2) >= 8) RC *= 2;
+    if (tuning().dm_rc && K / tuning().dm_rc >= 8) RC = tuning().dm_rc;
     s.RC = RC;
+    // gathers of the next tile in flight across the product and the scatter: measured faster or equal at every n
+    s.pipe = tuning().dm_pipe >= 0 ? tuning().dm_pipe != 0 : true;
     const long long tiles = (batch + T - 1) / T;
     s.grid = int(std::max<long long>(1, std::min<long long>(tiles, (long long)ctx.sm_count * s.blocks_per_sm)));
     return s;
@@ -383,7 +390,7 @@ CodegenResult dense_matrix_codegen(const MatrixRep& rep, const DenseMatLaunch& s
     src += "\nextern \"C\" __global__ void __launch_bounds__(GAAST_DM_THREADS, " + std::to_string(shape.blocks_per_sm) +
            ") gaast_dense_matrix(const __grid_constant__ DenseMatArgs d) {\n  dense_matrix_body<" + std::to_string(rep.mx) +
            ", " + std::to_string(rep.db) + ", " + std::to_string(rep.dl) + ", " + std::to_string(shape.T) + ", " +
-           std::to_string(shape.RC) + ", " + (rep.has_lx ? "true" : "false") + ">(d);\n}\n";
+           std::to_string(shape.RC) + ", " + (rep.has_lx ? "true" : "false") + ", " + (shape.pipe ? "true" : "false") + ", " + (shape.csep ? "true" : "false") + ">(d);\n}\n";
     CodegenResult cg;
     cg.source = std::move(src);
     cg.kernel_name = "gaast_dense_matrix";

@@ -661,7 +661,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
     // shared by every signature of that shape; null when it is switched off (variant bit 20) or cannot be built
     auto dense_matrix_kernel_for = [&](const gaast::DenseMatLaunch& shape) -> std::shared_ptr<gaast::JitKernel> {
         if (!plan->dense_warp.mat || plan->dm_jit_failed || (plan->variant & 1048576)) return nullptr;
-        auto it = plan->dm_jit.find(shape.threads * 4096 + shape.T * 32 + shape.blocks_per_sm);
+        auto it = plan->dm_jit.find(shape.RC * 4194304 + shape.threads * 8192 + shape.T * 64 + shape.blocks_per_sm * 4 + int(shape.pipe) * 2 + int(shape.csep));
         if (it != plan->dm_jit.end()) return it->second;
         try {
             gaast::CodegenResult cg = gaast::dense_matrix_codegen(*plan->dense_warp.mat, shape);
@@ -671,7 +671,7 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
             k->key = key;
             k->origin = origin;
             k->fma_per_elem = cg.fma_per_elem;
-            plan->dm_jit.emplace(shape.threads * 4096 + shape.T * 32 + shape.blocks_per_sm, k);
+            plan->dm_jit.emplace(shape.RC * 4194304 + shape.threads * 8192 + shape.T * 64 + shape.blocks_per_sm * 4 + int(shape.pipe) * 2 + int(shape.csep), k);
             return k;
         } catch (const Error&) {
             plan->dm_jit_failed = true;

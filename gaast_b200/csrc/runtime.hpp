@@ -139,6 +139,7 @@ struct MatrixRep {
 };
 struct DenseMatLaunch {
     int T = 0, RC = 1, threads = 0, grid = 0, blocks_per_sm = 1;
+    bool pipe = true, csep = true;
     size_t smem = 0;
 };
 struct DenseWarpHost {
