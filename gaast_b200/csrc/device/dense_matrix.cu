@@ -51,7 +51,7 @@ namespace {
 #include "dense_matrix_kernel.h"
 
 // the prologue of every launch: row addresses of the three multivectors (see DenseMatArgs)
-__global__ void __launch_bounds__(256) dense_matrix_rows_kernel(const __grid_constant__ DenseMatArgs d) {
+__global__ void __launch_bounds__(32) dense_matrix_rows_kernel(const __grid_constant__ DenseMatArgs d) {
     dense_matrix_rows_body(d);
 }
 
@@ -414,7 +414,12 @@ cudaError_t dense_matrix_launch(const DenseWarpHost& prog, const DenseWarpStep& 
     d.rowsL = d_rows;
     d.rowsR = d_rows + (size_t(1) << prog.n);
     d.rowsO = d_rows + (size_t(2) << prog.n);
+    uint2* const flags = reinterpret_cast<uint2*>(d_rows + (size_t(3) << prog.n));
+    d.flagsL = flags;
+    d.flagsR = flags + (size_t(1) << prog.mat->mx);
+    d.flagsO = flags + (size_t(2) << prog.mat->mx);
     d.n = int(prog.n);
+    d.mx = prog.mat->mx;
     d.batch = batch;
     for (uint32_t k = 0; k <= prog.n; ++k) {
         d.Lp[k] = L.ptr[k];
@@ -438,7 +443,7 @@ cudaError_t dense_matrix_launch(const DenseWarpHost& prog, const DenseWarpStep& 
     d.Lneg = step.L.neg_mask;
     d.Rneg = step.R.neg_mask;
     d.Oneg = step.O.neg_mask;
-    dense_matrix_rows_kernel<<<((1u << prog.n) + 255) / 256, 256, 0, stream>>>(d);
+    dense_matrix_rows_kernel<<<((1u << d.mx) + 31) / 32, 32, 0, stream>>>(d);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     void* params[] = {&d};

@@ -688,7 +688,8 @@ static void eval_impl(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_i
                 if (plan->dense_warp.mat) {
                     upload(plan->d_dm_src, gaast::matrix_rep_device_table(*plan->dense_warp.mat), ctx->stream);
                     upload(plan->d_dm_lx, plan->dense_warp.mat->lx, ctx->stream);
-                    cuda_check(cudaMalloc(&plan->d_dm_rows, (size_t(3) << h.n) * sizeof(unsigned long long)),
+                    cuda_check(cudaMalloc(&plan->d_dm_rows, ((size_t(3) << h.n) + (size_t(3) << plan->dense_warp.mat->mx)) *
+                                                                sizeof(unsigned long long)),  // row addresses + flag words
                                "cudaMalloc(dense-matrix row tables)");
                 }
             }
