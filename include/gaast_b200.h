@@ -148,13 +148,17 @@ typedef struct gaast_batch gaast_batch; /* device-resident SoA batch: one f64 (o
 /* Evaluation engines (all run on the GPU; there is no host engine). */
 typedef enum gaast_engine {
     GAAST_ENGINE_AUTO = 0,        /* specialised when the plan can be specialised (NVRTC or the kernel cache),
-                                     dense-warp for large dense product chains in G(7..10), else table */
+                                     the dense engine for large dense product chains in G(7..12), else table */
     GAAST_ENGINE_TABLE = 1,       /* generic table-driven kernels compiled into this library */
     GAAST_ENGINE_SPECIALIZED = 2, /* straight-line sm_100a kernel generated from the plan */
-    GAAST_ENGINE_DENSE_WARP = 3   /* one warp per multivector: chains of dense products (geometric, outer,
-                                     contraction) of multivectors in G(n), n = 7..10, +-1 metric, FMA
-                                     arithmetic (GAAST_ERR_UNSUPPORTED for any other plan).  AUTO picks it when
-                                     such a plan is too large to specialise. */
+    GAAST_ENGINE_DENSE_WARP = 3   /* chains of dense products of multivectors in G(n), +-1 metric, FMA arithmetic
+                                     (GAAST_ERR_UNSUPPORTED for any other plan).  Chains of GEOMETRIC products,
+                                     n = 7..12: the real matrix representation of the algebra on the FP64 tensor
+                                     cores, 2^(n+MX) multiplications instead of 4^n (gaast_diag_matrix_rep; its
+                                     rounding error is bounded norm-wise, not per component: tuning variant bit 20
+                                     selects the term-by-term kernel instead).  Outer products, contractions and
+                                     mixed chains, n = 7..10: one warp per multivector, one DFMA per term.  AUTO
+                                     picks the engine when such a plan is too large to specialise. */
 } gaast_engine;
 
 typedef enum gaast_arith {
@@ -216,7 +220,10 @@ gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, i
 gaast_status gaast_plan_precompile_typed(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, int store_out,
                                          int dtype);
 /* Tuning knobs of the specialised engine: elements per thread (0 = choose,
- * 1, or 2 = 128-bit accesses) and emission-policy bits (0 = choose). */
+ * 1, or 2 = 128-bit accesses) and emission-policy bits (0 = choose).  The bits that switch an algebraic
+ * lowering OFF (each replaces sums over an output's own terms by a re-associated form, FMA arithmetic only):
+ * 2048 shared-operand linear map, 65536 reflection form of a vector sandwich, 131072 matrix form of a full G(6)
+ * product, 1048576 matrix-representation kernel of the dense engine. */
 gaast_status gaast_plan_set_tuning(gaast_plan* plan, int elems_per_thread, int variant);
 
 /* batch: the device-resident counterpart of GradedData (graded.rs:43-47): for
