@@ -363,7 +363,7 @@ DenseMatLaunch dense_matrix_shape(const gaast_ctx& ctx, const MatrixRep& rep, lo
     const int pairs = (K * T + s.threads - 1) / s.threads;
     if (tuning().dm_threads) s.threads = tuning().dm_threads;
     // registers: 2 * pairs * 2^D0 loaded doubles per thread, all live at once
-    const int by_regs = std::max(1, 65536 / (s.threads * (pairs * NT >= 32 ? 256 : NT >= 16 ? 128 : 80)));
+    const int by_regs = std::max(1, 65536 / (s.threads * (pairs * NT >= 32 ? 256 : NT >= 16 ? 128 : 100)));
     s.blocks_per_sm = std::max(1, std::min(int(budget / (s.smem + 1024)), by_regs));
     if (NT == 16 && s.threads == 256) s.blocks_per_sm = 1;  // (n = 8: 32 + 32 doubles in flight want the whole register file)
     if (tuning().dm_blocks) s.blocks_per_sm = std::max(1, std::min(int(budget / (s.smem + 1024)), tuning().dm_blocks));
