@@ -142,6 +142,22 @@ def test_reference_panics_are_errors():
         c.exp().specialize([1.0] * 3)
 
 
+def test_fuzzed_expressions_the_reference_rejects_are_rejected_by_the_mirror():
+    """tests/test_gpu_lowering_fuzz.py splits its random sandwich-rich trees with the oracle alone; the mirror must
+    draw the same line: the reference's panic message for every rejected tree, a plan for every accepted one."""
+    from tests import test_gpu_lowering_fuzz as F
+    assert len(F.ACCEPTED) == 80 and len(F.REJECTED) >= 10
+    for seed in F.REJECTED + F.ACCEPTED:
+        n, metric, kinds, tree = F.random_case(seed)
+        expr = F.build(tree, [pmv(Input(s, grades)) for s, (grades, _) in enumerate(kinds)])
+        if seed in F.REJECTED:
+            with pytest.raises(g.GaastError) as ei:
+                expr.specialize(metric)
+            assert "[PANIC]" in str(ei.value) and "grade set" in str(ei.value), (seed, str(ei.value))
+        else:
+            assert expr.specialize(metric).plan_dict()["ops"], seed
+
+
 def test_includes_keeps_bitvec_length_semantics():
     """GradeSet::includes drops grades at or above maximal's BitVec length
     (grade_set.rs:149-151, 287-300): scalar + {0,2}-multivector specializes."""

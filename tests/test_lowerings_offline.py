@@ -88,3 +88,22 @@ def test_reflection_operation_count_on_cfg5():
     plan.set_tuning(0, 65536)
     plain = _fma(plan.precompile(0, L.ARITH_FMA, True, True))
     assert plain == 1608 and lowered < 400, (plain, lowered)
+
+
+def test_the_device_cases_of_the_reflection_test_are_expressions_the_reference_accepts():
+    """tests/test_gpu_lowerings.py::test_reflection_lowering selects its (signature, X grades, shape) cases without
+    running anything; here the oracle evaluates each of them on the CPU, so none can turn into a skip on the GPU box."""
+    from math import comb
+
+    import numpy as np
+
+    from tests import test_gpu_lowerings as T
+    from tests.helpers import oracle_eval
+    marks = [m for m in T.test_reflection_lowering.pytestmark if m.name == "parametrize"]
+    cases = [p.values for p in marks[0].args[1]]
+    assert len(cases) == 22
+    for metric, xgrades, shape in cases:
+        rng = np.random.default_rng(5)
+        host = [{1: T._vec(rng, metric, 4)}, {k: rng.uniform(-1, 1, (comb(5, k), 4)) for k in xgrades}]
+        got = oracle_eval(T.SANDWICHES[shape], metric, host, [False, False], 4)
+        assert got and all(np.isfinite(v).all() for v in got.values())
