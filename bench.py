@@ -249,7 +249,7 @@ class Resident:
     """One workload resident in HBM on this rank: plan, input/output sets, the step closure."""
 
     def __init__(self, ctx, w, torch, batch=None, engine=None, tuning=None, f32=False, with_sum=None, seed_shift=0,
-                 torch_out=False):
+                 torch_out=False, arith=None):
         import gaast_b200 as g
         from gaast_b200 import _lib as L
         from gaast_b200 import workloads as W
@@ -286,6 +286,7 @@ class Resident:
         self.use_sum = w.sum_root if with_sum is None else with_sum
         self.sums = torch.zeros(_root_cols(self.plan, w), dtype=torch.float64, device=self.dev)
         self.engine = L.ENGINE_AUTO if engine is None else engine
+        self.arith = L.ARITH_FMA if arith is None else arith
         self.counter = 0
         self.comm = None
 
@@ -293,13 +294,13 @@ class Resident:
         _, s_in, s_out = self.sets[self.counter % self.n_sets]
         self.counter += 1
         if self.use_sum:
-            self.plan.eval_sum(s_in, self.sums.data_ptr(), out=s_out, engine=self.engine)
+            self.plan.eval_sum(s_in, self.sums.data_ptr(), out=s_out, engine=self.engine, arith=self.arith)
             if self.comm is not None:
                 # the only collective of the path: the root vector (66 doubles for cfg5), through the library's own
                 # communicator (gaast_comm_allreduce_sum: NCCL behind the C ABI), ordered on the ctx stream
                 self.comm.allreduce_sum([self.sums.data_ptr()], self.sums.numel())
         else:
-            self.plan.eval(s_in, out=s_out, engine=self.engine)
+            self.plan.eval(s_in, out=s_out, engine=self.engine, arith=self.arith)
 
     def kernel(self):
         return self.plan.last_kernel()
@@ -378,7 +379,7 @@ def launches_per_step(res):
     return res.ctx.launch_count - c0
 
 
-def measure_e2e(res, steps, torch, dist, world, elements=None):
+def measure_e2e(res, steps, torch, dist, world, elements=None, host_mem="torch"):
     """Same metric through gaast_eval_host: pinned host arrays in and out, H2D + kernel + D2H in the timed
     region.  Under torchrun EVERY rank runs its own pipeline at the same time (barrier before and after);
     returns the slowest rank's time."""
@@ -386,13 +387,22 @@ def measure_e2e(res, steps, torch, dist, world, elements=None):
     w, plan = res.w, res.plan
     n = min(res.n, elements or res.n)
     tin = res.sets[0][0]
-    host_in, grades, bcs = [], [], []
+    host_in, grades, bcs, keep = [], [], [], []
     h2d = 0
     dt = next(iter(tin[0].values())).dtype  # float64, or float32 for the f32 variant
     es = 4 if dt == torch.float32 else 8
     for t, (gr, bc) in zip(tin, w.inputs):
         rows = sum(comb(w.n, k) for k in gr)
-        h = torch.empty((rows, 1 if bc else n), dtype=dt, pin_memory=True)
+        if host_mem != "torch" and not bc:
+            # the library's own page-locked allocation (gaast_host_alloc), write-combined for "gaast-wc": inputs are only
+            # ever written by the host
+            import numpy as np
+            import gaast_b200 as g
+            ha = g.HostArray(rows, n, dtype=np.float32 if dt == torch.float32 else np.float64, write_combined=host_mem == "gaast-wc")
+            keep.append(ha)
+            h = torch.from_numpy(ha.array)
+        else:
+            h = torch.empty((rows, 1 if bc else n), dtype=dt, pin_memory=True)
         r = 0
         for k in gr:
             c = comb(w.n, k)
@@ -632,10 +642,12 @@ def run_gpu(args):
         line["roofline"]["fp32_tflops"] = tflops
     if not args.no_e2e:
         try:
-            e = measure_e2e(res, max(2, min(args.steps, 3)), torch, dist, world)
+            e = measure_e2e(res, max(2, min(args.steps, 3)), torch, dist, world, host_mem=args.e2e_host)
             line["e2e"] = {"value": e["elements"] * world / (e["ms_per_step"] / 1e3) * w.products, "unit": UNIT,
                            "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
                            "ms_per_step": e["ms_per_step"], "matches_resident": e["matches_resident"],
+                           "host_memory": {"torch": "torch pin_memory (cudaHostAlloc)", "gaast": "gaast_host_alloc",
+                                           "gaast-wc": "gaast_host_alloc, inputs write-combined"}[args.e2e_host],
                            # PCIe is the bound of this leg: tools/pcie_peak.py measured 55.6 (H2D alone), 55.0 (D2H alone)
                            # and 47.1 GB/s each way at the same time on this pool (profiles/r1_pcie_peak.txt)
                            "gbs_each_way_per_gpu": max(e["h2d"], e["d2h"]) / (e["ms_per_step"] * 1e6),
@@ -705,6 +717,25 @@ def run_gpu(args):
                 del r
             except Exception as ex:
                 others[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        # GAAST_ARITH_STRICT on the specialised engine: the reference's own term list in the reference's order, (l * r) * coeff
+        # then +, no contraction and no lowering -- results BIT-IDENTICAL to eval.rs (tests/test_gpu_parity.py holds both engines
+        # to that).  The default arithmetic (FMA, within 1e-12) is what every other entry runs; this is what exactness costs.
+        from gaast_b200 import _lib as L
+        strict = {}
+        for name in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5"):
+            try:
+                torch.cuda.empty_cache()
+                ow = W.WORKLOADS[name]
+                r = Resident(ctx, ow, torch, engine=L.ENGINE_SPECIALIZED, arith=L.ARITH_STRICT, with_sum=False)
+                tt = timed(r, args.steps, args.warmup, torch, dist, 1)
+                rec = _workload_record(r, tt, peak_gbs, ow)
+                strict[name] = {k: rec[k] for k in ("elements_per_s", "products_per_s", "ms_per_step", "hbm_frac", "batch", "kernel")}
+                del r
+            except Exception as ex:
+                strict[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        strict["what"] = ("the five BASELINE workloads in GAAST_ARITH_STRICT on the specialised engine (no batch-sum): bit-identical to "
+                          "the reference's (l*r)*coeff-then-add sequence; 3 FP64 instructions per term instead of one FMA, no lowering")
+        others["strict_arithmetic"] = strict
         try:
             torch.cuda.empty_cache()
             others["dense_warp_g8"] = run_dense_warp(ctx, torch, dist, args.steps, args.warmup, peak_gbs)
@@ -756,6 +787,8 @@ def main():
                     help="f64 = the reference's precision (default, the BASELINE metric); f32 = the reduced-precision variant")
     ap.add_argument("--strong", action="store_true", help="headline workload: shard ONE BASELINE batch over the ranks")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-host", default="torch", choices=["torch", "gaast", "gaast-wc"],
+                    help="page-locked host arrays of the e2e leg: torch's, or the library's own (write-combined inputs)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the cfg5_sharded section")
     ap.add_argument("--all", action="store_true", default=True, help="also time the other BASELINE workloads (N=1)")

@@ -12,7 +12,7 @@ _EXPORTS = {
     "ARITH_FMA": "_lib", "ARITH_STRICT": "_lib", "ENGINE_AUTO": "_lib", "ENGINE_SPECIALIZED": "_lib",
     "ENGINE_TABLE": "_lib", "GaastError": "_lib",
     "F32": "_lib", "F64": "_lib",
-    "Comm": "device", "Ctx": "device", "DeviceBatch": "device", "Plan": "device",
+    "Comm": "device", "Ctx": "device", "DeviceBatch": "device", "Plan": "device", "HostArray": "device", "pin_host": "device",
     "Expr": "expr", "Input": "expr", "OrthoEuclidN": "expr", "SpecializedAst": "expr", "mv": "expr",
 }
 

@@ -26,6 +26,7 @@ vp = C.c_void_p
 STATUS_NAMES = ["OK", "INVALID", "UNSUPPORTED", "PANIC", "NO_DEVICE", "CUDA", "OOM", "JIT", "SHAPE"]
 
 ENGINE_AUTO, ENGINE_TABLE, ENGINE_SPECIALIZED, ENGINE_DENSE_WARP = 0, 1, 2, 3
+HOST_DEFAULT, HOST_WRITE_COMBINED = 0, 1
 ARITH_FMA, ARITH_STRICT = 0, 1
 F64, F32 = 0, 1  # gaast_dtype
 
@@ -94,6 +95,10 @@ PROTOTYPES = {
     "gaast_ctx_create": (C.c_int, C.c_int, vp, C.POINTER(vp)),
     "gaast_ctx_destroy": (C.c_int, vp),
     "gaast_ctx_sync": (C.c_int, vp),
+    "gaast_host_alloc": (C.c_int, C.c_size_t, C.c_int, C.POINTER(vp)),
+    "gaast_host_free": (C.c_int, vp),
+    "gaast_host_register": (C.c_int, vp, C.c_size_t),
+    "gaast_host_unregister": (C.c_int, vp),
     "gaast_ctx_stream": (vp, vp),
     "gaast_ctx_launch_count": (u64, vp),
     "gaast_plan_create": (C.c_int, vp, C.POINTER(PlanDesc), C.POINTER(vp)),

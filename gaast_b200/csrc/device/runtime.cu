@@ -208,6 +208,38 @@ gaast_status gaast_ctx_destroy(gaast_ctx* ctx) {
     });
 }
 
+// Page-locked host memory for the host-array entry points (portable: pinned for every device of the process)
+gaast_status gaast_host_alloc(size_t bytes, int flags, void** out) {
+    return guard([&] {
+        if (!out) throw Error(GAAST_ERR_INVALID, "host_alloc: null out");
+        *out = nullptr;
+        if (flags != GAAST_HOST_DEFAULT && flags != GAAST_HOST_WRITE_COMBINED) throw Error(GAAST_ERR_INVALID, "host_alloc: unknown flags");
+        if (!bytes) throw Error(GAAST_ERR_INVALID, "host_alloc: zero bytes");
+        const unsigned f = cudaHostAllocPortable | (flags == GAAST_HOST_WRITE_COMBINED ? cudaHostAllocWriteCombined : 0u);
+        cuda_check(cudaHostAlloc(out, bytes, f), "cudaHostAlloc");
+    });
+}
+
+gaast_status gaast_host_free(void* p) {
+    return guard([&] {
+        if (p) cuda_check(cudaFreeHost(p), "cudaFreeHost");
+    });
+}
+
+gaast_status gaast_host_register(void* p, size_t bytes) {
+    return guard([&] {
+        if (!p || !bytes) throw Error(GAAST_ERR_INVALID, "host_register: null or empty range");
+        cuda_check(cudaHostRegister(p, bytes, cudaHostRegisterPortable), "cudaHostRegister");
+    });
+}
+
+gaast_status gaast_host_unregister(void* p) {
+    return guard([&] {
+        if (!p) throw Error(GAAST_ERR_INVALID, "host_unregister: null pointer");
+        cuda_check(cudaHostUnregister(p), "cudaHostUnregister");
+    });
+}
+
 gaast_status gaast_ctx_sync(gaast_ctx* ctx) {
     return guard([&] {
         if (!ctx) throw Error(GAAST_ERR_INVALID, "null ctx");

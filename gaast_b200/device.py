@@ -372,6 +372,38 @@ class Comm:
             pass
 
 
+class HostArray:
+    """A page-locked [rows][cols] host array for the host-array entry points (gaast_host_alloc): `.array` is a numpy
+    view of it.  `write_combined=True` is for arrays the host only fills (inputs of gaast_eval_host)."""
+
+    def __init__(self, rows: int, cols: int, dtype=np.float64, write_combined: bool = False):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(rows) * int(cols) * self.dtype.itemsize
+        out = L.vp()
+        L.check(L.lib.gaast_host_alloc(self.nbytes, L.HOST_WRITE_COMBINED if write_combined else L.HOST_DEFAULT, C.byref(out)))
+        self._p = out
+        buf = (C.c_char * self.nbytes).from_address(out.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(int(rows), int(cols))
+
+    def free(self):
+        p, self._p = self._p, None
+        if p:
+            self.array = None
+            L.lib.gaast_host_free(p)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pin_host(a: np.ndarray):
+    """Pins an existing numpy array in place (gaast_host_register); returns a callable that unpins it."""
+    L.check(L.lib.gaast_host_register(L.vp(a.ctypes.data), a.nbytes))
+    return lambda: L.check(L.lib.gaast_host_unregister(L.vp(a.ctypes.data)))
+
+
 def _is_broadcast(b: DeviceBatch) -> bool:
     return False if b.length != 1 else True
 

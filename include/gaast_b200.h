@@ -289,6 +289,20 @@ gaast_status gaast_eval(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n
 gaast_status gaast_eval_sum(gaast_plan* plan, gaast_batch* const* inputs, uint32_t n_inputs, gaast_batch* out,
                             double* dev_sum, int engine, int arith);
 
+/* Page-locked host memory for the host-array entry points (gaast_eval_host, gaast_batch_upload /
+ * _download).  The reference keeps its multivectors in ordinary Rust allocations (`GradeMapMV`: a
+ * HashMap<Grade, Vec<f64>>, src/graded.rs:174); a caller that wants the copies of gaast_eval_host to overlap either
+ * allocates its arrays here or pins the ones it has (gaast_host_register takes any allocation, e.g.
+ * the buffer of a Vec<f64>; it must be unregistered before it is freed).  Memory is pinned for every
+ * device of the process.  GAAST_HOST_WRITE_COMBINED asks for write-combined pages: for arrays the host
+ * only WRITES (inputs) -- reading them back from the CPU is very slow. */
+#define GAAST_HOST_DEFAULT 0
+#define GAAST_HOST_WRITE_COMBINED 1
+gaast_status gaast_host_alloc(size_t bytes, int flags, void** out);
+gaast_status gaast_host_free(void* p);
+gaast_status gaast_host_register(void* p, size_t bytes);
+gaast_status gaast_host_unregister(void* p);
+
 /* End-to-end convenience used for the `e2e` measurement: host arrays in, host
  * arrays out, chunked so that H2D, kernels and D2H overlap.  host_in[s] points
  * to [comps of slot s][host_stride] (grades of in_masks[s] ascending), or, for a

@@ -45,6 +45,8 @@ pub const GAAST_ARITH_FMA: c_int = 0;
 pub const GAAST_ARITH_STRICT: c_int = 1;
 pub const GAAST_F64: c_int = 0;
 pub const GAAST_F32: c_int = 1;
+pub const GAAST_HOST_DEFAULT: c_int = 0;
+pub const GAAST_HOST_WRITE_COMBINED: c_int = 1;
 
 /// `IndividualCompMul` (ast/base_types.rs:46-55) with (grade, index) resolved to buffer slots.
 #[repr(C)]
@@ -111,6 +113,10 @@ extern "C" {
     pub fn gaast_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut gaast_ctx) -> c_int;
     pub fn gaast_ctx_destroy(ctx: *mut gaast_ctx) -> c_int;
     pub fn gaast_ctx_sync(ctx: *mut gaast_ctx) -> c_int;
+    pub fn gaast_host_alloc(bytes: usize, flags: c_int, out: *mut *mut c_void) -> c_int;
+    pub fn gaast_host_free(p: *mut c_void) -> c_int;
+    pub fn gaast_host_register(p: *mut c_void, bytes: usize) -> c_int;
+    pub fn gaast_host_unregister(p: *mut c_void) -> c_int;
     pub fn gaast_ctx_stream(ctx: *mut gaast_ctx) -> *mut c_void;
     pub fn gaast_ctx_launch_count(ctx: *mut gaast_ctx) -> u64;
 

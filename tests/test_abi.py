@@ -147,6 +147,22 @@ def test_no_device_means_no_compute():
     assert ei.value.status == L.ERR_NO_DEVICE
 
 
+def test_host_memory_entries_validate_their_arguments():
+    """gaast_host_alloc / _register check their arguments before any CUDA call: status codes without a device."""
+    import ctypes as C
+    out = L.vp()
+    assert L.lib.gaast_host_alloc(64, 7, C.byref(out)) == L.ERR_INVALID and not out.value
+    assert L.lib.gaast_host_alloc(0, L.HOST_DEFAULT, C.byref(out)) == L.ERR_INVALID
+    assert L.lib.gaast_host_alloc(64, L.HOST_DEFAULT, None) == L.ERR_INVALID
+    assert L.lib.gaast_host_register(None, 64) == L.ERR_INVALID
+    assert L.lib.gaast_host_unregister(None) == L.ERR_INVALID
+    assert L.lib.gaast_host_free(None) == L.OK
+    import torch
+    if not torch.cuda.is_available():
+        # without a device the allocation itself is an error, never a crash
+        assert L.lib.gaast_host_alloc(64, L.HOST_DEFAULT, C.byref(out)) != L.OK and not out.value
+
+
 def test_huge_plans_are_left_to_the_table_engine():
     """G(8,0) A*B has 65 536 terms: the code generator refuses, AUTO falls back to the table engine."""
     from gaast_b200.expr import Input, mv

@@ -174,6 +174,93 @@ def test_eval_host_pipeline(ctx):
     assert np.array_equal(out, want[1])
 
 
+@pytest.mark.parametrize("name", sorted(W.WORKLOADS))
+@pytest.mark.parametrize("batch,pad", [(1, 0), (5, 3), (4096 * 3 + 1, 64)], ids=["one", "five-padded", "ragged-padded"])
+def test_eval_host_every_workload_strided_host_arrays(ctx, name, batch, pad):
+    """gaast_eval_host on every BASELINE workload: host arrays whose row stride exceeds the batch length (a view into a
+    larger allocation), batches shorter than a chunk, strict arithmetic bit-exact against the ORACLE (not only against
+    the resident path), and the padding of the output rows left untouched."""
+    w = W.WORKLOADS[name]
+    host = W.host_inputs(w, batch)
+    stride = batch + pad
+    flat, grades, bcs = [], [], []
+    for h, (gr, bc) in zip(host, w.inputs):
+        rows = np.concatenate([h[k] for k in gr], axis=0)
+        if bc:
+            flat.append(np.ascontiguousarray(rows[:, 0]))
+        else:
+            a = np.full((rows.shape[0], stride), np.nan)
+            a[:, :batch] = rows
+            flat.append(a)
+        grades.append(gr)
+        bcs.append(bc)
+    plan = g.Plan(ctx, W.specialize(w))
+    want = oracle_eval(w.build, w.metric, host, [bc for _, bc in w.inputs], batch)
+    out_rows = sum(comb(w.n, k) for k in plan.root_grades())
+    for arith, engine in ((L.ARITH_STRICT, L.ENGINE_SPECIALIZED), (L.ARITH_STRICT, L.ENGINE_TABLE), (L.ARITH_FMA, L.ENGINE_AUTO)):
+        out = np.full((out_rows, stride), 7.5)
+        plan.eval_host(flat, grades, bcs, batch, out, host_stride=stride, engine=engine, arith=arith)
+        assert np.all(out[:, batch:] == 7.5), "eval_host wrote beyond the batch length"
+        got, r = {}, 0
+        for k in plan.root_grades():
+            got[k] = out[r:r + comb(w.n, k), :batch]
+            r += comb(w.n, k)
+        if arith == L.ARITH_STRICT:
+            assert_bit_exact(got, want, f"{name} eval_host strict engine {engine}")
+        else:
+            scale = oracle_abs_scale(w.build, w.metric, host, [bc for _, bc in w.inputs], batch)
+            assert_close(got, want, scale, what=f"{name} eval_host fma")
+
+
+def test_eval_host_with_library_pinned_arrays(ctx):
+    """gaast_host_alloc (write-combined inputs, ordinary pinned output) and gaast_host_register (a numpy array pinned in
+    place) feed gaast_eval_host; the results equal the resident path bit for bit."""
+    w = W.WORKLOADS["cfg2"]
+    batch = 4096 * 50 + 3
+    host = W.host_inputs(w, batch)
+    plan = g.Plan(ctx, W.specialize(w))
+    want = plan.eval(_device_inputs(ctx, w, host)).to_host()
+    Rh = np.ascontiguousarray(np.concatenate([host[0][k] for k in (0, 2, 4)], axis=0)[:, 0])
+    X = g.HostArray(5, batch, write_combined=True)
+    X.array[:] = host[1][1]
+    out = g.HostArray(5, batch)
+    out.array[:] = 0.0
+    plan.eval_host([Rh, X.array], [(0, 2, 4), (1,)], [True, False], batch, out.array)
+    assert np.array_equal(out.array, want[1])
+    X2 = np.ascontiguousarray(host[1][1])
+    out2 = np.zeros((5, batch))
+    unpin_x, unpin_out = g.pin_host(X2), g.pin_host(out2)
+    try:
+        plan.eval_host([Rh, X2], [(0, 2, 4), (1,)], [True, False], batch, out2)
+    finally:
+        unpin_x()
+        unpin_out()
+    assert np.array_equal(out2, want[1])
+    X.free()
+    out.free()
+
+
+def test_eval_host_rejects_bad_arguments(ctx):
+    """Status codes, not crashes: wrong input count, a stride shorter than the batch, a null output."""
+    w = W.WORKLOADS["cfg1"]
+    plan = g.Plan(ctx, W.specialize(w))
+    host = W.host_inputs(w, 8)
+    flat = [np.concatenate([h[k] for k in gr], axis=0) for h, (gr, _) in zip(host, w.inputs)]
+    grades = [gr for gr, _ in w.inputs]
+    out = np.zeros((3, 8))
+    with pytest.raises(g.GaastError) as ei:
+        plan.eval_host(flat[:2], grades[:2], [False] * 2, 8, out)
+    assert ei.value.status == L.ERR_SHAPE
+    with pytest.raises(g.GaastError) as ei:
+        plan.eval_host(flat, grades, [False] * 3, 8, out, host_stride=4)
+    assert ei.value.status == L.ERR_INVALID
+    # the plan still works afterwards
+    plan.eval_host(flat, grades, [False] * 3, 8, out)
+    want = oracle_eval(w.build, w.metric, host, [False] * 3, 8)
+    scale = oracle_abs_scale(w.build, w.metric, host, [False] * 3, 8)
+    assert_close({2: out}, want, scale)
+
+
 def test_wrap_torch_tensors(ctx):
     import torch
     w = W.WORKLOADS["cfg1"]
