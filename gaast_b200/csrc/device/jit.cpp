@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <atomic>
 #include <mutex>
 #include <sstream>
 
@@ -115,7 +116,9 @@ bool read_file(const std::string& path, std::vector<char>& out) {
 }
 
 void write_file_atomic(const std::string& path, const char* data, size_t n) {
-    const std::string tmp = path + ".tmp" + std::to_string(getpid());
+    // unique per process AND per call: two threads of one process may build the same kernel at the same time
+    static std::atomic<unsigned> serial{0};
+    const std::string tmp = path + ".tmp" + std::to_string(getpid()) + "." + std::to_string(serial.fetch_add(1));
     {
         std::ofstream f(tmp, std::ios::binary);
         if (!f) return;

@@ -9,6 +9,7 @@
 """
 from __future__ import annotations
 
+import threading
 from math import comb
 from typing import Callable, Dict, List, Sequence
 
@@ -59,13 +60,28 @@ def oracle_abs_scale(build: Callable, metric, inputs, broadcast, batch: int) -> 
     return {k: (v if v.ndim == 2 else np.repeat(v[:, None], batch, 1)) for k, v in res.m.items()}
 
 
+# Magnitudes only: while a thread evaluates an abs-scale, sign flips are no-ops FOR THAT THREAD (a thread-local flag
+# behind a wrapper installed once; swapping the method itself would blind concurrent oracle_eval calls of other threads
+# to their sign flips -- tests/test_gpu_threads.py runs the oracle from several threads)
+_tls = threading.local()
+_negate_grade = go.GradeMapMV.negate_grade
+
+
+def _negate_grade_unless_magnitudes_only(self, k):
+    if getattr(_tls, "magnitudes_only", False):
+        return None
+    return _negate_grade(self, k)
+
+
+go.GradeMapMV.negate_grade = _negate_grade_unless_magnitudes_only
+
+
 def _eval_abs(ast, batch):
-    saved = go.GradeMapMV.negate_grade
-    go.GradeMapMV.negate_grade = lambda self, k: None  # magnitudes only: sign flips are no-ops
+    _tls.magnitudes_only = True
     try:
         res = go.eval_specialized(ast, batch)
     finally:
-        go.GradeMapMV.negate_grade = saved
+        _tls.magnitudes_only = False
     return go.GradeMapMV({k: np.abs(v) for k, v in res.m.items()})
 
 

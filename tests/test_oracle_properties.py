@@ -180,3 +180,42 @@ def test_cpp_port_is_bit_identical_to_numpy_oracle(storage):
     V = go.mv(v)
     ast = (V.clone() * go.mv(x) * V.vinv()).g(1).specialize(alg)
     assert port.eval_port(ast, B, storage=storage) == ast.eval(B)
+
+
+def test_oracle_helpers_are_reentrant_across_threads():
+    """tests/test_gpu_threads.py calls oracle_eval and oracle_abs_scale from several host threads at once.  The
+    magnitudes-only evaluation of the abs-scale must not blind the other threads' oracle to sign flips (it once swapped
+    GradeMapMV.negate_grade for everybody): threaded results equal the serial ones bit for bit."""
+    import threading
+
+    from gaast_b200 import workloads as W
+    from tests.helpers import oracle_abs_scale, oracle_eval
+    names = ["cfg1", "cfg2", "cfg2_full", "cfg5"]
+
+    def case(i, r):
+        w = W.WORKLOADS[names[i]]
+        batch = 40 + 8 * r + i
+        return w, batch, W.host_inputs(w, batch, seed=50 * i + r), [bc for _, bc in w.inputs]
+
+    serial = {}
+    for i in range(4):
+        for r in range(4):
+            w, batch, host, bcs = case(i, r)
+            serial[i, r] = (oracle_eval(w.build, w.metric, host, bcs, batch), oracle_abs_scale(w.build, w.metric, host, bcs, batch))
+    bad = []
+
+    def worker(i):
+        for _ in range(3):
+            for r in range(4):
+                w, batch, host, bcs = case(i, r)
+                got, scale = oracle_eval(w.build, w.metric, host, bcs, batch), oracle_abs_scale(w.build, w.metric, host, bcs, batch)
+                for k in got:
+                    if not np.array_equal(got[k], serial[i, r][0][k]) or not np.array_equal(scale[k], serial[i, r][1][k]):
+                        bad.append((i, r, k))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not bad, bad[:8]
