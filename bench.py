@@ -574,7 +574,7 @@ def run_gpu(args):
     sampler = ClockSampler(local) if rank == 0 else None
     res = Resident(ctx, w, torch, batch=batch, engine={'auto': 0, 'table': 1, 'specialized': 2}[args.engine],
                    tuning=(args.ept, args.variant) if (args.ept or args.variant) else None,
-                   with_sum=False if args.no_sum else None, f32=f32)
+                   with_sum=False if args.no_sum else None, f32=f32, arith={"fma": 0, "strict": 1}[args.arith])
     if res.use_sum and world > 1:
         uid = [g.Comm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -780,6 +780,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override the batch length (default: the BASELINE size)")
     ap.add_argument("--impl", default="gaast_b200", choices=["gaast_b200", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "table", "specialized"])
+    ap.add_argument("--arith", default="fma", choices=["fma", "strict"],
+                    help="fma: one FMA per term, lowerings on (within 1e-12); strict: the reference's own operation sequence, bit-identical")
     ap.add_argument("--ept", type=int, default=0, help="tuning: elements per thread of the specialised kernel")
     ap.add_argument("--variant", type=int, default=0, help="tuning: code generator policy bits")
     ap.add_argument("--no-sum", action="store_true", help="skip the batch-sum node of cfg5")

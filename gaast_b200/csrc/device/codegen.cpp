@@ -2014,6 +2014,22 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
         const bool dense = !g.strict && outs.size() + ls.size() + rs.size() > kDenseBudget &&
                            live_terms * 4 >= ls.size() * rs.size() && load_opnds * 4 >= (ls.size() + rs.size()) * 3;
         Policy pol = outs.size() > kAccBudget ? P_GATHER : P_TABLE;
+        // Strict arithmetic cannot block a dense product (the reference's term order is per output), and one accumulator per
+        // output NEXT TO both operands in registers does not fit: 64 + 64 + 64 values for G(6) A*B spilled 888 bytes per thread.
+        // One output chain at a time instead (cfg3 strict: 30.0 -> 20.2 ms, profiles/r2_strict_policies.txt).
+        if (g.strict) {
+            // (strict operands are 0.0 + row, the reference's add_grades_from onto a zeroed buffer: count those as rows)
+            auto rowish = [&](int id) {
+                const Node& n = g.nodes[id];
+                if (n.uniform) return false;
+                if (n.k == N_LOAD) return true;
+                return n.k == N_ADD && g.nodes[n.a.id].k == N_ZERO && g.nodes[n.b.id].k == N_LOAD;
+            };
+            size_t row_opnds = 0;
+            for (int id : ls) row_opnds += rowish(id);
+            for (int id : rs) row_opnds += rowish(id);
+            if (outs.size() + row_opnds > kLiveBudget + (opt.f32 ? 64 : 32)) pol = P_GATHER;
+        }
         if (dense && outs.size() <= 144) pol = P_BLOCKED;  // (up to 2 x the f64 accumulator budget)
         if (opt.variant & 1) pol = P_TABLE;
         if (opt.variant & 2) pol = P_GATHER;
