@@ -108,3 +108,59 @@ def test_cfg5_vector_sandwich_preserves_the_bivector_norm_and_batch_sum():
     scale = out_t[2].abs().sum(dim=1)
     assert bool(((sums - ref).abs() <= 1e-12 * scale).all())
     _sample_check(torch, w, tin, out_t, n)
+
+
+def test_more_than_2_pow_31_elements_in_one_batch():
+    """Maximum sizes: a batch longer than 2^31 elements (every row is 17 GB, the second row of a grade starts beyond
+    2^34 bytes) through the specialised engine (strict and FMA), the table engine, and the batch-sum: element indices,
+    row offsets and grid sizes must all be 64-bit clean.  G(2,0), v (vector) * s (scalar): the reference computes
+    0.0 + (v_i * s) * 1.0 per component, which torch reproduces bit for bit on the device; the last elements of the
+    batch -- where a 32-bit index would have wrapped -- are also compared with the oracle."""
+    import torch
+    from gaast_b200.expr import Input, mv as pmv
+    n_elem = (1 << 31) + 4096 + 3
+    free, _ = torch.cuda.mem_get_info(0)
+    need = 5 * n_elem * 8 + (8 << 30)
+    if free < need:
+        torch.cuda.empty_cache()
+        free, _ = torch.cuda.mem_get_info(0)
+    assert free >= need, f"needs {need >> 30} GiB of free device memory, {free >> 30} GiB available"
+    ctx = g.Ctx.on_torch_stream(0)
+    gen = torch.Generator(device="cuda:0").manual_seed(31)
+    v = torch.rand((2, n_elem), dtype=torch.float64, device="cuda:0", generator=gen) * 2 - 1
+    s = torch.rand((1, n_elem), dtype=torch.float64, device="cuda:0", generator=gen) * 2 - 1
+    out_t = torch.empty((2, n_elem), dtype=torch.float64, device="cuda:0")
+    metric = [1.0, 1.0]
+    build = lambda a, b: a * b  # noqa: E731
+    plan = g.Plan(ctx, build(pmv(Input(0, (1,))), pmv(Input(1, (0,)))).specialize(metric))
+    ins = [g.DeviceBatch.wrap_torch(ctx, 2, {1: v}), g.DeviceBatch.wrap_torch(ctx, 2, {0: s})]
+    out = g.DeviceBatch.wrap_torch(ctx, 2, {1: out_t})
+    tail = slice(n_elem - 1000, n_elem)
+    host = [{1: v[:, tail].cpu().numpy()}, {0: s[:, tail].cpu().numpy()}]
+    want_tail = oracle_eval(build, metric, host, [False, False], 1000)[1]
+
+    def check(what):
+        torch.cuda.synchronize()
+        step = 1 << 28
+        for lo in range(0, n_elem, step):
+            hi = min(n_elem, lo + step)
+            assert torch.equal(out_t[:, lo:hi], v[:, lo:hi] * s[:, lo:hi] + 0.0), f"{what}: elements {lo}..{hi}"
+        assert np.array_equal(out_t[:, tail].cpu().numpy(), want_tail), f"{what}: the last 1000 elements against the oracle"
+        out_t.zero_()
+
+    for engine, arith, what in ((L.ENGINE_SPECIALIZED, L.ARITH_STRICT, "specialised strict"),
+                                (L.ENGINE_SPECIALIZED, L.ARITH_FMA, "specialised fma"),
+                                (L.ENGINE_TABLE, L.ARITH_STRICT, "table strict")):
+        plan.eval(ins, out=out, engine=engine, arith=arith)
+        check(what)
+    sums = torch.zeros(2, dtype=torch.float64, device="cuda:0")
+    plan.eval_sum(ins, sums.data_ptr(), out=out)
+    torch.cuda.synchronize()
+    ref = torch.zeros(2, dtype=torch.float64, device="cuda:0")
+    mag = torch.zeros(2, dtype=torch.float64, device="cuda:0")
+    for lo in range(0, n_elem, 1 << 28):
+        hi = min(n_elem, lo + (1 << 28))
+        ref += out_t[:, lo:hi].sum(dim=1)
+        mag += out_t[:, lo:hi].abs().sum(dim=1)
+    assert torch.all((sums - ref).abs() <= 1e-12 * mag), (sums, ref, mag)
+    check("specialised fma + batch-sum")
