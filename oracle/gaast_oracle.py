@@ -360,10 +360,6 @@ class GradeMapMV:
         return "GradeMapMV(%r)" % ({k: v.tolist() for k, v in sorted(self.m.items())},)
 
 
-def grade_map_mv(**_):  # pragma: no cover - python cannot spell the macro; use gmv()
-    raise NotImplementedError
-
-
 def gmv(d: Dict[int, Iterable[float]]) -> GradeMapMV:
     """graded.rs:209-223 (`grade_map_mv!`)."""
     return GradeMapMV({k: np.array(list(v), dtype=np.float64) for k, v in d.items()})
