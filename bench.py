@@ -483,7 +483,7 @@ def run_cfg5_sharded(ctx, torch, dist, rank, world, steps, warmup, peak_gbs):
     w = W.WORKLOADS["cfg5"]
     total = w.batch
     rec = {"workload": f"{w.name}: {w.title}", "batch_total": total, "n_gpus": world, "scaling": "strong",
-           "collective": "gaast_comm_allreduce_sum (ncclAllReduce, 66 f64, sum) on the ctx stream, inside every timed step"}
+           "collective": "gaast_comm_allreduce_sum (66 f64, sum) on the ctx stream, inside every timed step"}
     one_ms = None
     if world > 1:
         # (1) the same 32 M batch on ONE GPU of this box (rank 0; the other ranks wait at the barrier inside timed())
@@ -504,6 +504,9 @@ def run_cfg5_sharded(ctx, torch, dist, rank, world, steps, warmup, peak_gbs):
         uid = [g.Comm.unique_id() if rank == 0 else None]  # torch.distributed only ships the 128-byte id
         dist.broadcast_object_list(uid, src=0)
         res.comm = g.Comm.join(ctx, world, rank, uid[0])
+        rec["collective_transport"] = res.comm.transport  # "peer": the library's one-shot kernel over NVLink peer memory
+        rec["collective"] += {"peer": "; transport: this library's peer-memory kernel (one launch, NVLink stores + flags, rank-ordered sum)",
+                              "nccl": "; transport: ncclAllReduce"}.get(res.comm.transport, "")
     t = timed(res, steps, warmup, torch, dist, world, allow_graph=False)
     s = t["ms_per_step"] / 1e3
     rec.update({"ms_per_step": t["ms_per_step"], "ms_per_step_min": t["ms_per_step_min"], "timed_reps": t["reps"],
@@ -534,6 +537,14 @@ def run_cfg5_sharded(ctx, torch, dist, rank, world, steps, warmup, peak_gbs):
         res.comm = comm
         rec["ms_per_step_without_allreduce"] = t0["ms_per_step"]
         rec["allreduce_cost_ms"] = t["ms_per_step"] - t0["ms_per_step"]
+        if comm.transport == "peer":
+            # (4) the same step with NCCL carrying the 66 doubles instead of the library's peer-memory kernel
+            from gaast_b200 import _lib as L
+            comm.set_transport(L.COMM_NCCL)
+            tn = timed(res, steps, warmup, torch, dist, world, allow_graph=False)
+            comm.set_transport(L.COMM_AUTO)
+            rec["ms_per_step_with_nccl_allreduce"] = tn["ms_per_step"]
+            rec["nccl_allreduce_cost_ms"] = tn["ms_per_step"] - t0["ms_per_step"]
         one = torch.tensor([one_ms or 0.0], dtype=torch.float64, device=res.dev)
         dist.all_reduce(one, op=dist.ReduceOp.MAX)
         one_ms = float(one.item())

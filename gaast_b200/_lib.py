@@ -27,6 +27,7 @@ STATUS_NAMES = ["OK", "INVALID", "UNSUPPORTED", "PANIC", "NO_DEVICE", "CUDA", "O
 
 ENGINE_AUTO, ENGINE_TABLE, ENGINE_SPECIALIZED, ENGINE_DENSE_WARP = 0, 1, 2, 3
 HOST_DEFAULT, HOST_WRITE_COMBINED = 0, 1
+COMM_AUTO, COMM_NCCL, COMM_PEER = 0, 1, 2
 ARITH_FMA, ARITH_STRICT = 0, 1
 F64, F32 = 0, 1  # gaast_dtype
 
@@ -145,6 +146,8 @@ PROTOTYPES = {
     "gaast_comm_unique_id": (C.c_int, C.c_char_p),
     "gaast_comm_create_rank": (C.c_int, vp, u32, u32, C.c_char_p, C.POINTER(vp)),
     "gaast_comm_size": (u32, vp),
+    "gaast_comm_transport": (C.c_char_p, vp),
+    "gaast_comm_set_transport": (C.c_int, vp, C.c_int),
     "gaast_comm_allreduce_sum": (C.c_int, vp, C.POINTER(vp), C.c_size_t),
     "gaast_comm_destroy": (C.c_int, vp),
     # gaast_b200_host.h

@@ -32,7 +32,7 @@ SOURCES = [
     "host/host_capi.cpp",
     "device/codegen.cpp",
     "device/jit.cpp",
-    "device/comm.cpp",
+    "device/comm.cu",
     "device/table_engine.cu",
     "device/dense_warp.cu",
     "device/dense_matrix.cu",

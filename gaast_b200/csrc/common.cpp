@@ -44,6 +44,7 @@ static Tuning read_tuning() {
         if (v.test_hooks) v.kernel_cache_override = str("GAAST_KERNEL_CACHE");
         v.nvrtc_path = str("GAAST_NVRTC");
         v.nccl_path = str("GAAST_NCCL");
+        v.comm_transport = str("GAAST_COMM");
         return v;
     }
 }

@@ -33,6 +33,7 @@ struct Tuning {
     bool test_hooks = false;          // GAAST_TEST_HOOKS=1: enables kernel_cache_override (tests and timing experiments only)
     std::string kernel_cache_override;  // GAAST_KERNEL_CACHE (honoured only with GAAST_TEST_HOOKS=1)
     std::string nvrtc_path, nccl_path;  // GAAST_NVRTC / GAAST_NCCL: explicit library paths tried first
+    std::string comm_transport;         // GAAST_COMM=nccl: new communicators do not set up the peer-memory transport
 };
 const Tuning& tuning();
 void reload_tuning();  // gaast_reload_env(): tests and timing experiments; not thread-safe

@@ -325,9 +325,10 @@ class Plan:
 
 
 class Comm:
-    """gaast_comm: the all-reduce of batch-sum vectors across the GPUs of one node (NCCL behind the
-    C ABI).  `Comm(ctxs)` = one process driving several devices; `Comm.join(ctx, n, rank, id)` =
-    one process per device, `Comm.unique_id()` drawn on rank 0 and shipped by the caller."""
+    """gaast_comm: the all-reduce of batch-sum vectors across the GPUs of one node, behind the C ABI: the library's
+    own kernel over NVLink peer memory (`transport == "peer"`), NCCL as the fallback.  `Comm(ctxs)` = one process
+    driving several devices; `Comm.join(ctx, n, rank, id)` = one process per device, `Comm.unique_id()` drawn on
+    rank 0 and shipped by the caller."""
 
     def __init__(self, ctxs: Sequence[Ctx], _handle=None):
         self.ctxs = list(ctxs)
@@ -353,6 +354,15 @@ class Comm:
     @property
     def size(self) -> int:
         return L.lib.gaast_comm_size(self._h)
+
+    @property
+    def transport(self) -> str:
+        """"peer" or "nccl" (gaast_comm_transport)."""
+        return (L.lib.gaast_comm_transport(self._h) or b"").decode()
+
+    def set_transport(self, transport: int):
+        """L.COMM_AUTO / COMM_NCCL / COMM_PEER; every rank must make the same call."""
+        L.check(L.lib.gaast_comm_set_transport(self._h, int(transport)))
 
     def allreduce_sum(self, dev_ptrs: Sequence[int], count: int):
         """In place on every local device: dev_ptrs[i] -> `count` doubles on self.ctxs[i]'s device."""

@@ -325,9 +325,10 @@ gaast_status gaast_eval_host_f32(gaast_plan* plan, const float* const* host_in, 
  * Multi-GPU: batch elements are independent, so a batch is sharded into
  * contiguous slices, one per device, and every device evaluates its slice with its own ctx /
  * plan / batches -- no communication.  The ONE collective of the path is the all-reduce of the
- * batch-sum vector gaast_eval_sum leaves on each device (66 doubles for the G(8,4) workload).
- * NCCL (over NVLink / NVSwitch) is loaded with dlopen("libnccl.so.2"): GAAST_ERR_UNSUPPORTED if
- * it is not installed.  gaast has no counterpart (it is single-threaded and batch-less). */
+ * batch-sum vector gaast_eval_sum leaves on each device (66 doubles for the G(8,4) workload):
+ * a kernel of this library over NVLink / NVSwitch peer memory (gaast_comm_transport below), NCCL
+ * for the set-up and as the fallback.  NCCL is loaded with dlopen("libnccl.so.2"):
+ * GAAST_ERR_UNSUPPORTED if it is not installed.  gaast has no counterpart (it is single-threaded and batch-less). */
 typedef struct gaast_comm gaast_comm;
 #define GAAST_COMM_ID_BYTES 128u
 /* One process driving n devices of one node: ctxs[i] is rank i (ncclCommInitAll). */
@@ -338,6 +339,19 @@ gaast_status gaast_comm_unique_id(unsigned char* id);
 gaast_status gaast_comm_create_rank(gaast_ctx* ctx, uint32_t n_ranks, uint32_t rank, const unsigned char* id,
                                     gaast_comm** out);
 uint32_t gaast_comm_size(const gaast_comm* comm);
+/* How gaast_comm_allreduce_sum moves its vector.  "peer": this library's own one-shot all-reduce over NVLink /
+ * NVSwitch peer memory -- one kernel launch per device; every rank stores its vector into every peer's mailbox
+ * (cudaDeviceEnablePeerAccess within a process, CUDA IPC between processes), raises a flag, waits for the others'
+ * flags and adds the contributions in rank order, so the total is bit-identical on every rank; vectors of up to 512
+ * doubles.  "nccl": ncclAllReduce.  A communicator uses "peer" whenever every rank could map every other (the ranks
+ * agree on this at creation; GAAST_COMM=nccl in the environment opts out) and falls back to NCCL otherwise, or for
+ * longer vectors.  gaast_comm_set_transport overrides per communicator -- every rank must make the same call;
+ * GAAST_COMM_PEER returns GAAST_ERR_UNSUPPORTED when peer memory is not available. */
+#define GAAST_COMM_AUTO 0
+#define GAAST_COMM_NCCL 1
+#define GAAST_COMM_PEER 2
+const char* gaast_comm_transport(const gaast_comm* comm);
+gaast_status gaast_comm_set_transport(gaast_comm* comm, int transport);
 /* In place: dev_sums[i] addresses `count` doubles on the i-th LOCAL device of the communicator (all
  * of them after gaast_comm_create, exactly one after gaast_comm_create_rank); afterwards every
  * device holds the element-wise total over all ranks.  Ordered on each ctx's stream, asynchronous. */

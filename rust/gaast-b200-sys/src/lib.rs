@@ -47,6 +47,9 @@ pub const GAAST_F64: c_int = 0;
 pub const GAAST_F32: c_int = 1;
 pub const GAAST_HOST_DEFAULT: c_int = 0;
 pub const GAAST_HOST_WRITE_COMBINED: c_int = 1;
+pub const GAAST_COMM_AUTO: c_int = 0;
+pub const GAAST_COMM_NCCL: c_int = 1;
+pub const GAAST_COMM_PEER: c_int = 2;
 
 /// `IndividualCompMul` (ast/base_types.rs:46-55) with (grade, index) resolved to buffer slots.
 #[repr(C)]
@@ -160,6 +163,8 @@ extern "C" {
     pub fn gaast_comm_unique_id(id: *mut u8) -> c_int;
     pub fn gaast_comm_create_rank(ctx: *mut gaast_ctx, n_ranks: u32, rank: u32, id: *const u8, out: *mut *mut gaast_comm) -> c_int;
     pub fn gaast_comm_size(comm: *const gaast_comm) -> u32;
+    pub fn gaast_comm_transport(comm: *const gaast_comm) -> *const c_char;
+    pub fn gaast_comm_set_transport(comm: *mut gaast_comm, transport: c_int) -> c_int;
     pub fn gaast_comm_allreduce_sum(comm: *mut gaast_comm, dev_sums: *const *mut f64, count: usize) -> c_int;
     pub fn gaast_comm_destroy(comm: *mut gaast_comm) -> c_int;
 
