@@ -125,14 +125,15 @@ constexpr int kPeerMaxCount = 512;  // doubles per vector (66 for cfg5; a full G
 // slow rank is still adding up for epoch e.
 struct PeerMailbox {
     unsigned long long flags[kPeerMaxRanks];  // flags[r] = last epoch rank r has delivered here
-    unsigned long long pad[16 - kPeerMaxRanks % 16];
+    unsigned long long epoch;                 // all-reduces this device has started: advanced by the kernel itself, so a
+                                              // launch carries no host-side state and may be captured in a CUDA graph
+    unsigned long long pad[15];
     double data[2][kPeerMaxRanks][kPeerMaxCount];
 };
 
 struct PeerArgs {
     PeerMailbox* box[kPeerMaxRanks];  // every rank's mailbox, as addressable from THIS device
     double* inout;                    // count doubles on this device: contribution in, total out
-    unsigned long long epoch;
     int rank, n_ranks, count;
     long long timeout_ns;
 };
@@ -153,9 +154,15 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
 
 __global__ void __launch_bounds__(256) peer_allreduce_kernel(const __grid_constant__ PeerArgs a) {
     const int tid = threadIdx.x;
-    const int buf = int(a.epoch & 1ull);
     __shared__ int timed_out;
-    if (tid == 0) timed_out = 0;
+    __shared__ unsigned long long epoch_sh;
+    if (tid == 0) {
+        timed_out = 0;
+        epoch_sh = ++a.box[a.rank]->epoch;  // only this device's kernels touch its counter, one at a time (stream order)
+    }
+    __syncthreads();
+    const unsigned long long epoch = epoch_sh;
+    const int buf = int(epoch & 1ull);
     // 1. my vector into slot [rank] of every rank's mailbox (my own included): plain stores through the peer mapping
     for (int i = tid; i < a.n_ranks * a.count; i += blockDim.x) {
         const int p = i / a.count, c = i - p * a.count;
@@ -165,12 +172,12 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(const __grid_consta
     __syncthreads();
     // 2. raise my flag everywhere (release: the stores above are visible before it), 3. wait for everybody's flag here
     if (tid < a.n_ranks) {
-        st_release_sys(&a.box[tid]->flags[a.rank], a.epoch);
+        st_release_sys(&a.box[tid]->flags[a.rank], epoch);
         const unsigned long long* mine = &a.box[a.rank]->flags[tid];
         unsigned long long t0 = 0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         unsigned spins = 0;
-        while (ld_acquire_sys(mine) < a.epoch) {
+        while (ld_acquire_sys(mine) < epoch) {
             if ((++spins & 1023u) == 0) {
                 unsigned long long t1;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -204,7 +211,6 @@ struct gaast_comm {
     std::vector<PeerMailbox*> box;                 // [local device]
     std::vector<std::vector<PeerMailbox*>> peers;  // [local device][rank]
     std::vector<void*> ipc_opened;                 // mappings to close (per-process mode)
-    unsigned long long epoch = 0;
     std::string why_not_peer;
 };
 
@@ -420,7 +426,6 @@ gaast_status gaast_comm_allreduce_sum(gaast_comm* comm, double* const* dev_sums,
                                                    (comm->peer_ok ? std::string("the vector is longer than the mailbox") : comm->why_not_peer));
         if (use_peer(comm, count)) {
             // this library's own collective: one block per device over peer memory, ordered on each ctx's stream
-            ++comm->epoch;
             int prev = -1;
             cudaGetDevice(&prev);
             for (size_t i = 0; i < comm->ctxs.size(); ++i) {
@@ -428,7 +433,6 @@ gaast_status gaast_comm_allreduce_sum(gaast_comm* comm, double* const* dev_sums,
                 std::memset(&a, 0, sizeof a);
                 for (uint32_t r = 0; r < comm->n_ranks; ++r) a.box[r] = comm->peers[i][r];
                 a.inout = dev_sums[i];
-                a.epoch = comm->epoch;
                 a.rank = int(comm->first_rank + i);
                 a.n_ranks = int(comm->n_ranks);
                 a.count = int(count);

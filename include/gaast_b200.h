@@ -354,7 +354,9 @@ const char* gaast_comm_transport(const gaast_comm* comm);
 gaast_status gaast_comm_set_transport(gaast_comm* comm, int transport);
 /* In place: dev_sums[i] addresses `count` doubles on the i-th LOCAL device of the communicator (all
  * of them after gaast_comm_create, exactly one after gaast_comm_create_rank); afterwards every
- * device holds the element-wise total over all ranks.  Ordered on each ctx's stream, asynchronous. */
+ * device holds the element-wise total over all ranks.  Ordered on each ctx's stream, asynchronous; with
+ * the peer transport a launch carries no host-side state (the epoch lives in device memory) and may be
+ * captured in a CUDA graph.  Every rank must issue the same sequence of all-reduces. */
 gaast_status gaast_comm_allreduce_sum(gaast_comm* comm, double* const* dev_sums, size_t count);
 gaast_status gaast_comm_destroy(gaast_comm* comm);
 

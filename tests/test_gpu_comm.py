@@ -29,6 +29,19 @@ def test_comm_single_rank_is_identity():
                 ctx.sync()
                 assert torch.equal(x.cpu(), torch.arange(66, dtype=torch.float64) * 0.5)
         comm.set_transport(L.COMM_AUTO)
+        # the peer kernel keeps its epoch in device memory: a captured launch can be replayed
+        y = torch.full((66,), 1.5, dtype=torch.float64, device="cuda:0")
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=ctx.torch_stream):
+            comm.allreduce_sum([y.data_ptr()], 66)
+        for _ in range(5):
+            graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y.cpu(), torch.full((66,), 1.5, dtype=torch.float64))
+        comm.allreduce_sum([y.data_ptr()], 66)  # and ordinary launches keep working after the replays
+        ctx.sync()
+        assert torch.equal(y.cpu(), torch.full((66,), 1.5, dtype=torch.float64))
         big = torch.ones(4096, dtype=torch.float64, device="cuda:0")  # longer than the mailbox: NCCL carries it
         torch.cuda.synchronize()
         comm.allreduce_sum([big.data_ptr()], 4096)
