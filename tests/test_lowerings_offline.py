@@ -107,3 +107,19 @@ def test_the_device_cases_of_the_reflection_test_are_expressions_the_reference_a
         host = [{1: T._vec(rng, metric, 4)}, {k: rng.uniform(-1, 1, (comb(5, k), 4)) for k in xgrades}]
         got = oracle_eval(T.SANDWICHES[shape], metric, host, [False, False], 4)
         assert got and all(np.isfinite(v).all() for v in got.values())
+
+
+def test_strict_dense_products_run_one_output_chain_at_a_time():
+    """Strict arithmetic keeps the reference's per-output term order, so a dense product cannot be blocked; with one
+    accumulator per output next to both operands (64 + 64 + 64 values in G(6)) the kernel spilled, so such products
+    take the gather order (one chain at a time).  Narrow products and products of intermediates keep the table order."""
+    n = _notes(g.Plan(None, W.specialize(W.WORKLOADS["cfg3"])), arith=L.ARITH_STRICT)
+    assert "gather(outs=64,terms=4096)" in n, n
+    w = W.WORKLOADS["cfg5"]
+    n = _notes(g.Plan(None, W.specialize(w)), arith=L.ARITH_STRICT)
+    assert "gather(outs=232,terms=792)" in n and "table(outs=66,terms=792)" in n, n
+    n = _notes(g.Plan(None, W.specialize(W.WORKLOADS["cfg1"])), arith=L.ARITH_STRICT)
+    assert "table(outs=3,terms=24)" in n, n
+    # and the kernel builds for sm_100a (from the cache when build() has run)
+    info = g.Plan(None, W.specialize(W.WORKLOADS["cfg3"])).precompile(0, L.ARITH_STRICT, False, True, L.F64)
+    assert "origin=" in info and "fma/elem=4096" in info
