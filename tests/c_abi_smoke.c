@@ -208,6 +208,10 @@ int main(void) {
             double* ptrs[1] = {dev_sum};
             CHECK(gaast_comm_allreduce_sum(comm, ptrs, 3));
             if (gaast_comm_size(comm) != 1) return 1;
+            printf("all-reduce transport: %s\n", gaast_comm_transport(comm));
+            CHECK(gaast_comm_set_transport(comm, GAAST_COMM_NCCL)); /* the same vector through NCCL: still the identity */
+            CHECK(gaast_comm_allreduce_sum(comm, ptrs, 3));
+            CHECK(gaast_comm_set_transport(comm, GAAST_COMM_AUTO));
         } else if (cst != GAAST_ERR_UNSUPPORTED) { /* UNSUPPORTED = NCCL is not installed */
             fprintf(stderr, "gaast_comm_create: %s\n", gaast_last_error());
             return 1;
@@ -226,6 +230,41 @@ int main(void) {
         printf("batch-sum%s ok\n", comm ? " + gaast_comm all-reduce (1 rank)" : "");
         if (comm) gaast_comm_destroy(comm);
         gaast_batch_free(sum_batch);
+    }
+    /* the host-array entry point on page-locked memory of the library's own (gaast_host_alloc; the second input is an
+     * ordinary array pinned in place with gaast_host_register): H2D + kernel + D2H, results equal the resident path's */
+    {
+        void* pin[3] = {NULL, NULL, NULL};
+        void* pout = NULL;
+        const double* hin[3];
+        const uint32_t masks[3] = {0xF, 0xF, 0xF};
+        const int bcast[3] = {0, 0, 0};
+        for (int s = 0; s < 3; ++s) {
+            if (s == 1) {
+                CHECK(gaast_host_register(&host[1][0][0], sizeof host[1]));
+                hin[s] = &host[1][0][0];
+            } else {
+                CHECK(gaast_host_alloc(sizeof host[s], s == 0 ? GAAST_HOST_WRITE_COMBINED : GAAST_HOST_DEFAULT, &pin[s]));
+                memcpy(pin[s], host[s], sizeof host[s]);
+                hin[s] = (const double*)pin[s];
+            }
+        }
+        CHECK(gaast_host_alloc(sizeof got, GAAST_HOST_DEFAULT, &pout));
+        memset(pout, 0, sizeof got);
+        CHECK(gaast_eval_host(plan, hin, masks, bcast, 3, N, N, (double*)pout, GAAST_ENGINE_AUTO, GAAST_ARITH_FMA));
+        CHECK(gaast_eval(plan, in, 3, out, GAAST_ENGINE_AUTO, GAAST_ARITH_FMA));
+        CHECK(gaast_batch_download(out, 2, &got[0][0], N));
+        CHECK(gaast_ctx_sync(ctx));
+        if (memcmp(pout, got, sizeof got) != 0) {
+            fprintf(stderr, "gaast_eval_host on pinned arrays differs from the resident path\n");
+            return 1;
+        }
+        CHECK(gaast_host_unregister(&host[1][0][0]));
+        CHECK(gaast_host_free(pout));
+        CHECK(gaast_host_free(pin[0]));
+        CHECK(gaast_host_free(pin[2]));
+        if (gaast_host_alloc(64, 99, &pout) != GAAST_ERR_INVALID) return 1;
+        printf("eval_host on gaast_host_alloc / gaast_host_register memory ok\n");
     }
     printf("launches: %llu\n", (unsigned long long)gaast_ctx_launch_count(ctx));
 
