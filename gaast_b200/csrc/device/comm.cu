@@ -490,7 +490,11 @@ gaast_status gaast_comm_destroy(gaast_comm* comm) {
             cudaStreamSynchronize(comm->ctxs[i]->stream);
         }
         for (void* p : comm->ipc_opened) cudaIpcCloseMemHandle(p);
-        for (size_t i = 0; i < comm->box.size(); ++i)
+        // A mailbox that was exported over CUDA IPC must outlive every importer's mapping, and the ranks destroy their
+        // communicators at times of their own choosing (a barrier in here could wait for a process that has exited): such
+        // a mailbox (133 KB) is left to the process's teardown.  Within one process nothing else maps it: freed here.
+        const bool exported = comm->n_ranks > comm->ctxs.size();
+        for (size_t i = 0; i < comm->box.size() && !exported; ++i)
             if (comm->box[i]) {
                 cudaSetDevice(comm->ctxs[i]->device);
                 cudaFree(comm->box[i]);
