@@ -888,6 +888,19 @@ struct Gen {
         if (n.k == N_ACC) {
             const Policy pol = (in_prologue || n.uniform) ? P_GATHER : op_policy[n.op];
             if (pol == P_TABLE) {
+                if (size_t(n.op) < table_in_progress.size() && table_in_progress[n.op]) {
+                    // a term of the op that is being emitted, wanted by an EARLIER term of the same op (two rewriting
+                    // passes on one plan leave their new terms in creation order, not in dependency order): emit
+                    // this one now -- the values are SSA names, any topological order is the same kernel
+                    emit(n.a.id);
+                    emit(n.b.id);
+                    emit(n.c.id);
+                    if (emitted[id]) return;
+                    emitted[id] = 1;
+                    emit_node_line(id);
+                    store_if_root(id);
+                    return;
+                }
                 emit_op_table(n.op);
                 return;
             }
@@ -925,18 +938,23 @@ struct Gen {
         emit_node_line(id);
     }
 
+    std::vector<char> table_in_progress;  // per op: emit_op_table is walking its terms
     void emit_op_table(int op) {
-        for (int id : op_accs[op]) {
-            const Node& n = nodes[id];
-            if (!n.live || emitted[id]) continue;
-            if (n.uniform && !in_prologue) continue;
-            emit(n.a.id);
-            emit(n.b.id);
-            emit(n.c.id);
+        if (table_in_progress.size() < op_accs.size()) table_in_progress.resize(op_accs.size(), 0);
+        table_in_progress[op] = 1;
+        for (size_t i = 0; i < op_accs[op].size(); ++i) {
+            const int id = op_accs[op][i];
+            if (!nodes[id].live || emitted[id]) continue;
+            if (nodes[id].uniform && !in_prologue) continue;
+            emit(nodes[id].a.id);
+            emit(nodes[id].b.id);
+            emit(nodes[id].c.id);
+            if (emitted[id]) continue;  // (reached through one of its own operands' readers)
             emitted[id] = 1;
             emit_node_line(id);
             store_if_root(id);
         }
+        table_in_progress[op] = 0;
     }
 
     // Root components are stored (and batch-summed) as soon as their value
@@ -1939,23 +1957,27 @@ CodegenResult generate_kernel(const DevicePlanHost& h, const CodegenOptions& opt
     std::ostringstream notes;
     const int pseudo_op = int(h.ops.size());  // the linear-map lowering's FMAs belong to an extra "op"
     g.op_accs.resize(h.ops.size() + 1);
+    size_t reflected = 0;
+    if (!(opt.variant & 65536)) {
+        reflected = g.lower_reflections(pseudo_op);
+        if (reflected) {
+            for (Node& n : g.nodes) n.live = false;
+            g.mark_live();
+            notes << "reflection(" << reflected << " sandwich" << (reflected > 1 ? "es) " : ") ");
+        }
+    }
     // Opt-in (variant bit 12): measured on cfg5 it frees 12 register rows but does not pay --
     // 7.20 ms vs 7.15 ms at 36 parked rows, and with fewer parked rows (20-28, still no spills)
     // ptxas has no slack left to overlap loads and FMAs: 9.1-9.4 ms.
-    if (opt.variant & 4096) {
+    // Both passes rewrite the same sandwich (the factoring pulls 1/(v.v) out of the last product, the reflection pass
+    // replaces that product): a plan the reflection pass took is left alone -- factoring first handed it terms it then
+    // matched against their old operands (wrong results, found by tests/test_kernels_on_cpu.py).
+    if ((opt.variant & 4096) && !reflected) {
         const size_t factored = g.factor_common_scalars(pseudo_op);
         if (factored) {
             for (Node& n : g.nodes) n.live = false;
             g.mark_live();
             notes << "scalar-factored(" << factored << " products) ";
-        }
-    }
-    if (!(opt.variant & 65536)) {
-        const size_t reflected = g.lower_reflections(pseudo_op);
-        if (reflected) {
-            for (Node& n : g.nodes) n.live = false;
-            g.mark_live();
-            notes << "reflection(" << reflected << " sandwich" << (reflected > 1 ? "es) " : ") ");
         }
     }
     if (!(opt.variant & 2048)) {
