@@ -1663,10 +1663,14 @@ struct Gen {
         }
         // ---- store the finished coset ----
         if (opt.store_out) {
+            // (with the operand in tensor memory whole warps run: a lane past the end of the batch shadows the last
+            // element and must not store -- unguarded, its result from a stale staging row overwrote that element)
+            if (guard_stores) line("if (active) {");
             line(S + "* const ro = s" + std::to_string(root0) + " + e;");
             for (int ol = 0; ol < 16; ++ol)
                 line("ro[dense_out[(oh << " + std::to_string(hb) + ") + " +
                      std::to_string(ol) + "]] = q" + std::to_string(ol) + ";");
+            if (guard_stores) line("}");
         }
         --indent;
         line("}");

@@ -67,6 +67,10 @@ static inline double __hiloint2double(int hi, int lo) {
     std::memcpy(&v, &u, 8);
     return v;
 }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline int __clz(int x) { return x ? __builtin_clz(unsigned(x)) : 32; }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline double __longlong_as_double(long long x) {
     double v;
     std::memcpy(&v, &x, 8);

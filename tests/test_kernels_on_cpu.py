@@ -49,6 +49,7 @@ def test_baseline_workload_kernels(name, batch):
 VARIANTS = [
     ("cfg3", 131072, "rolled dense product, operands staged by TMA"),
     ("cfg3", 8192, "matrix representation, transformed operand parked in tensor memory"),
+    ("cfg3", 131072 | 8192, "rolled product, left operand parked in tensor memory"),
     ("cfg3", 8, "matrix representation, persistent blocks with double-buffered TMA staging"),
     ("cfg3", 131072 | 8, "rolled product, persistent blocks with double-buffered TMA staging"),
     ("cfg3", 256, "lane-parallel TMA issue"),
