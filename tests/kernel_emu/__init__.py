@@ -61,7 +61,7 @@ def host_source(cuda_src: str) -> str:
                 j += 1
             block = lines[i:j + 1]
             text = "\n".join(block)
-            if re.search(r'asm volatile\(\s*"[^"]', text):  # real PTX inside: the shim defines this helper
+            if "__global__" not in text and re.search(r'asm volatile\(\s*"[^"]', text):  # a PTX helper: the shim has it
                 i = j + 1
                 continue
             out.extend(block)

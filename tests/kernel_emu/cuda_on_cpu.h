@@ -30,6 +30,7 @@
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __constant__ static const
+#define __align__(x)
 
 struct EmuDim3 {
     unsigned x = 1, y = 1, z = 1;
@@ -51,6 +52,10 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 static inline int __double2hiint(double v) {
     uint64_t u;
     std::memcpy(&u, &v, 8);
@@ -143,7 +148,7 @@ static inline void emu_mbar_settle(EmuMbar* m) {
         m->pending = uint16_t(m->count_phase & 0x7fffu);
     }
 }
-static inline void mbar_init(unsigned long long* bar, unsigned count) {
+static inline void mbar_init(void* bar, unsigned count) {
     std::lock_guard<std::mutex> g(emu_mbar_mu);
     EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
     m->tx = 0;
@@ -152,14 +157,14 @@ static inline void mbar_init(unsigned long long* bar, unsigned count) {
 }
 static inline void fence_mbar_init() {}
 static inline void fence_proxy_async() {}
-static inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {  // arrive.expect_tx
+static inline void mbar_expect_tx(void* bar, unsigned bytes) {  // arrive.expect_tx
     std::lock_guard<std::mutex> g(emu_mbar_mu);
     EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
     m->tx += int32_t(bytes);
     m->pending -= 1;
     emu_mbar_settle(m);
 }
-static inline void tma_row(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+static inline void tma_row(void* dst, const void* src, unsigned bytes, void* bar) {
     if (bytes % 16u) emu_fault = 2;  // cp.async.bulk moves multiples of 16 bytes
     std::memcpy(dst, src, bytes);
     std::lock_guard<std::mutex> g(emu_mbar_mu);
@@ -167,8 +172,9 @@ static inline void tma_row(double* dst, const double* src, unsigned bytes, unsig
     m->tx -= int32_t(bytes);
     emu_mbar_settle(m);
 }
-static inline void l2_prefetch_row(const double*, unsigned) {}
-static inline void mbar_wait(unsigned long long* bar, unsigned parity) {
+static inline void l2_prefetch_row(const void*, unsigned) {}
+static inline void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) { tma_row(dst, src, bytes, bar); }
+static inline void mbar_wait(void* bar, unsigned parity) {
     const EmuMbar* m = reinterpret_cast<const EmuMbar*>(bar);
     for (long spins = 0;; ++spins) {
         unsigned phase;
