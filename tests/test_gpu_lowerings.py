@@ -134,3 +134,23 @@ def test_matrix_representation_product(ctx, name, shape):
         # two factors in matrix form: 1 024 FMAs + 448 adds = 1 248 FMA-equivalents; G(0,6) = H x M_2(R) x H has one: 2 176
         assert ("fma/elem=1248" in kern) or ("fma/elem=2176" in kern), kern
     assert_close(out.to_host(), want, scale, what=f"{name} {shape} fma [{kern[:70]}]")
+
+
+# Two opt-in tuning variants the CPU run of the generated kernels (tests/test_kernels_on_cpu.py) found broken:
+# scalar factoring ahead of the reflection pass (segfault in the emitter, then wrong results), and the rolled dense
+# product with its operand in tensor memory (lanes past the end of the batch stored over the last element).
+@pytest.mark.parametrize("name,variant", [("cfg5", 4096), ("cfg5", 65536 | 4096), ("cfg3", 131072 | 8192), ("cfg3", 8192)])
+def test_tuning_variants_fixed_after_the_cpu_run(ctx, name, variant):
+    from gaast_b200 import workloads as W
+    w = W.WORKLOADS[name]
+    batch = 262  # two full tiles and a ragged one
+    host = W.host_inputs(w, batch)
+    bcs = [bc for _, bc in w.inputs]
+    want = oracle_eval(w.build, w.metric, host, bcs, batch)
+    scale = oracle_abs_scale(w.build, w.metric, host, bcs, batch)
+    plan = g.Plan(ctx, W.specialize(w))
+    plan.set_tuning(0, variant)
+    dev = [g.DeviceBatch.from_host(ctx, w.n, host[s], broadcast=bc) for s, bc in enumerate(bcs)]
+    out = plan.eval(dev, engine=L.ENGINE_SPECIALIZED, arith=L.ARITH_FMA)
+    ctx.sync()
+    assert_close(out.to_host(), want, scale, what=f"{name} variant {variant} [{plan.last_kernel()[:80]}]")
