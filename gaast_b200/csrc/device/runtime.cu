@@ -339,10 +339,13 @@ size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int 
         gaast::CodegenOptions opt;
         opt.broadcast_slots = broadcast_slots;
         opt.arith = arith;
-        opt.with_sum = with_sum != 0;
+        opt.with_sum = (with_sum & GAAST_SRC_WITH_SUM) != 0;
+        opt.store_out = !(with_sum & GAAST_SRC_NO_STORE);
+        opt.f32 = (with_sum & GAAST_SRC_F32) != 0;
+        if (!opt.store_out && !opt.with_sum) throw Error(GAAST_ERR_INVALID, "kernel_source: a kernel that neither stores nor sums");
         opt.elems_per_thread = plan->force_ept;
         opt.variant = plan->variant;
-        // the kernel gaast_eval launches for an aligned f64 batch (the same choices as eval_impl / precompile)
+        // the kernel gaast_eval launches for an aligned batch (the same choices as eval_impl / precompile)
         opt.pipelined = (opt.variant & 8) != 0;
         opt.tma_stage = !opt.pipelined && !opt.with_sum && !(opt.variant & 1024);
         gaast::CodegenResult cg = gaast::generate_kernel(plan->h, opt);

@@ -260,12 +260,14 @@ class Plan:
     def set_tuning(self, elems_per_thread: int = 0, variant: int = 0):
         L.check(L.lib.gaast_plan_set_tuning(self._h, elems_per_thread, variant))
 
-    def kernel_source(self, broadcast_slots: int = 0, arith: int = L.ARITH_FMA, with_sum: bool = False) -> str:
-        n = L.lib.gaast_plan_kernel_source(self._h, broadcast_slots, arith, int(with_sum), None, 0)
+    def kernel_source(self, broadcast_slots: int = 0, arith: int = L.ARITH_FMA, with_sum: bool = False,
+                      store_out: bool = True, dtype: int = L.F64) -> str:
+        flags = int(bool(with_sum)) | (0 if store_out else 2) | (4 if dtype == L.F32 else 0)  # GAAST_SRC_*
+        n = L.lib.gaast_plan_kernel_source(self._h, broadcast_slots, arith, flags, None, 0)
         if n == 0:
             raise L.GaastError(L.ERR_JIT, L.last_error())
         buf = C.create_string_buffer(n + 1)
-        L.lib.gaast_plan_kernel_source(self._h, broadcast_slots, arith, int(with_sum), buf, n + 1)
+        L.lib.gaast_plan_kernel_source(self._h, broadcast_slots, arith, flags, buf, n + 1)
         return buf.value.decode()
 
     def precompile(self, broadcast_slots: int = 0, arith: int = L.ARITH_FMA, with_sum: bool = False,

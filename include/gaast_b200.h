@@ -209,7 +209,13 @@ uint32_t gaast_plan_num_slots(const gaast_plan* plan);
 /* Grades of batch slot `slot` that the plan actually reads. */
 uint32_t gaast_plan_slot_mask(const gaast_plan* plan, uint32_t slot);
 /* CUDA source of the specialised kernel for this plan (for inspection / offline
- * nvcc -Xptxas -v); returns the length, copies at most `cap` bytes (NUL-terminated). */
+ * nvcc -Xptxas -v / the CPU run of the generated text in tests/kernel_emu); returns the length, copies at most `cap`
+ * bytes (NUL-terminated).  `with_sum` is a set of GAAST_SRC_* flags: 0 / 1 keep their meaning (plain kernel / fused
+ * batch-sum); GAAST_SRC_NO_STORE = the kernel gaast_eval_sum launches with out == NULL (sums only),
+ * GAAST_SRC_F32 = the kernel of the f32 variant. */
+#define GAAST_SRC_WITH_SUM 1
+#define GAAST_SRC_NO_STORE 2
+#define GAAST_SRC_F32 4
 size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, char* buf,
                                 size_t cap);
 /* Generates and compiles the specialised kernel into the in-tree cubin cache

@@ -50,6 +50,10 @@ pub const GAAST_HOST_WRITE_COMBINED: c_int = 1;
 pub const GAAST_COMM_AUTO: c_int = 0;
 pub const GAAST_COMM_NCCL: c_int = 1;
 pub const GAAST_COMM_PEER: c_int = 2;
+// flags of gaast_plan_kernel_source's `with_sum` argument
+pub const GAAST_SRC_WITH_SUM: c_int = 1;
+pub const GAAST_SRC_NO_STORE: c_int = 2;
+pub const GAAST_SRC_F32: c_int = 4;
 
 /// `IndividualCompMul` (ast/base_types.rs:46-55) with (grade, index) resolved to buffer slots.
 #[repr(C)]

@@ -97,10 +97,10 @@ _cache: Dict[str, C.CDLL] = {}
 _tmp = None
 
 
-def _compile(cuda_src: str) -> C.CDLL:
+def _compile(cuda_src: str, f32: bool = False) -> C.CDLL:
     global _tmp
     body = host_source(cuda_src)
-    key = hashlib.sha256(body.encode()).hexdigest()[:24]  # (of the text that is compiled: dlopen caches by path)
+    key = hashlib.sha256((body + str(f32)).encode()).hexdigest()[:24]  # (of the text that is compiled: dlopen caches by path)
     if key in _cache:
         return _cache[key]
     if _tmp is None:
@@ -120,7 +120,8 @@ def _compile(cuda_src: str) -> C.CDLL:
     so = os.path.join(_tmp.name, key + ".so")
     with open(cpp, "w") as f:
         f.write(text)
-    cmd = ["g++", *FLAGS, "-shared", "-I", _tmp.name, cpp, "-o", so]
+    # (the f32 variant defines GAAST_EMU_F32: the precompiled header does not apply, g++ reads the header itself)
+    cmd = ["g++", *FLAGS, *(["-DGAAST_EMU_F32"] if f32 else []), "-shared", "-I", _tmp.name, cpp, "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ rejected the generated kernel:\n" + r.stderr[-3000:])
@@ -143,7 +144,7 @@ FAULTS = {1: "a barrier / shuffle in sequential mode", 2: "a bulk copy that is n
 
 def run_generated_kernel(ast, inputs: Sequence[Dict[int, np.ndarray]], broadcast: Sequence[bool], batch: int,
                          arith: int = L.ARITH_FMA, with_sum: bool = False, tuning: Optional[Tuple[int, int]] = None,
-                         grid: Optional[int] = None):
+                         grid: Optional[int] = None, store_out: bool = True, dtype=np.float64):
     """Evaluate the specialised engine's kernel for `ast` (a gaast_b200.expr.SpecializedAst) on host arrays.
     inputs[slot] = {grade: (C(n,k), batch) array, or (C(n,k), 1) for a broadcast slot}.
     Returns (out: {grade: (C, batch)}, sums or None, info) where info = {"notes", "threads", "ept", "grid", "source"}."""
@@ -153,8 +154,10 @@ def run_generated_kernel(ast, inputs: Sequence[Dict[int, np.ndarray]], broadcast
     n = plan.n
     slots = plan.num_slots()
     bmask = sum(1 << s for s in range(slots) if broadcast[s])
-    src = plan.kernel_source(broadcast_slots=bmask, arith=arith, with_sum=with_sum)
-    lib = _compile(src)
+    f32 = dtype == np.float32
+    src = plan.kernel_source(broadcast_slots=bmask, arith=arith, with_sum=with_sum, store_out=store_out,
+                             dtype=L.F32 if f32 else L.F64)
+    lib = _compile(src, f32)
     threads, ept = lib.emu_threads(), lib.emu_elems_per_thread()
     per_block = threads * ept
     padded = (batch + per_block - 1) // per_block * per_block  # rows padded as the runtime pads an odd batch
@@ -164,14 +167,14 @@ def run_generated_kernel(ast, inputs: Sequence[Dict[int, np.ndarray]], broadcast
     for s in range(slots):
         for k in plan.slot_grades(s):
             rows = comb(n, k)
-            src_arr = np.asarray(inputs[s][k], dtype=np.float64)
+            src_arr = np.asarray(inputs[s][k], dtype=dtype)
             if broadcast[s]:
-                arr = np.zeros((rows, 2))
+                arr = np.zeros((rows, 4), dtype=dtype)
                 arr[:, 0] = src_arr.reshape(rows, -1)[:, 0]
                 launch.bcast[si >> 6] |= 1 << (si & 63)
             else:
                 assert src_arr.shape == (rows, batch), (src_arr.shape, rows, batch)
-                arr = np.full((rows, padded), np.nan)  # the padding is never part of a result
+                arr = np.full((rows, padded), np.nan, dtype=dtype)  # the padding is never part of a result
                 arr[:, :batch] = src_arr
             keep.append(arr)
             launch.sptr[si] = arr.ctypes.data
@@ -179,7 +182,7 @@ def run_generated_kernel(ast, inputs: Sequence[Dict[int, np.ndarray]], broadcast
             si += 1
     outs = {}
     for k in plan.root_grades():
-        arr = np.full((comb(n, k), padded), np.nan)
+        arr = np.full((comb(n, k), padded), np.nan, dtype=dtype)
         outs[k] = arr
         launch.sptr[si] = arr.ctypes.data
         launch.srow[si] = padded
@@ -196,15 +199,16 @@ def run_generated_kernel(ast, inputs: Sequence[Dict[int, np.ndarray]], broadcast
     # gaast_eval's contract for the kernel `kernel_source` returns (the ALIGNED variant, csrc/device/runtime.cu): rows on
     # 16-byte boundaries and an even element count -- an odd batch into a library-owned output is launched over its
     # padding column too; with a batch-sum the runtime switches to the one-element-per-thread variant instead
-    launch_n = batch + (batch & 1)
+    quantum = 4 if f32 else 2  # elements per 16 bytes
+    launch_n = (batch + quantum - 1) // quantum * quantum
     if with_sum:
-        assert batch % max(2, ept) == 0, "emulated batch-sum: use an even batch (the padding must not reach the sums)"
+        assert batch % max(quantum, ept) == 0, "emulated batch-sum: use an aligned batch (the padding must not reach the sums)"
     launch.n = launch_n
     launch.consts = consts.ctypes.data
     launch.uniform = uniform.ctypes.data
     launch.partials = partials.ctypes.data
     launch.n_sum_cols = root_cols
-    launch.store_out = 1
+    launch.store_out = int(store_out)
     launch.grid = grid
     launch.threaded = int(threaded)
     if "gaast_uniform(" in src:

@@ -42,6 +42,20 @@ struct double2 {
     double x, y;
 };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+struct float2 {
+    float x, y;
+};
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline unsigned __float_as_uint(float v) {
+    unsigned u;
+    std::memcpy(&u, &v, 4);
+    return u;
+}
+static inline float __uint_as_float(unsigned u) {
+    float v;
+    std::memcpy(&v, &u, 4);
+    return v;
+}
 template <class T>
 static inline T __ldg(const T* p) {
     T v;
@@ -116,19 +130,25 @@ static inline size_t __cvta_generic_to_shared(const void* p) {
 }
 
 // ---- the shared-memory staging area of parked rows ---------------------------------------------
+// (GAAST_EMU_F32: the f32 variant's kernels park binary32 values under the same helper names)
+#ifdef GAAST_EMU_F32
+typedef float EmuScalar;
+#else
+typedef double EmuScalar;
+#endif
 template <int OFF>
-static inline void xs_st(unsigned base, double v) {
-    std::memcpy(reinterpret_cast<char*>(sums) + base + OFF, &v, 8);
+static inline void xs_st(unsigned base, EmuScalar v) {
+    std::memcpy(reinterpret_cast<char*>(sums) + base + OFF, &v, sizeof v);
 }
 template <int OFF>
-static inline double xs_ld(unsigned base) {
-    double v;
-    std::memcpy(&v, reinterpret_cast<const char*>(sums) + base + OFF, 8);
+static inline EmuScalar xs_ld(unsigned base) {
+    EmuScalar v;
+    std::memcpy(&v, reinterpret_cast<const char*>(sums) + base + OFF, sizeof v);
     return v;
 }
-static inline double xs_ldd(unsigned addr) {
-    double v;
-    std::memcpy(&v, reinterpret_cast<const char*>(sums) + addr, 8);
+static inline EmuScalar xs_ldd(unsigned addr) {
+    EmuScalar v;
+    std::memcpy(&v, reinterpret_cast<const char*>(sums) + addr, sizeof v);
     return v;
 }
 

@@ -288,6 +288,58 @@ def test_sandwich_rich_random_expression_kernels(seed):
     assert_close(out, want, scale, rel=1e-9, what=f"seed {seed} [{info['notes']}]: {tree}")
 
 
+# ---- the f32 variant and the sums-only kernels ---------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(W.WORKLOADS))
+def test_f32_kernels(name):
+    """binary32 batches and arithmetic: strict = the plan's operation sequence replayed in binary32, bit for bit; FMA
+    arithmetic (lowerings on) within 1e-5 of the f64 oracle's scale (the bars of tests/test_gpu_f32.py)."""
+    from tests.helpers import REL_TOL_F32, run_plan_numpy
+    w = W.WORKLOADS[name]
+    batch = 262  # not a multiple of 4: the aligned f32 kernel is launched over the padding
+    host = [{k: v.astype(np.float32) for k, v in d.items()} for d in W.host_inputs(w, batch)]
+    host64 = [{k: v.astype(np.float64) for k, v in d.items()} for d in host]
+    bcs = [bc for _, bc in w.inputs]
+    ast = W.specialize(w)
+    with np.errstate(all="ignore"):
+        want32 = run_plan_numpy(ast.plan_dict(), host, batch, dtype=np.float32)
+    out, _, info = run_generated_kernel(ast, host, bcs, batch, arith=L.ARITH_STRICT, dtype=np.float32)
+    assert_bit_exact(out, want32, f"{name} f32 strict [{info['notes']}]")
+    out, _, info = run_generated_kernel(ast, host, bcs, batch, arith=L.ARITH_FMA, dtype=np.float32)
+    want = oracle_eval(w.build, w.metric, host64, bcs, batch)
+    scale = oracle_abs_scale(w.build, w.metric, host64, bcs, batch)
+    assert_close({k: v.astype(np.float64) for k, v in out.items()}, want, scale, rel=REL_TOL_F32, what=f"{name} f32 fma")
+
+
+@pytest.mark.parametrize("name", sorted(W.WORKLOADS))
+def test_sums_only_kernels(name):
+    """gaast_eval_sum with out == NULL: the kernel keeps the batch-sum and stores nothing."""
+    w = W.WORKLOADS[name]
+    batch = 300
+    host = W.host_inputs(w, batch)
+    bcs = [bc for _, bc in w.inputs]
+    want = oracle_eval(w.build, w.metric, host, bcs, batch)
+    scale = oracle_abs_scale(w.build, w.metric, host, bcs, batch)
+    out, sums, info = run_generated_kernel(W.specialize(w), host, bcs, batch, arith=L.ARITH_FMA, with_sum=True,
+                                           store_out=False, grid=2)
+    assert all(np.isnan(v).all() for v in out.values()), "a sums-only kernel stored results"
+    for k in want:
+        ref = want[k].sum(axis=1)
+        tol = 1e-12 * np.maximum(np.abs(want[k]).sum(axis=1), scale[k].sum(axis=1)) + 1e-300
+        assert (np.abs(sums[k] - ref) <= tol).all(), f"{name} [{info['notes']}]: batch-sum of grade {k} off"
+
+
+@pytest.mark.parametrize("seed", _random_seeds()[:24])
+def test_random_expression_kernels_f32(seed):
+    from tests.helpers import run_plan_numpy
+    from tests.test_random_exprs import BATCH, evaluate_case
+    n, metric, slots, inputs, want, ast, oracle_error, mine_error = evaluate_case(seed)
+    in32 = [{k: v.astype(np.float32) for k, v in d.items()} for d in inputs]
+    with np.errstate(all="ignore"):
+        want32 = run_plan_numpy(ast.plan_dict(), in32, BATCH, dtype=np.float32)
+        out, _, info = run_generated_kernel(ast, in32, [bc for _, bc in slots], BATCH, arith=L.ARITH_STRICT, dtype=np.float32)
+    assert_bit_exact(out, want32, f"seed {seed} f32 [{info['notes']}]")
+
+
 # ---- the harness itself ---------------------------------------------------------------------------------
 def test_the_harness_sees_a_wrong_kernel():
     """A kernel with one sign flipped must fail the comparison (the emulation is not comparing the oracle to itself)."""
