@@ -101,6 +101,7 @@ constexpr int kEmuMaxThreads = 1024;
 constexpr size_t kEmuSmemBytes = 256 * 1024;
 alignas(1024) double sums[kEmuSmemBytes / 8];  // `extern __shared__ double sums[];` of the generated kernels
 static pthread_barrier_t emu_block_bar;
+static thread_local pthread_barrier_t* emu_block_bar_p = &emu_block_bar;  // (the peer all-reduce test runs one block per rank AT ONCE)
 static pthread_barrier_t emu_warp_bar[kEmuMaxThreads / 32];
 static double emu_shfl[kEmuMaxThreads];
 static bool emu_threaded = false;  // false: threads of a block run one after the other (kernels without barriers)
@@ -111,8 +112,9 @@ static inline void __syncthreads() {
         emu_fault = 1;
         return;
     }
-    pthread_barrier_wait(&emu_block_bar);
+    pthread_barrier_wait(emu_block_bar_p);
 }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline double __shfl_xor_sync(unsigned, double v, int d) {
     if (!emu_threaded) {
         emu_fault = 1;
