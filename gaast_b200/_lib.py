@@ -110,6 +110,8 @@ PROTOTYPES = {
     "gaast_plan_num_slots": (u32, vp),
     "gaast_plan_slot_mask": (u32, vp, u32),
     "gaast_plan_kernel_source": (C.c_size_t, vp, u64, C.c_int, C.c_int, C.c_char_p, C.c_size_t),
+    "gaast_plan_kernel_source_sparse": (C.c_size_t, vp, u64, C.c_int, C.c_int, C.POINTER(C.POINTER(u64)), u32, C.c_char_p,
+                                        C.c_size_t),
     "gaast_plan_precompile": (C.c_int, vp, u64, C.c_int, C.c_int, C.c_int),
     "gaast_plan_precompile_typed": (C.c_int, vp, u64, C.c_int, C.c_int, C.c_int, C.c_int),
     "gaast_plan_set_tuning": (C.c_int, vp, C.c_int, C.c_int),

@@ -331,8 +331,8 @@ gaast_status gaast_plan_set_tuning(gaast_plan* plan, int elems_per_thread, int v
     });
 }
 
-size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, char* buf,
-                                size_t cap) {
+static size_t kernel_source_impl(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum,
+                                 const uint64_t* const* present, uint32_t n_present, char* buf, size_t cap) {
     size_t len = 0;
     gaast_status st = guard([&] {
         if (!plan) throw Error(GAAST_ERR_INVALID, "null plan");
@@ -348,6 +348,16 @@ size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int 
         // the kernel gaast_eval launches for an aligned batch (the same choices as eval_impl / precompile)
         opt.pipelined = (opt.variant & 8) != 0;
         opt.tma_stage = !opt.pipelined && !opt.with_sum && !(opt.variant & 1024);
+        if (present) {
+            const gaast::DevicePlanHost& h = plan->h;
+            if (n_present != h.n_in_streams) throw Error(GAAST_ERR_SHAPE, "kernel_source_sparse: one bitmap pointer per (slot, grade) the plan reads");
+            opt.sparse.resize(h.streams.size());
+            for (uint32_t i = 0; i < n_present; ++i) {
+                if (!present[i]) continue;
+                const size_t words = (size_t(h.streams[i].rows) + 63) / 64;
+                opt.sparse[i].assign(present[i], present[i] + words);
+            }
+        }
         gaast::CodegenResult cg = gaast::generate_kernel(plan->h, opt);
         len = cg.source.size();
         if (buf && cap) {
@@ -357,6 +367,16 @@ size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int 
         }
     });
     return st == GAAST_OK ? len : 0;
+}
+
+size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, char* buf,
+                                size_t cap) {
+    return kernel_source_impl(plan, broadcast_slots, arith, with_sum, nullptr, 0, buf, cap);
+}
+
+size_t gaast_plan_kernel_source_sparse(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum,
+                                       const uint64_t* const* present, uint32_t n_present, char* buf, size_t cap) {
+    return kernel_source_impl(plan, broadcast_slots, arith, with_sum, present, n_present, buf, cap);
 }
 
 gaast_status gaast_plan_precompile(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, int store_out) {

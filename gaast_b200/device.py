@@ -261,13 +261,30 @@ class Plan:
         L.check(L.lib.gaast_plan_set_tuning(self._h, elems_per_thread, variant))
 
     def kernel_source(self, broadcast_slots: int = 0, arith: int = L.ARITH_FMA, with_sum: bool = False,
-                      store_out: bool = True, dtype: int = L.F64) -> str:
+                      store_out: bool = True, dtype: int = L.F64, present: Optional[Dict] = None) -> str:
+        """`present` = {(slot, grade): stored component indices} for inputs in sparse per-grade storage."""
         flags = int(bool(with_sum)) | (0 if store_out else 2) | (4 if dtype == L.F32 else 0)  # GAAST_SRC_*
-        n = L.lib.gaast_plan_kernel_source(self._h, broadcast_slots, arith, flags, None, 0)
+        if present:
+            keys = [(s, k) for s in range(self.num_slots()) for k in self.slot_grades(s)]
+            maps = []
+            for s, k in keys:
+                if (s, k) not in present:
+                    maps.append(None)
+                    continue
+                bits = (L.u64 * ((comb(self.n, k) + 63) // 64))()
+                for i in present[(s, k)]:
+                    bits[int(i) // 64] |= 1 << (int(i) % 64)
+                maps.append(bits)
+            ptrs = (C.POINTER(L.u64) * max(1, len(keys)))(*[C.cast(b, C.POINTER(L.u64)) if b is not None else None for b in maps])
+            call = lambda buf, cap: L.lib.gaast_plan_kernel_source_sparse(self._h, broadcast_slots, arith, flags, ptrs,  # noqa: E731
+                                                                          len(keys), buf, cap)
+        else:
+            call = lambda buf, cap: L.lib.gaast_plan_kernel_source(self._h, broadcast_slots, arith, flags, buf, cap)  # noqa: E731
+        n = call(None, 0)
         if n == 0:
             raise L.GaastError(L.ERR_JIT, L.last_error())
         buf = C.create_string_buffer(n + 1)
-        L.lib.gaast_plan_kernel_source(self._h, broadcast_slots, arith, flags, buf, n + 1)
+        call(buf, n + 1)
         return buf.value.decode()
 
     def precompile(self, broadcast_slots: int = 0, arith: int = L.ARITH_FMA, with_sum: bool = False,

@@ -218,6 +218,11 @@ uint32_t gaast_plan_slot_mask(const gaast_plan* plan, uint32_t slot);
 #define GAAST_SRC_F32 4
 size_t gaast_plan_kernel_source(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum, char* buf,
                                 size_t cap);
+/* The same for inputs in sparse per-grade storage (gaast_batch_alloc_sparse): present[i] is the presence bitmap of the
+ * i-th (slot, grade) array the plan reads -- slots in order, within a slot the grades of gaast_plan_slot_mask in
+ * ascending order -- or NULL where that array is dense; n_present = the number of such arrays. */
+size_t gaast_plan_kernel_source_sparse(gaast_plan* plan, uint64_t broadcast_slots, int arith, int with_sum,
+                                       const uint64_t* const* present, uint32_t n_present, char* buf, size_t cap);
 /* Generates and compiles the specialised kernel into the in-tree cubin cache
  * without a device (the plan may have been created with ctx == NULL).  Used
  * by the build step so that the shipped workloads never compile at run time. */

@@ -135,6 +135,7 @@ extern "C" {
     pub fn gaast_plan_num_slots(plan: *const gaast_plan) -> u32;
     pub fn gaast_plan_slot_mask(plan: *const gaast_plan, slot: u32) -> u32;
     pub fn gaast_plan_kernel_source(plan: *mut gaast_plan, broadcast_slots: u64, arith: c_int, with_sum: c_int, buf: *mut c_char, cap: usize) -> usize;
+    pub fn gaast_plan_kernel_source_sparse(plan: *mut gaast_plan, broadcast_slots: u64, arith: c_int, with_sum: c_int, present: *const *const u64, n_present: u32, buf: *mut c_char, cap: usize) -> usize;
     pub fn gaast_plan_precompile(plan: *mut gaast_plan, broadcast_slots: u64, arith: c_int, with_sum: c_int, store_out: c_int) -> c_int;
     pub fn gaast_plan_precompile_typed(plan: *mut gaast_plan, broadcast_slots: u64, arith: c_int, with_sum: c_int, store_out: c_int, dtype: c_int) -> c_int;
     pub fn gaast_plan_set_tuning(plan: *mut gaast_plan, elems_per_thread: c_int, variant: c_int) -> c_int;

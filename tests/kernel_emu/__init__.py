@@ -144,9 +144,12 @@ FAULTS = {1: "a barrier / shuffle in sequential mode", 2: "a bulk copy that is n
 
 def run_generated_kernel(ast, inputs: Sequence[Dict[int, np.ndarray]], broadcast: Sequence[bool], batch: int,
                          arith: int = L.ARITH_FMA, with_sum: bool = False, tuning: Optional[Tuple[int, int]] = None,
-                         grid: Optional[int] = None, store_out: bool = True, dtype=np.float64):
+                         grid: Optional[int] = None, store_out: bool = True, dtype=np.float64,
+                         present: Optional[Dict] = None):
     """Evaluate the specialised engine's kernel for `ast` (a gaast_b200.expr.SpecializedAst) on host arrays.
     inputs[slot] = {grade: (C(n,k), batch) array, or (C(n,k), 1) for a broadcast slot}.
+    present = {(slot, grade): stored component indices} for inputs in sparse per-grade storage: that grade's array
+    then holds the stored rows only, in component order.
     Returns (out: {grade: (C, batch)}, sums or None, info) where info = {"notes", "threads", "ept", "grid", "source"}."""
     plan = g.Plan(None, ast)
     if tuning is not None:
@@ -156,7 +159,7 @@ def run_generated_kernel(ast, inputs: Sequence[Dict[int, np.ndarray]], broadcast
     bmask = sum(1 << s for s in range(slots) if broadcast[s])
     f32 = dtype == np.float32
     src = plan.kernel_source(broadcast_slots=bmask, arith=arith, with_sum=with_sum, store_out=store_out,
-                             dtype=L.F32 if f32 else L.F64)
+                             dtype=L.F32 if f32 else L.F64, present=present)
     lib = _compile(src, f32)
     threads, ept = lib.emu_threads(), lib.emu_elems_per_thread()
     per_block = threads * ept
@@ -166,7 +169,7 @@ def run_generated_kernel(ast, inputs: Sequence[Dict[int, np.ndarray]], broadcast
     si = 0
     for s in range(slots):
         for k in plan.slot_grades(s):
-            rows = comb(n, k)
+            rows = len(present[(s, k)]) if present and (s, k) in present else comb(n, k)
             src_arr = np.asarray(inputs[s][k], dtype=dtype)
             if broadcast[s]:
                 arr = np.zeros((rows, 4), dtype=dtype)

@@ -340,6 +340,67 @@ def test_random_expression_kernels_f32(seed):
     assert_bit_exact(out, want32, f"seed {seed} f32 [{info['notes']}]")
 
 
+# ---- sparse per-grade storage of inputs --------------------------------------------------------------------
+def _sparsify(rng, n, k, batch, keep):
+    c = comb(n, k)
+    idx = sorted(rng.choice(c, size=min(keep, c), replace=False).tolist())
+    compact = rng.uniform(-1, 1, (len(idx), batch))
+    dense = np.zeros((c, batch))
+    dense[idx] = compact
+    return idx, compact, dense
+
+
+def test_sparse_bivector_in_the_cfg5_sandwich():
+    """G(8,4) (V*X*V.vinv()).g(2) with X storing 9 of its 66 bivector components: the oracle is the reference on the
+    dense multivectors with the zeros written out (tests/test_gpu_sparse.py on the device)."""
+    w = W.WORKLOADS["cfg5"]
+    batch = 131
+    rng = np.random.default_rng(17)
+    host = W.host_inputs(w, batch)
+    idx, compact, dense = _sparsify(rng, w.n, 2, batch, 9)
+    host[1] = {2: dense}
+    want = oracle_eval(w.build, w.metric, host, [False, False], batch)
+    scale = oracle_abs_scale(w.build, w.metric, host, [False, False], batch)
+    stored = [host[0], {2: compact}]
+    present = {(1, 2): idx}
+    out, _, info = run_generated_kernel(W.specialize(w), stored, [False, False], batch, arith=L.ARITH_STRICT, present=present)
+    assert_bit_exact(out, want, "sparse X strict")
+    out, _, info = run_generated_kernel(W.specialize(w), stored, [False, False], batch, arith=L.ARITH_FMA, present=present)
+    assert_close(out, want, scale, what=f"sparse X fma [{info['notes']}]")
+    body = info["source"][info["source"].rindex('extern "C" __global__'):]
+    assert body.count("d_load(") == 12 + 9, "the kernel loads the 12 components of V and the 9 stored ones of X"
+
+
+@pytest.mark.parametrize("shape", ["A*B", "A*B+B", "A*B.rev()*A"])
+@pytest.mark.parametrize("seed", [23, 24])
+def test_sparse_full_multivectors(shape, seed):
+    """G(4,1) with both operands sparse in several grades, one grade stored completely, one grade empty."""
+    n = 5
+    metric = [1.0, 1.0, 1.0, -1.0, 1.0]
+    batch = 70
+    rng = np.random.default_rng(seed)
+    full = tuple(range(n + 1))
+    keep = {0: 1, 1: 2, 2: 4, 3: 0, 4: 5, 5: 1}  # grade 3 stores nothing, grade 4 everything
+    build = {"A*B": lambda a, b: a * b, "A*B+B": lambda a, b: a * b + b, "A*B.rev()*A": lambda a, b: a * b.rev() * a}[shape]
+    stored, dense, present = [], [], {}
+    for s in range(2):
+        st, de = {}, {}
+        for k in full:
+            idx, compact, d = _sparsify(rng, n, k, batch, keep[k])
+            st[k], de[k] = compact, d
+            if len(idx) < comb(n, k):
+                present[(s, k)] = idx
+        stored.append(st)
+        dense.append(de)
+    want = oracle_eval(build, metric, dense, [False, False], batch)
+    scale = oracle_abs_scale(build, metric, dense, [False, False], batch)
+    ast = build(pmv(Input(0, full)), pmv(Input(1, full))).specialize(metric)
+    out, _, info = run_generated_kernel(ast, stored, [False, False], batch, arith=L.ARITH_STRICT, present=present)
+    assert_bit_exact(out, want, f"{shape} sparse strict")
+    out, _, info = run_generated_kernel(ast, stored, [False, False], batch, arith=L.ARITH_FMA, present=present)
+    assert_close(out, want, scale, what=f"{shape} sparse fma [{info['notes']}]")
+
+
 # ---- the harness itself ---------------------------------------------------------------------------------
 def test_the_harness_sees_a_wrong_kernel():
     """A kernel with one sign flipped must fail the comparison (the emulation is not comparing the oracle to itself)."""
