@@ -97,12 +97,8 @@ _cache: Dict[str, C.CDLL] = {}
 _tmp = None
 
 
-def _compile(cuda_src: str, f32: bool = False) -> C.CDLL:
+def _ensure_tmp():
     global _tmp
-    body = host_source(cuda_src)
-    key = hashlib.sha256((body + str(f32)).encode()).hexdigest()[:24]  # (of the text that is compiled: dlopen caches by path)
-    if key in _cache:
-        return _cache[key]
     if _tmp is None:
         # one precompiled header of the shim per session: the standard headers cost more than most kernels
         _tmp = tempfile.TemporaryDirectory(prefix="gaast_kernel_emu_")
@@ -113,6 +109,15 @@ def _compile(cuda_src: str, f32: bool = False) -> C.CDLL:
                             os.path.join(_tmp.name, "cuda_on_cpu.h.gch")], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("g++ rejected cuda_on_cpu.h:\n" + r.stderr[-3000:])
+
+
+def _compile(cuda_src: str, f32: bool = False) -> C.CDLL:
+    global _tmp
+    body = host_source(cuda_src)
+    key = hashlib.sha256((body + str(f32)).encode()).hexdigest()[:24]  # (of the text that is compiled: dlopen caches by path)
+    if key in _cache:
+        return _cache[key]
+    _ensure_tmp()
     has_uniform = 'void __launch_bounds__(32) gaast_uniform(' in cuda_src
     text = ('#include "cuda_on_cpu.h"\n' + ("#define EMU_HAS_UNIFORM 1\n" if has_uniform else "") + body +
             '\n#include "driver.inc"\n')
@@ -130,6 +135,47 @@ def _compile(cuda_src: str, f32: bool = False) -> C.CDLL:
     lib.emu_launch.restype = C.c_int
     _cache[key] = lib
     return lib
+
+
+def prefetch(ast, broadcast, variants, tuning=None):
+    """Compile the kernels of several (arith, with_sum, store_out, dtype) variants of one plan side by side (g++ is the
+    cost of a test here, and the box has more than one core); run_generated_kernel then finds them in the cache."""
+    from concurrent.futures import ThreadPoolExecutor
+    plan = g.Plan(None, ast)
+    if tuning is not None:
+        plan.set_tuning(*tuning)
+    bmask = sum(1 << s for s in range(plan.num_slots()) if broadcast[s])
+    jobs = []
+    for arith, with_sum, store_out, dtype in variants:
+        f32 = dtype == np.float32
+        jobs.append((plan.kernel_source(broadcast_slots=bmask, arith=arith, with_sum=with_sum, store_out=store_out,
+                                        dtype=L.F32 if f32 else L.F64), f32))
+    _ensure_tmp()  # (the precompiled header first)
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        list(ex.map(lambda j: _compile(*j), jobs))
+
+
+def prefetch_many(cases, workers: int = 6):
+    """cases: iterable of (ast, broadcast flags, arith, dtype[, with_sum[, tuning]]).  Compiles their kernels side by
+    side; a plan the generator refuses is left for the test to report."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = []
+    for case in cases:
+        ast, broadcast, arith, dtype = case[:4]
+        with_sum = case[4] if len(case) > 4 else False
+        plan = g.Plan(None, ast)
+        if len(case) > 5 and case[5] is not None:
+            plan.set_tuning(*case[5])
+        bmask = sum(1 << s for s in range(plan.num_slots()) if broadcast[s])
+        f32 = dtype == np.float32
+        try:
+            jobs.append((plan.kernel_source(broadcast_slots=bmask, arith=arith, with_sum=with_sum,
+                                            dtype=L.F32 if f32 else L.F64), f32))
+        except L.GaastError:
+            pass
+    _ensure_tmp()
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        list(ex.map(lambda j: _compile(*j), jobs))
 
 
 def needs_threads(cuda_src: str) -> bool:

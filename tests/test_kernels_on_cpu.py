@@ -16,7 +16,7 @@ from gaast_b200 import _lib as L
 from gaast_b200 import workloads as W
 from gaast_b200.expr import Input, mv as pmv
 from tests.helpers import assert_bit_exact, assert_close, oracle_abs_scale, oracle_eval
-from tests.kernel_emu import run_generated_kernel
+from tests.kernel_emu import prefetch, prefetch_many, run_generated_kernel
 
 pytestmark = pytest.mark.timeout(300)
 
@@ -24,6 +24,7 @@ pytestmark = pytest.mark.timeout(300)
 def _both_arithmetics(ast, build, metric, host, bcs, batch, what, fma_rel=1e-12, **kw):
     want = oracle_eval(build, metric, host, bcs, batch)
     scale = oracle_abs_scale(build, metric, host, bcs, batch)
+    prefetch(ast, bcs, [(L.ARITH_FMA, False, True, np.float64), (L.ARITH_STRICT, False, True, np.float64)])
     out, _, info = run_generated_kernel(ast, host, bcs, batch, arith=L.ARITH_STRICT, **kw)
     assert_bit_exact(out, want, f"{what} strict [{info['notes']}]")
     out, _, info = run_generated_kernel(ast, host, bcs, batch, arith=L.ARITH_FMA, **kw)
@@ -68,8 +69,17 @@ VARIANTS = [
 ]
 
 
+@pytest.fixture(scope="module")
+def variant_kernels_compiled():
+    cases = [(W.specialize(W.WORKLOADS[n]), [bc for _, bc in W.WORKLOADS[n].inputs], L.ARITH_FMA, np.float64, False, (0, v))
+             for n, v, _ in VARIANTS]
+    cases += [(W.specialize(W.WORKLOADS[n]), [bc for _, bc in W.WORKLOADS[n].inputs], L.ARITH_FMA, np.float64, True, (0, v))
+              for n, v, _ in SUM_CASES]
+    prefetch_many(cases)
+
+
 @pytest.mark.parametrize("name,variant,what", VARIANTS, ids=[f"{n}-v{v}" for n, v, _ in VARIANTS])
-def test_kernel_variants(name, variant, what):
+def test_kernel_variants(name, variant, what, variant_kernels_compiled):
     w = W.WORKLOADS[name]
     batch = 262  # two full tiles of 128 and a ragged one
     host = W.host_inputs(w, batch)
@@ -99,7 +109,7 @@ SUM_CASES = [
 
 
 @pytest.mark.parametrize("name,variant,what", SUM_CASES, ids=[f"{n}-v{v}" for n, v, _ in SUM_CASES])
-def test_batch_sum_kernels(name, variant, what):
+def test_batch_sum_kernels(name, variant, what, variant_kernels_compiled):
     w = W.WORKLOADS[name]
     batch = 600
     host = W.host_inputs(w, batch)
@@ -230,10 +240,19 @@ MATREP_SHAPES = {"A*B": lambda a, b, c: a * b, "C+A*B": lambda a, b, c: c + a * 
                  "A*B.ginvol()": lambda a, b, c: a * b.ginvol()}
 
 
-@pytest.mark.parametrize("shape,name", [
-    pytest.param(shape, name, id=f"{shape}-{name}") for shape in sorted(MATREP_SHAPES) for name in sorted(SIGNATURES_6)
-    if shape == "A*B" or name in ("G(3,3)", "G(0,6)")])
-def test_matrix_representation_kernels(shape, name):
+MATREP_CASES = [(shape, name) for shape in sorted(MATREP_SHAPES) for name in sorted(SIGNATURES_6)
+                if shape == "A*B" or name in ("G(3,3)", "G(0,6)")]
+
+
+@pytest.fixture(scope="module")
+def matrep_kernels_compiled():
+    full = tuple(range(7))
+    prefetch_many([(MATREP_SHAPES[shape](*[pmv(Input(s, full)) for s in range(3)]).specialize(SIGNATURES_6[name]),
+                    [False] * 3, L.ARITH_FMA, np.float64) for shape, name in MATREP_CASES])
+
+
+@pytest.mark.parametrize("shape,name", [pytest.param(shape, name, id=f"{shape}-{name}") for shape, name in MATREP_CASES])
+def test_matrix_representation_kernels(shape, name, matrep_kernels_compiled):
     """The G(6) product through M_2(R) x F x M_2(R), every +-1 signature: FMA arithmetic only (strict arithmetic runs
     the reference's 4 096 terms; test_baseline_workload_kernels covers that kernel)."""
     metric = SIGNATURES_6[name]
@@ -258,8 +277,31 @@ def _random_seeds():
     return GPU_SEEDS[:48]
 
 
+@pytest.fixture(scope="module")
+def random_kernels_compiled():
+    from tests.test_random_exprs import evaluate_case
+    cases = []
+    for i, seed in enumerate(_random_seeds()):
+        n, metric, slots, inputs, want, ast, _, _ = evaluate_case(seed)
+        cases.append((ast, [bc for _, bc in slots], L.ARITH_STRICT, np.float64))
+        if i < 24:
+            cases.append((ast, [bc for _, bc in slots], L.ARITH_STRICT, np.float32))
+    prefetch_many(cases)
+
+
+@pytest.fixture(scope="module")
+def fuzz_kernels_compiled():
+    from tests.test_gpu_lowering_fuzz import _inputs, build
+    cases = []
+    for seed in _fuzz_seeds():
+        n, metric, kinds, tree, host, bcs = _inputs(seed)
+        ast = build(tree, [pmv(Input(s, grades)) for s, (grades, _) in enumerate(kinds)]).specialize(metric)
+        cases.append((ast, bcs, L.ARITH_FMA, np.float64))
+    prefetch_many(cases)
+
+
 @pytest.mark.parametrize("seed", _random_seeds())
-def test_random_expression_kernels(seed):
+def test_random_expression_kernels(seed, random_kernels_compiled):
     """Random algebra (incl. degenerate and non-unit metrics), random grade sets, random operator trees: the
     strict-arithmetic kernel equals the oracle bit for bit."""
     from tests.test_random_exprs import BATCH, evaluate_case
@@ -275,7 +317,7 @@ def _fuzz_seeds():
 
 
 @pytest.mark.parametrize("seed", _fuzz_seeds())
-def test_sandwich_rich_random_expression_kernels(seed):
+def test_sandwich_rich_random_expression_kernels(seed, fuzz_kernels_compiled):
     """Random trees rich in vector sandwiches and shared operands: whatever the lowering passes decide, the FMA kernel
     agrees with the oracle (1e-9 of the scale: 1/(v.v) in a mixed signature, see tests/test_gpu_lowering_fuzz.py)."""
     from tests.test_gpu_lowering_fuzz import BATCH, _inputs, build
@@ -302,6 +344,7 @@ def test_f32_kernels(name):
     ast = W.specialize(w)
     with np.errstate(all="ignore"):
         want32 = run_plan_numpy(ast.plan_dict(), host, batch, dtype=np.float32)
+    prefetch(ast, bcs, [(L.ARITH_STRICT, False, True, np.float32), (L.ARITH_FMA, False, True, np.float32)])
     out, _, info = run_generated_kernel(ast, host, bcs, batch, arith=L.ARITH_STRICT, dtype=np.float32)
     assert_bit_exact(out, want32, f"{name} f32 strict [{info['notes']}]")
     out, _, info = run_generated_kernel(ast, host, bcs, batch, arith=L.ARITH_FMA, dtype=np.float32)
@@ -329,7 +372,7 @@ def test_sums_only_kernels(name):
 
 
 @pytest.mark.parametrize("seed", _random_seeds()[:24])
-def test_random_expression_kernels_f32(seed):
+def test_random_expression_kernels_f32(seed, random_kernels_compiled):
     from tests.helpers import run_plan_numpy
     from tests.test_random_exprs import BATCH, evaluate_case
     n, metric, slots, inputs, want, ast, oracle_error, mine_error = evaluate_case(seed)
