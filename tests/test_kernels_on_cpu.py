@@ -462,3 +462,34 @@ def test_the_harness_sees_a_wrong_kernel():
         K._cache.clear()
     assert "d_fma(d_neg(v6), v13, v23)" in info["source"], "cfg1's kernel changed: pick another statement to break"
     assert np.abs(out[2] - want[2]).max() > 1e-3
+
+
+# ---- Exponential / Logarithm (this library's own definition; the reference has todo!() there) -------------------
+def _explog_cases():
+    from tests.test_explog import SHAPES
+    return sorted(SHAPES)
+
+
+@pytest.mark.parametrize("shape", _explog_cases())
+@pytest.mark.parametrize("metric", [[1.0] * 3, [1.0, 1.0, -1.0]], ids=["G(3,0)", "G(2,1)"])
+def test_exp_log_kernels(shape, metric):
+    """Both engines' device code against the numpy statement of the definition (oracle/explog_extension.py), at the bar
+    of tests/test_gpu_explog.py: cos / sin / atan2 come from another math library here (the host's instead of CUDA's),
+    so even strict arithmetic is held to 1e-12 of max(|result|, 1)."""
+    from tests.kernel_emu.table_engine import run_table_engine
+    from tests.test_explog import SHAPES, _inputs, _oracle
+    build, first, second = SHAPES[shape]
+    n, batch = len(metric), 130
+    host = _inputs(np.random.default_rng(8), n, first, second, batch)
+    want = _oracle(build, metric, host, batch)
+    ast = build(pmv(Input(0, first)), pmv(Input(1, second))).specialize(metric)
+    prefetch(ast, [False, False], [(L.ARITH_FMA, False, True, np.float64), (L.ARITH_STRICT, False, True, np.float64)])
+    results = {}
+    for arith in (L.ARITH_STRICT, L.ARITH_FMA):
+        results[f"specialised {arith}"] = run_generated_kernel(ast, host, [False, False], batch, arith=arith)[0]
+        results[f"table {arith}"] = run_table_engine(ast, host, [False, False], batch, strict=arith == L.ARITH_STRICT)[0]
+    for what, out in results.items():
+        assert sorted(out) == sorted(want)
+        for k in want:
+            tol = 1e-12 * np.maximum(np.abs(want[k]), 1.0)
+            assert np.all(np.abs(out[k] - want[k]) <= tol), (shape, what, k, np.abs(out[k] - want[k]).max())
