@@ -133,3 +133,19 @@ def run_table_engine(ast, inputs: Sequence[Dict[int, np.ndarray]], broadcast: Se
             sums[k] = tot[c:c + comb(n, k)].copy()
             c += comb(n, k)
     return out, sums
+
+
+def reduce_partials(partials: np.ndarray) -> np.ndarray:
+    """The library's deterministic reduction of per-block partial sums ([n_blocks][n_cols]) -- one level, or two beyond
+    2 048 rows (the cfg5 batch-sum runs ~19 000 blocks) -- through its own kernels."""
+    lib = _library()
+    src = open(os.path.join(CSRC, "runtime.hpp")).read()
+    g1 = int(re.search(r"constexpr int kReduceStage1Rows = (\d+);", src).group(1))
+    n_blocks, n_cols = partials.shape
+    buf = np.full((n_blocks + g1, n_cols), np.nan)
+    buf[:n_blocks] = partials
+    out = np.full(n_cols, np.nan)
+    lib.emu_reduce_partials.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.emu_reduce_partials.restype = C.c_int
+    levels = lib.emu_reduce_partials(buf.ctypes.data, n_blocks, n_cols, g1, out.ctypes.data)
+    return out, levels

@@ -118,3 +118,19 @@ def test_random_expressions(seed):
         want32 = run_plan_numpy(ast.plan_dict(), in32, BATCH, dtype=np.float32)
         out32, _ = run_table_engine(ast, in32, bcs, BATCH, strict=True, dtype=np.float32)
         assert_bit_exact(out32, want32, f"seed {seed} f32")
+
+
+@pytest.mark.parametrize("n_blocks,n_cols,levels", [(7, 3, 1), (2049, 66, 2), (18944, 66, 2), (5000, 1, 2), (3000, 300, 1)])
+def test_partial_sum_reduction(n_blocks, n_cols, levels):
+    """Per-block partials -> the batch-sum: the one-level kernel, and the two-level one the cfg5 batch-sum takes
+    (18 944 blocks of 66 columns on a B200).  Deterministic, and equal to the plain sum within the rounding of a
+    different summation order."""
+    from tests.kernel_emu.table_engine import reduce_partials
+    rng = np.random.default_rng(n_blocks + n_cols)
+    partials = rng.uniform(-1, 1, (n_blocks, n_cols))
+    out, took = reduce_partials(partials)
+    assert took == levels
+    ref = partials.sum(axis=0)
+    assert np.all(np.abs(out - ref) <= 1e-13 * np.abs(partials).sum(axis=0))
+    again, _ = reduce_partials(partials)
+    assert np.array_equal(out, again)
