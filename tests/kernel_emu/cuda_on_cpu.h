@@ -25,6 +25,7 @@
 #include <vector>
 
 #define __device__
+#define __host__
 #define __global__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
@@ -99,7 +100,7 @@ static inline double __longlong_as_double(long long x) {
 // ---- block-wide state ------------------------------------------------------------------------
 constexpr int kEmuMaxThreads = 1024;
 constexpr size_t kEmuSmemBytes = 256 * 1024;
-alignas(1024) double sums[kEmuSmemBytes / 8];  // `extern __shared__ double sums[];` of the generated kernels
+__attribute__((weak)) alignas(1024) double sums[kEmuSmemBytes / 8];  // `extern __shared__ double sums[];` of the generated kernels
 static pthread_barrier_t emu_block_bar;
 static thread_local pthread_barrier_t* emu_block_bar_p = &emu_block_bar;  // (the peer all-reduce test runs one block per rank AT ONCE)
 static pthread_barrier_t emu_warp_bar[kEmuMaxThreads / 32];
@@ -113,6 +114,13 @@ static inline void __syncthreads() {
         return;
     }
     pthread_barrier_wait(emu_block_bar_p);
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+    if (!emu_threaded) {
+        emu_fault = 1;
+        return;
+    }
+    pthread_barrier_wait(&emu_warp_bar[threadIdx.x >> 5]);
 }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline double __shfl_xor_sync(unsigned, double v, int d) {
