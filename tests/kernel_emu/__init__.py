@@ -16,6 +16,7 @@ import os
 import re
 import subprocess
 import tempfile
+import threading
 from math import comb
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -95,6 +96,13 @@ def host_source(cuda_src: str) -> str:
 FLAGS = ["-std=c++17", "-O0", "-ffp-contract=off", "-mfma", "-fPIC", "-pthread", "-w"]
 _cache: Dict[str, C.CDLL] = {}
 _tmp = None
+_locks: Dict[str, threading.Lock] = {}
+_locks_guard = threading.Lock()
+
+
+def _build_lock(key: str) -> threading.Lock:
+    with _locks_guard:
+        return _locks.setdefault(key, threading.Lock())
 
 
 def _ensure_tmp():
@@ -121,20 +129,26 @@ def _compile(cuda_src: str, f32: bool = False) -> C.CDLL:
     has_uniform = 'void __launch_bounds__(32) gaast_uniform(' in cuda_src
     text = ('#include "cuda_on_cpu.h"\n' + ("#define EMU_HAS_UNIFORM 1\n" if has_uniform else "") + body +
             '\n#include "driver.inc"\n')
-    cpp = os.path.join(_tmp.name, key + ".cpp")
     so = os.path.join(_tmp.name, key + ".so")
-    with open(cpp, "w") as f:
-        f.write(text)
-    # (the f32 variant defines GAAST_EMU_F32: the precompiled header does not apply, g++ reads the header itself)
-    cmd = ["g++", *FLAGS, *(["-DGAAST_EMU_F32"] if f32 else []), "-shared", "-I", _tmp.name, cpp, "-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("g++ rejected the generated kernel:\n" + r.stderr[-3000:])
-    lib = C.CDLL(so)
-    lib.emu_launch.argtypes = [C.POINTER(EmuLaunch)]
-    lib.emu_launch.restype = C.c_int
-    _cache[key] = lib
-    return lib
+    with _build_lock(key):  # (two threads asking for the same text: one build, the other finds the library)
+        if key in _cache:
+            return _cache[key]
+        if not os.path.exists(so):
+            cpp = os.path.join(_tmp.name, key + ".cpp")
+            with open(cpp, "w") as f:
+                f.write(text)
+            # (the f32 variant defines GAAST_EMU_F32: the precompiled header does not apply, g++ reads the header itself)
+            part = so + f".{threading.get_ident()}.part"
+            cmd = ["g++", *FLAGS, *(["-DGAAST_EMU_F32"] if f32 else []), "-shared", "-I", _tmp.name, cpp, "-o", part]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("g++ rejected the generated kernel:\n" + r.stderr[-3000:])
+            os.replace(part, so)
+        lib = C.CDLL(so)
+        lib.emu_launch.argtypes = [C.POINTER(EmuLaunch)]
+        lib.emu_launch.restype = C.c_int
+        _cache[key] = lib
+        return lib
 
 
 def prefetch(ast, broadcast, variants, tuning=None):
@@ -151,6 +165,7 @@ def prefetch(ast, broadcast, variants, tuning=None):
         jobs.append((plan.kernel_source(broadcast_slots=bmask, arith=arith, with_sum=with_sum, store_out=store_out,
                                         dtype=L.F32 if f32 else L.F64), f32))
     _ensure_tmp()  # (the precompiled header first)
+    jobs = list(dict.fromkeys(jobs))  # (two variants may print the same text: one build each)
     with ThreadPoolExecutor(max_workers=4) as ex:
         list(ex.map(lambda j: _compile(*j), jobs))
 
@@ -174,6 +189,7 @@ def prefetch_many(cases, workers: int = 6):
         except L.GaastError:
             pass
     _ensure_tmp()
+    jobs = list(dict.fromkeys(jobs))  # (two tuning variants may print the same text: one build each)
     with ThreadPoolExecutor(max_workers=workers) as ex:
         list(ex.map(lambda j: _compile(*j), jobs))
 
