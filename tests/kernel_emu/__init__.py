@@ -94,6 +94,12 @@ def host_source(cuda_src: str) -> str:
 # not matter); -ffp-contract=off: the compiler never fuses a*b+c on its own (strict arithmetic is two roundings; an FMA
 # is spelled fma() in the source and is correctly rounded whether it becomes an instruction or a libm call)
 FLAGS = ["-std=c++17", "-O0", "-ffp-contract=off", "-mfma", "-fPIC", "-pthread", "-w"]
+# GAAST_EMU_ASAN=1 (with LD_PRELOAD=libasan.so libstdc++.so.6): the kernels run under AddressSanitizer on batches whose
+# rows are padded exactly as the library pads them (128 bytes) -- an access outside a batch or outside shared memory
+# aborts the run
+ASAN = os.environ.get("GAAST_EMU_ASAN") == "1"
+if ASAN:
+    FLAGS += ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"]
 _cache: Dict[str, C.CDLL] = {}
 _tmp = None
 _locks: Dict[str, threading.Lock] = {}
@@ -225,7 +231,9 @@ def run_generated_kernel(ast, inputs: Sequence[Dict[int, np.ndarray]], broadcast
     lib = _compile(src, f32)
     threads, ept = lib.emu_threads(), lib.emu_elems_per_thread()
     per_block = threads * ept
-    padded = (batch + per_block - 1) // per_block * per_block  # rows padded as the runtime pads an odd batch
+    padded = (batch + per_block - 1) // per_block * per_block  # (generous: a whole block's worth)
+    if ASAN:
+        padded = (batch + 15) // 16 * 16  # rows on 128-byte boundaries: gaast_batch_alloc's layout, nothing more
     launch = EmuLaunch()
     keep = []
     si = 0

@@ -35,8 +35,10 @@ static inline double ld_volatile_f64(const double* p) {
     return v;
 }
 static int emu_slow_rank = -1;  // this rank dawdles between seeing everybody's flag and adding the slots up
+static int emu_slow_ms = 4;
+extern "C" void emu_set_slow_ms(int ms) { emu_slow_ms = ms; }
 static inline void emu_before_sum(int rank) {
-    if (rank == emu_slow_rank) std::this_thread::sleep_for(std::chrono::milliseconds(4));
+    if (rank == emu_slow_rank) std::this_thread::sleep_for(std::chrono::milliseconds(emu_slow_ms));
 }
 static inline unsigned long long emu_globaltimer() {
     timespec ts;
@@ -95,8 +97,10 @@ def library(text: str = None) -> C.CDLL:
 
 
 def run_peer_allreduce(n_ranks: int, count: int, epochs: int, threads: int = 64, skew_rank: int = -1,
-                       timeout_s: float = 20.0, text: str = None) -> int:
+                       timeout_s: float = 20.0, text: str = None, slow_ms: int = 4) -> int:
     """Number of (rank, epoch, component) results that differ from the rank-ordered sum (0 = correct).
     `skew_rank` is slow: it starts every third epoch late and dawdles before every summation.  `text` replaces the
     kernel text (a deliberately broken protocol, to show that the harness sees it)."""
-    return library(text).emu_peer_run(n_ranks, count, epochs, threads, skew_rank, int(timeout_s * 1e9), None)
+    lib = library(text)
+    lib.emu_set_slow_ms(slow_ms)
+    return lib.emu_peer_run(n_ranks, count, epochs, threads, skew_rank, int(timeout_s * 1e9), None)

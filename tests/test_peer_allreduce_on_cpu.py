@@ -31,8 +31,10 @@ def test_a_single_buffer_is_caught():
     text = P.kernel_text()
     broken = text.replace("const int buf = int(epoch & 1ull);", "const int buf = 0;")
     assert broken != text, "comm.cu picks its buffer differently now: break the protocol another way"
-    assert any(P.run_peer_allreduce(2, 66, 30, 64, 1, text=broken) > 0 for _ in range(4))
-    assert P.run_peer_allreduce(2, 66, 30, 64, 1) == 0
+    # the slow rank waits 50 ms before it adds the slots up: far longer than the fast rank needs to launch its next epoch
+    # (64 OS threads), on a loaded box too
+    assert any(P.run_peer_allreduce(2, 66, 8, 64, 1, text=broken, slow_ms=50) > 0 for _ in range(3))
+    assert P.run_peer_allreduce(2, 66, 8, 64, 1, slow_ms=50) == 0
 
 
 def test_a_missing_peer_times_out_with_nan_instead_of_hanging():
