@@ -41,7 +41,7 @@ def _run_all_kinds(build, metric, slots, batch, seed, what, expect, bcs=None):
 @pytest.mark.parametrize("metric,batch", [
     ([1.0] * 7, 1), ([1.0] * 5 + [-1.0] * 2, 33), ([1.0] * 4 + [-1.0] * 3, 40),   # M(C), two blocks
     ([1.0] * 8, 5), ([-1.0, 1.0] * 4, 37), ([1.0] * 6 + [-1.0], 21),               # M(R), narrow column blocks
-    ([1.0] * 8 + [-1.0], 4)])  # (n = 10 runs the same code with J = 32; the numpy oracle takes a minute there)
+    ([1.0] * 8 + [-1.0], 2)])  # (n = 10 runs the same code with J = 32; the numpy oracle takes a minute there)
 def test_full_geometric_product(metric, batch):
     """A*B on full multivectors, every type of algebra the matrix kernel distinguishes, ragged tiles."""
     n = len(metric)
