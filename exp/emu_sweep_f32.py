@@ -3,7 +3,7 @@ the batch-sum, through the generated kernels on the CPU (tests/kernel_emu): FMA 
 arithmetic bit for bit against the binary32 replay.    python exp/emu_sweep_f32.py"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gaast_b200 import _lib as L, workloads as W
 from tests.helpers import assert_bit_exact, assert_close, oracle_abs_scale, oracle_eval, run_plan_numpy
 from tests.kernel_emu import run_generated_kernel
