@@ -28,7 +28,6 @@ def library(src: str = None) -> C.CDLL:
     src = src or pipeline_source()
     if src in _libs:
         return _libs[src]
-    os.environ.setdefault("GAAST_HOST_CHUNK_MIB", "1")  # small chunks: a test batch goes through the sets several times
     if _tmp is None:
         _tmp = tempfile.TemporaryDirectory(prefix="gaast_pipeline_emu_")
     cpp = os.path.join(_tmp.name, f"pipeline_emu_{len(_libs)}.cpp")
@@ -45,5 +44,16 @@ def library(src: str = None) -> C.CDLL:
         raise RuntimeError("g++ rejected host_pipeline.cu:\n" + r.stderr[-4000:])
     lib = C.CDLL(so)
     lib.emu_pipeline_run.restype = C.c_int
+    # small chunks, so that a test batch goes through the buffer sets several times: this copy of the library reads its
+    # tuning environment now, and the process environment is put back (the real library must not see the setting)
+    before = os.environ.get("GAAST_HOST_CHUNK_MIB")
+    os.environ["GAAST_HOST_CHUNK_MIB"] = "1"
+    try:
+        assert lib.emu_pipeline_read_env() == 1
+    finally:
+        if before is None:
+            del os.environ["GAAST_HOST_CHUNK_MIB"]
+        else:
+            os.environ["GAAST_HOST_CHUNK_MIB"] = before
     _libs[src] = lib
     return lib
