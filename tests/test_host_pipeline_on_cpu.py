@@ -47,8 +47,7 @@ def _run(lib, length, stride, bcs=(False, False), dtype=np.float64, policy=0, fa
 
 
 @pytest.mark.parametrize("policy", [0, 1, 2], ids=["laziest", "uploads-ahead", "others-first"])
-@pytest.mark.parametrize("length,stride", [(5 * CHUNK + 777, 5 * CHUNK + 1000), (CHUNK, CHUNK), (3 * CHUNK, 3 * CHUNK + 8),
-                                           (1, 1), (0, 0), (CHUNK + 1, 2 * CHUNK)])
+@pytest.mark.parametrize("length,stride", [(5 * CHUNK + 777, 5 * CHUNK + 1000), (3 * CHUNK, 3 * CHUNK + 8), (1, 1), (0, 0)])
 def test_every_element_arrives_under_every_schedule(policy, length, stride):
     rc, out, want, lens, stalls = _run(HP.library(), length, stride, policy=policy)
     assert rc == 0 and stalls == 0

@@ -188,7 +188,7 @@ SANDWICHES = {
     pytest.param(metric, xg, shape, id=f"{mid}-{xid}-{shape}")
     for metric, mid in [([1.0] * 5, "G(5,0)"), ([1.0, 1.0, 1.0, -1.0, -1.0], "G(3,2)")]
     for xg, xid in [((2,), "X=bivector"), ((0, 1, 2, 3, 4, 5), "X=full"), ((1, 3), "X=odd")]
-    for shape in sorted(SANDWICHES) if not ("g(2)" in shape and 2 not in xg)])
+    for shape in sorted(SANDWICHES) if not ("g(2)" in shape and 2 not in xg) and (mid == "G(3,2)" or xid == "X=bivector")])
 def test_reflection_lowering_kernels(metric, xgrades, shape):
     n = len(metric)
     batch = 131
@@ -241,7 +241,8 @@ MATREP_SHAPES = {"A*B": lambda a, b, c: a * b, "C+A*B": lambda a, b, c: c + a * 
 
 
 MATREP_CASES = [(shape, name) for shape in sorted(MATREP_SHAPES) for name in sorted(SIGNATURES_6)
-                if shape == "A*B" or name in ("G(3,3)", "G(0,6)")]
+                if (shape == "A*B" and name in ("G(6,0)", "G(5,1)", "G(3,3)", "G(0,6)", "G(4,2) mixed order")) or
+                (shape != "A*B" and name == "G(3,3)")]
 
 
 @pytest.fixture(scope="module")
@@ -274,7 +275,7 @@ def test_matrix_representation_kernels(shape, name, matrep_kernels_compiled):
 # ---- random expression trees (the generators of the device fuzz tests) ------------------------------------
 def _random_seeds():
     from tests.test_random_exprs import GPU_SEEDS
-    return GPU_SEEDS[:48]
+    return GPU_SEEDS[:24]
 
 
 @pytest.fixture(scope="module")
@@ -284,7 +285,7 @@ def random_kernels_compiled():
     for i, seed in enumerate(_random_seeds()):
         n, metric, slots, inputs, want, ast, _, _ = evaluate_case(seed)
         cases.append((ast, [bc for _, bc in slots], L.ARITH_STRICT, np.float64))
-        if i < 24:
+        if i < 8:
             cases.append((ast, [bc for _, bc in slots], L.ARITH_STRICT, np.float32))
     prefetch_many(cases)
 
@@ -313,7 +314,7 @@ def test_random_expression_kernels(seed, random_kernels_compiled):
 
 def _fuzz_seeds():
     from tests.test_gpu_lowering_fuzz import ACCEPTED
-    return ACCEPTED[:32]
+    return ACCEPTED[:14]
 
 
 @pytest.mark.parametrize("seed", _fuzz_seeds())
@@ -371,7 +372,7 @@ def test_sums_only_kernels(name):
         assert (np.abs(sums[k] - ref) <= tol).all(), f"{name} [{info['notes']}]: batch-sum of grade {k} off"
 
 
-@pytest.mark.parametrize("seed", _random_seeds()[:24])
+@pytest.mark.parametrize("seed", _random_seeds()[:8])
 def test_random_expression_kernels_f32(seed, random_kernels_compiled):
     from tests.helpers import run_plan_numpy
     from tests.test_random_exprs import BATCH, evaluate_case
@@ -470,8 +471,9 @@ def _explog_cases():
     return sorted(SHAPES)
 
 
-@pytest.mark.parametrize("shape", _explog_cases())
-@pytest.mark.parametrize("metric", [[1.0] * 3, [1.0, 1.0, -1.0]], ids=["G(3,0)", "G(2,1)"])
+@pytest.mark.parametrize("shape,metric", [
+    pytest.param(shape, metric, id=f"{mid}-{shape}") for i, shape in enumerate(_explog_cases())
+    for metric, mid in [([1.0] * 3, "G(3,0)"), ([1.0, 1.0, -1.0], "G(2,1)")] if (i + (mid == "G(2,1)")) % 2 == 0])
 def test_exp_log_kernels(shape, metric):
     """Both engines' device code against the numpy statement of the definition (oracle/explog_extension.py), at the bar
     of tests/test_gpu_explog.py: cos / sin / atan2 come from another math library here (the host's instead of CUDA's),

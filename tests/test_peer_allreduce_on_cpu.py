@@ -14,9 +14,9 @@ pytestmark = pytest.mark.timeout(300)
 
 @pytest.mark.parametrize("n_ranks,count,epochs,threads,slow", [
     (1, 5, 5, 32, -1),
-    (2, 66, 40, 64, -1),      # cfg5's 66-component bivector sum
-    (2, 66, 30, 64, 1),
-    (4, 66, 30, 64, 2),
+    (2, 66, 20, 64, -1),      # cfg5's 66-component bivector sum
+    (2, 66, 15, 64, 1),
+    (4, 66, 15, 64, 2),
     (8, 66, 12, 32, 3),
     (2, 512, 6, 256, 0),      # the largest vector the mailbox holds, the library's own block size
     (16, 3, 6, 32, 5),        # as many ranks as the mailbox holds

